@@ -1,0 +1,197 @@
+/*
+ * pnp_b200.h - C ABI of libpnp_b200.so: the B200 (sm_100a) implementation of the
+ * mujoco-panda-pnp hot path (Panda position IK + goal-conditioned reward).
+ *
+ * Drop-in boundary.  The reference has no native FFI: its hot path is Python calling
+ * MuJoCo / NumPy.  Each entry point below replaces one reference interface:
+ *
+ *   pnp_set_tree           model data read by JacobianIKController.__init__
+ *                          (panda_mujoco_gym/skills/ik_solver.py:27-33) and by MuJoCo inside
+ *                          mj_kinematics / mj_jacSite (ik_solver.py:58,72)
+ *   pnp_fk_jac_*           mujoco.mj_kinematics + mujoco.mj_jacSite + mju_mat2Quat for the EE
+ *                          site (ik_solver.py:58-59,70-72; envs/panda_env.py:337-346)
+ *   pnp_ik_solve_*         JacobianIKController.solve (ik_solver.py:35-101), batched
+ *   pnp_ik_waypoints_*     the warm-started solve sequence of MoveIKSkill.reset
+ *                          (skills/move.py:106-137), fixed number of waypoints per env
+ *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
+ *                          (envs/panda_env.py:205-245, 303-306, 311-315), row-wise
+ *   pnp_*_host             the same operators taking HOST buffers (what a Python/ctypes
+ *                          caller of the reference API holds): chunked H2D -> kernel -> D2H
+ *                          pipeline on library-owned streams
+ *
+ * Conventions
+ *   - Plain C types only.  "_dev" style entry points (no suffix) take DEVICE pointers and a
+ *     cudaStream_t passed as void*; they never allocate, never synchronise and never throw.
+ *   - Every function returns 0 on success or a negative PNP_E* code / positive cudaError_t.
+ *     pnp_last_error() returns a thread-local message for the last failure.
+ *   - Outputs are overwritten.  `counters` (nullable) is ACCUMULATED with atomics; the caller
+ *     zeroes it.  Any output pointer documented "nullable" may be NULL to skip that store.
+ *   - _f32 kernels compute in FP32 registers (the product path); _f64 kernels run the same
+ *     algorithm in FP64 (used to separate algorithmic parity from FP32 rounding).
+ *   - Arm joints are qpos[0:7] (ik_solver.py:31-33,51).  Quaternions are wxyz (MuJoCo).
+ */
+#ifndef PNP_B200_H_
+#define PNP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNP_ABI_VERSION 1
+#define PNP_NJOINT 7
+
+/* error codes (negative; positive values are cudaError_t) */
+#define PNP_OK 0
+#define PNP_EINVAL (-1)      /* bad argument (null pointer, negative size, bad enum) */
+#define PNP_ENOTREE (-2)     /* pnp_set_tree has not been called on this device */
+#define PNP_ENODEVICE (-3)   /* no CUDA device / wrong architecture (needs sm_100) */
+#define PNP_ENOMEM (-4)      /* host-API scratch allocation failed */
+
+/* Canonical 7-hinge chain (FP64, host memory).  See mujoco_panda_pnp_b200/tree.py:
+ *   frame_0 = I;  A_i = frame_i * Fixed(link_pos[i], link_rot[i]);
+ *   frame_{i+1} = A_i * Rz(q_i - qref[i]);  site = frame_7 * Fixed(ee_pos, ee_rot)
+ * Rotations are row-major 3x3.  lower/upper = model.jnt_range[:7] (ik_solver.py:32-33). */
+typedef struct PnpTree {
+  int32_t njoint;   /* must be PNP_NJOINT */
+  int32_t reserved;
+  double link_pos[PNP_NJOINT * 3];
+  double link_rot[PNP_NJOINT * 9];
+  double ee_pos[3];
+  double ee_rot[9];
+  double lower[PNP_NJOINT];
+  double upper[PNP_NJOINT];
+  double qref[PNP_NJOINT];
+} PnpTree;
+
+/* JacobianIKController.solve keyword arguments (ik_solver.py:35-37), same defaults upstream */
+typedef struct PnpIkParams {
+  int32_t max_iters;   /* 100  */
+  int32_t kinematics;  /* PNP_KIN_AUTO / _GENERIC / _SPECIALIZED */
+  double pos_thresh;   /* 1e-3 */
+  double damping;      /* 1e-2, added un-squared: J J^T + damping * I (ik_solver.py:79) */
+  double step_limit;   /* 0.1  */
+} PnpIkParams;
+
+#define PNP_KIN_AUTO 0         /* specialised code when the uploaded tree matches it, else generic */
+#define PNP_KIN_GENERIC 1      /* always read the tree from __constant__ memory */
+#define PNP_KIN_SPECIALIZED 2  /* require the build-time specialised tree (error if mismatch) */
+
+/* flags[] bits written by the IK kernels (IKResult.converged / .success, ik_solver.py:92-100) */
+#define PNP_IK_CONVERGED 1u
+#define PNP_IK_SUCCESS 2u
+
+/* counters[] layout for the IK kernels: the 4 values reduced across GPUs */
+#define PNP_IK_CNT_N 0
+#define PNP_IK_CNT_CONVERGED 1
+#define PNP_IK_CNT_SUCCESS 2
+#define PNP_IK_CNT_ITERATIONS 3
+
+/* env scalars read by compute_reward (panda_env.py:205-245; shelf_pnp.py:17-26) */
+typedef struct PnpRewardParams {
+  int32_t sparse;                /* reward_type == "sparse" */
+  int32_t n_tasks;               /* len(task_sequence) */
+  double initial_object_height;  /* panda_env.py:139-141 */
+  double distance_threshold;     /* 0.05 */
+  double high_pick_z;            /* 0.35 */
+  double threshold_report_tol;   /* rows with |d - threshold| < tol are counted (1e-6) */
+} PnpRewardParams;
+
+/* counters[] layout for the reward kernels */
+#define PNP_RW_CNT_N 0
+#define PNP_RW_CNT_PLACED 1
+#define PNP_RW_CNT_GRIPPED 2
+#define PNP_RW_CNT_THRESHOLD_ADJACENT 3
+
+/* ---- library / device ------------------------------------------------------------------ */
+int pnp_abi_version(void);
+const char* pnp_last_error(void);
+/* sm count, clock (kHz), compute capability major*10+minor of the current device */
+int pnp_device_info(int32_t* sm_count, int32_t* clock_khz, int32_t* cc);
+
+/* ---- kinematic tree -------------------------------------------------------------------- */
+/* Upload the chain to __constant__ memory of the current device (FP64 and FP32 copies). */
+int pnp_set_tree(const PnpTree* host_tree);
+int pnp_get_tree(PnpTree* host_tree_out);
+/* 1 when the uploaded tree is bit-identical to the build-time specialised one */
+int pnp_tree_is_specialized(void);
+/* copy of the tree the specialised kernels were generated for */
+int pnp_get_specialized_tree(PnpTree* host_tree_out);
+
+/* ---- FK + 6x7 geometric Jacobian (mj_kinematics + mj_jacSite + mju_mat2Quat) ------------- */
+/* q[n,7] -> pos[n,3], quat[n,4] (wxyz, nullable), jac[n,6,7] row-major rows 0-2 jacp, 3-5 jacr
+ * (nullable).  kinematics: PNP_KIN_*. */
+int pnp_fk_jac_f32(const float* q, int64_t n, float* pos, float* quat, float* jac, int32_t kinematics, void* stream);
+int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double* jac, int32_t kinematics, void* stream);
+
+/* ---- batched JacobianIKController.solve ------------------------------------------------- */
+/* targets[n,3]; q_init[n,7] when q_init_stride == 7 or one broadcast [7] when 0.
+ * Outputs: q_out[n,7], final_pos[n,3] (nullable), pos_err[n] (nullable), iters[n] int32
+ * (nullable), flags[n] uint8 (nullable), counters[4] uint64 (nullable, accumulated). */
+int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                     const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err,
+                     int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
+int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
+                     const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err,
+                     int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
+
+/* ---- warm-started waypoint sequences (MoveIKSkill.reset inner loop, move.py:106-137) ----- */
+/* Per env: start joints q_start[n,7], goal[n,3].  n_steps times: pos = FK(q); dist = |goal-pos|;
+ * step = min(step_size, 0.1*dist, 0.02); next = pos + dir*step/dist (or goal when dist<=step);
+ * solve(next, q) with `params`; accept iff success and pos_err < 2*step_size (move.py:131).
+ * q is carried in registers across the n_steps solves (one launch).  Outputs: q_out[n,7],
+ * pos_out[n,3] final EE position, n_accepted[n] int32 (nullable), iters_total[n] int32
+ * (nullable), counters[4] (nullable; N counts solves = n*n_steps). */
+int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int32_t n_steps,
+                         double step_size, const PnpIkParams* params, float* q_out, float* pos_out,
+                         int32_t* n_accepted, int32_t* iters_total, unsigned long long* counters,
+                         void* stream);
+
+/* ---- compute_reward / _is_success, row-wise --------------------------------------------- */
+/* Per row: achieved_goal[n,3], desired_goal[n,3], ee_pos[n,3], ee_quat[n,4] wxyz,
+ * fingers_width[n], task_index[n] int32.  Math is FP64 in the reference's operation order
+ * without FMA contraction, one final round-to-nearest cast to float (bit-exact).
+ * reward[n] float; is_success[n] float (nullable); counters[4] (nullable). */
+int pnp_reward_f32(const float* ag, const float* dg, const float* ee_pos, const float* ee_quat,
+                   const float* width, const int32_t* task_index, int64_t n,
+                   const PnpRewardParams* params, float* reward, float* is_success,
+                   unsigned long long* counters, void* stream);
+int pnp_reward_f64(const double* ag, const double* dg, const double* ee_pos, const double* ee_quat,
+                   const double* width, const int32_t* task_index, int64_t n,
+                   const PnpRewardParams* params, float* reward, float* is_success,
+                   unsigned long long* counters, void* stream);
+/* goal_distance (panda_env.py:311-315): a[n,3], b[n,3] -> d[n] (FP64 math) */
+int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream);
+
+/* ---- host-buffer operators (end-to-end path: copies inside) ----------------------------- */
+typedef struct PnpHostCtx PnpHostCtx;
+/* chunk_rows: rows per pipeline stage (0 = default).  Allocates device scratch + 3 streams. */
+int pnp_host_ctx_create(PnpHostCtx** out, int64_t chunk_rows);
+int pnp_host_ctx_destroy(PnpHostCtx* ctx);
+/* Same arguments as pnp_ik_solve_f32 but every pointer is HOST memory (pinned for full
+ * overlap; pageable works).  counters[4] is host memory, overwritten.  Blocks until done. */
+int pnp_ik_solve_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_init,
+                          int32_t q_init_stride, int64_t n, const PnpIkParams* params, float* q_out,
+                          float* final_pos, float* pos_err, int32_t* iters, uint8_t* flags,
+                          unsigned long long* counters);
+int pnp_reward_host_f32(PnpHostCtx* ctx, const float* ag, const float* dg, const float* ee_pos,
+                        const float* ee_quat, const float* width, const int32_t* task_index,
+                        int64_t n, const PnpRewardParams* params, float* reward, float* is_success,
+                        unsigned long long* counters);
+int pnp_reward_host_f64(PnpHostCtx* ctx, const double* ag, const double* dg, const double* ee_pos,
+                        const double* ee_quat, const double* width, const int32_t* task_index,
+                        int64_t n, const PnpRewardParams* params, float* reward, float* is_success,
+                        unsigned long long* counters);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* FFMA throughput microbenchmark on the current device: the FP32 roofline denominator
+ * (MEASURED_PEAKS.json has none).  Returns TFLOP/s (FMA = 2) and the elapsed ms. */
+int pnp_probe_fp32_peak(double* tflops_out, double* ms_out);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long pnp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_B200_H_ */

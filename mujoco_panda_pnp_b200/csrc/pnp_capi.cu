@@ -1,0 +1,428 @@
+// C ABI of libpnp_b200.so (declared in include/pnp_b200.h).  Host-side glue only: argument
+// checks, constant-memory upload, launch geometry, the host-buffer pipeline.
+#include <atomic>
+#include <cstdarg>
+#include <new>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "pnp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+struct DeviceState {
+  bool have_tree = false;
+  bool specialized = false;
+  PnpTree tree{};
+  int sm_count = 0;
+  unsigned long long* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
+  unsigned ticket_seq = 0;
+  int occ_ik[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+constexpr int kMaxDevices = 16;
+constexpr int kTicketSlots = 64;
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+
+#define CUDA_TRY(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
+  } while (0)
+
+int current_state(DeviceState** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDevices) return fail(PNP_ENODEVICE, "device index %d out of range", dev);
+  DeviceState* s = &g_dev[dev];
+  if (s->sm_count == 0) {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+      return fail(PNP_ENODEVICE, "libpnp_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major,
+                  prop.minor);
+    s->sm_count = prop.multiProcessorCount;
+  }
+  *out = s;
+  return PNP_OK;
+}
+
+bool tree_matches_spec(const PnpTree& t) {
+  return t.njoint == PNP_NJOINT && !memcmp(t.link_pos, pnp_spec::kLinkPos, sizeof t.link_pos) &&
+         !memcmp(t.link_rot, pnp_spec::kLinkRot, sizeof t.link_rot) &&
+         !memcmp(t.ee_pos, pnp_spec::kEePos, sizeof t.ee_pos) &&
+         !memcmp(t.ee_rot, pnp_spec::kEeRot, sizeof t.ee_rot) &&
+         !memcmp(t.lower, pnp_spec::kLower, sizeof t.lower) && !memcmp(t.upper, pnp_spec::kUpper, sizeof t.upper) &&
+         !memcmp(t.qref, pnp_spec::kQref, sizeof t.qref);
+}
+
+template <typename T>
+void fill_tree_dev(const PnpTree& t, pnp::TreeDev<T>* d) {
+  for (int i = 0; i < 21; ++i) d->link_pos[i] = (T)t.link_pos[i];
+  for (int i = 0; i < 63; ++i) d->link_rot[i] = (T)t.link_rot[i];
+  for (int i = 0; i < 3; ++i) d->ee_pos[i] = (T)t.ee_pos[i];
+  for (int i = 0; i < 9; ++i) d->ee_rot[i] = (T)t.ee_rot[i];
+  for (int i = 0; i < 7; ++i) {
+    d->lower[i] = (T)t.lower[i];
+    d->upper[i] = (T)t.upper[i];
+    d->qref[i] = (T)t.qref[i];
+  }
+}
+
+// kinematics selector -> use the specialised instantiation?
+int pick_kin(const DeviceState* s, int kinematics, bool* use_spec) {
+  if (!s->have_tree) return fail(PNP_ENOTREE, "pnp_set_tree has not been called on this device");
+  switch (kinematics) {
+    case PNP_KIN_AUTO: *use_spec = s->specialized; return PNP_OK;
+    case PNP_KIN_GENERIC: *use_spec = false; return PNP_OK;
+    case PNP_KIN_SPECIALIZED:
+      if (!s->specialized) return fail(PNP_EINVAL, "uploaded tree differs from the build-time specialised tree");
+      *use_spec = true;
+      return PNP_OK;
+    default: return fail(PNP_EINVAL, "bad kinematics selector %d", kinematics);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int grid_for(long long work_items, int block, int sm_count, int blocks_per_sm) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)sm_count * blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename T>
+pnp::IkConst<T> make_ik_const(const PnpIkParams* p) {
+  pnp::IkConst<T> k;
+  k.pos_thresh = (T)p->pos_thresh;
+  k.damping = (T)p->damping;
+  k.step_limit = (T)p->step_limit;
+  k.max_iters = p->max_iters;
+  return k;
+}
+
+int check_ik_params(const PnpIkParams* p) {
+  if (!p) return fail(PNP_EINVAL, "params is NULL");
+  if (p->max_iters < 0) return fail(PNP_EINVAL, "max_iters must be >= 0");
+  if (!(p->damping > 0.0)) return fail(PNP_EINVAL, "damping must be > 0 (J J^T + damping I must be SPD)");
+  if (!(p->step_limit >= 0.0)) return fail(PNP_EINVAL, "step_limit must be >= 0");
+  return PNP_OK;
+}
+
+template <typename T>
+int fk_jac_impl(const T* q, int64_t n, T* pos, T* quat, T* jac, int32_t kinematics, void* stream) {
+  if (n < 0 || (n > 0 && (!q || !pos))) return fail(PNP_EINVAL, "fk_jac: null pointer or negative n");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  const int grid = grid_for(n, 128, s->sm_count, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spec)
+    pnp::fk_jac_kernel<T, pnp::SpecKin><<<grid, 128, 0, st>>>(q, n, pos, quat, jac);
+  else
+    pnp::fk_jac_kernel<T, pnp::GenericKin><<<grid, 128, 0, st>>>(q, n, pos, quat, jac);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+template <typename T, typename Kin>
+int ik_occupancy(DeviceState* s, int slot, int block) {
+  if (s->occ_ik[slot] == 0) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_kernel<T, Kin>, block, 0);
+    s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
+  }
+  return s->occ_ik[slot];
+}
+
+template <typename T>
+int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int64_t n, const PnpIkParams* params,
+                  T* q_out, T* final_pos, T* pos_err, int32_t* iters, uint8_t* flags, unsigned long long* counters,
+                  void* stream) {
+  int rc = check_ik_params(params);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!targets || !q_init || !q_out))) return fail(PNP_EINVAL, "ik_solve: null pointer or negative n");
+  if (q_init_stride != 0 && q_init_stride != PNP_NJOINT) return fail(PNP_EINVAL, "q_init_stride must be 0 or 7");
+  DeviceState* s;
+  if ((rc = current_state(&s))) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  unsigned long long* ticket;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
+  }
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+
+  pnp::IkArgs<T> a;
+  a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = n;
+  a.k = make_ik_const<T>(params);
+  a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
+  a.counters = counters; a.ticket = ticket;
+
+  // Persistent grid: every resident lane keeps pulling queries.  Small batches use 32-lane
+  // blocks so the few warps spread over as many SMs as possible (latency bound).
+  const int slot = (sizeof(T) == 8 ? 2 : 0) + (spec ? 1 : 0);
+  const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  int grid;
+  if (spec) {
+    const int occ = ik_occupancy<T, pnp::SpecKin>(s, slot, pnp::IK_BLOCK);
+    grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
+    pnp::ik_solve_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
+  } else {
+    const int occ = ik_occupancy<T, pnp::GenericKin>(s, slot, pnp::IK_BLOCK);
+    grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
+    pnp::ik_solve_kernel<T, pnp::GenericKin><<<grid, block, 0, st>>>(a);
+  }
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+pnp::RewardConst make_reward_const(const PnpRewardParams* p) {
+  pnp::RewardConst k;
+  k.sparse = p->sparse;
+  k.n_tasks = (double)p->n_tasks;
+  k.h0 = p->initial_object_height;
+  k.thr = p->distance_threshold;
+  k.high_z = p->high_pick_z;
+  k.tol = p->threshold_report_tol;
+  return k;
+}
+
+template <typename TIn>
+int reward_impl(const TIn* ag, const TIn* dg, const TIn* ee, const TIn* eq, const TIn* width, const int32_t* task,
+                int64_t n, const PnpRewardParams* params, float* reward, float* success,
+                unsigned long long* counters, void* stream) {
+  if (!params) return fail(PNP_EINVAL, "params is NULL");
+  if (params->n_tasks <= 0) return fail(PNP_EINVAL, "n_tasks must be > 0");
+  if (n < 0 || (n > 0 && (!ag || !dg || !ee || !eq || !width || !task || !reward)))
+    return fail(PNP_EINVAL, "reward: null pointer or negative n");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::RewardArgs<TIn> a;
+  a.ag = ag; a.dg = dg; a.ee = ee; a.eq = eq; a.width = width; a.task = task; a.n = n;
+  a.k = make_reward_const(params);
+  a.reward = reward; a.success = success; a.counters = counters;
+  constexpr int R = pnp::RowsPerLane<TIn>::value;
+  const bool vec = aligned16(ag) && aligned16(dg) && aligned16(ee) && aligned16(eq) && aligned16(width) &&
+                   aligned16(task) && aligned16(reward) && (!success || aligned16(success));
+  const long long groups = (n + R - 1) / R;
+  const int grid = grid_for(groups, 256, s->sm_count, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    pnp::reward_kernel<TIn, true><<<grid, 256, 0, st>>>(a);
+  else
+    pnp::reward_kernel<TIn, false><<<grid, 256, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int pnp_abi_version(void) { return PNP_ABI_VERSION; }
+const char* pnp_last_error(void) { return g_err.c_str(); }
+unsigned long long pnp_launch_count(void) { return g_launches.load(); }
+
+int pnp_device_info(int32_t* sm_count, int32_t* clock_khz, int32_t* cc) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (clock_khz) *clock_khz = prop.clockRate;
+  if (cc) *cc = prop.major * 10 + prop.minor;
+  return PNP_OK;
+}
+
+int pnp_set_tree(const PnpTree* t) {
+  if (!t) return fail(PNP_EINVAL, "tree is NULL");
+  if (t->njoint != PNP_NJOINT) return fail(PNP_EINVAL, "tree.njoint must be %d", PNP_NJOINT);
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  pnp::TreeDev<float> tf;
+  pnp::TreeDev<double> td;
+  fill_tree_dev(*t, &tf);
+  fill_tree_dev(*t, &td);
+  CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f32, &tf, sizeof tf));
+  CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
+  if (!s->tickets) CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned long long)));
+  s->tree = *t;
+  s->have_tree = true;
+  s->specialized = tree_matches_spec(*t);
+  return PNP_OK;
+}
+
+int pnp_get_tree(PnpTree* out) {
+  if (!out) return fail(PNP_EINVAL, "out is NULL");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  if (!s->have_tree) return fail(PNP_ENOTREE, "pnp_set_tree has not been called on this device");
+  *out = s->tree;
+  return PNP_OK;
+}
+
+int pnp_tree_is_specialized(void) {
+  DeviceState* s;
+  if (current_state(&s)) return 0;
+  return s->have_tree && s->specialized ? 1 : 0;
+}
+
+int pnp_get_specialized_tree(PnpTree* out) {
+  if (!out) return fail(PNP_EINVAL, "out is NULL");
+  memset(out, 0, sizeof *out);
+  out->njoint = PNP_NJOINT;
+  memcpy(out->link_pos, pnp_spec::kLinkPos, sizeof out->link_pos);
+  memcpy(out->link_rot, pnp_spec::kLinkRot, sizeof out->link_rot);
+  memcpy(out->ee_pos, pnp_spec::kEePos, sizeof out->ee_pos);
+  memcpy(out->ee_rot, pnp_spec::kEeRot, sizeof out->ee_rot);
+  memcpy(out->lower, pnp_spec::kLower, sizeof out->lower);
+  memcpy(out->upper, pnp_spec::kUpper, sizeof out->upper);
+  memcpy(out->qref, pnp_spec::kQref, sizeof out->qref);
+  return PNP_OK;
+}
+
+int pnp_fk_jac_f32(const float* q, int64_t n, float* pos, float* quat, float* jac, int32_t kin, void* stream) {
+  return fk_jac_impl<float>(q, n, pos, quat, jac, kin, stream);
+}
+int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double* jac, int32_t kin, void* stream) {
+  return fk_jac_impl<double>(q, n, pos, quat, jac, kin, stream);
+}
+
+int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                     const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err, int32_t* iters,
+                     uint8_t* flags, unsigned long long* counters, void* stream) {
+  return ik_solve_impl<float>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters, flags,
+                              counters, stream);
+}
+int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
+                     const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err, int32_t* iters,
+                     uint8_t* flags, unsigned long long* counters, void* stream) {
+  return ik_solve_impl<double>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters, flags,
+                               counters, stream);
+}
+
+int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int32_t n_steps, double step_size,
+                         const PnpIkParams* params, float* q_out, float* pos_out, int32_t* n_accepted,
+                         int32_t* iters_total, unsigned long long* counters, void* stream) {
+  int rc = check_ik_params(params);
+  if (rc) return rc;
+  if (n < 0 || n_steps < 0 || (n > 0 && (!q_start || !goal || !q_out || !pos_out)))
+    return fail(PNP_EINVAL, "ik_waypoints: null pointer or negative size");
+  DeviceState* s;
+  if ((rc = current_state(&s))) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::WaypointArgs<float> a;
+  a.q_start = q_start; a.goal = goal; a.n = n; a.n_steps = n_steps;
+  a.step_size = (float)step_size; a.reach_thresh = 0.01f;
+  a.k = make_ik_const<float>(params);
+  a.q_out = q_out; a.pos_out = pos_out; a.n_accepted = n_accepted; a.iters_total = iters_total;
+  a.counters = counters;
+  const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spec)
+    pnp::ik_waypoints_kernel<float, pnp::SpecKin><<<grid, block, 0, st>>>(a);
+  else
+    pnp::ik_waypoints_kernel<float, pnp::GenericKin><<<grid, block, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+int pnp_reward_f32(const float* ag, const float* dg, const float* ee_pos, const float* ee_quat, const float* width,
+                   const int32_t* task_index, int64_t n, const PnpRewardParams* params, float* reward,
+                   float* is_success, unsigned long long* counters, void* stream) {
+  return reward_impl<float>(ag, dg, ee_pos, ee_quat, width, task_index, n, params, reward, is_success, counters, stream);
+}
+int pnp_reward_f64(const double* ag, const double* dg, const double* ee_pos, const double* ee_quat,
+                   const double* width, const int32_t* task_index, int64_t n, const PnpRewardParams* params,
+                   float* reward, float* is_success, unsigned long long* counters, void* stream) {
+  return reward_impl<double>(ag, dg, ee_pos, ee_quat, width, task_index, n, params, reward, is_success, counters,
+                             stream);
+}
+
+int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream) {
+  if (n < 0 || (n > 0 && (!a || !b || !d))) return fail(PNP_EINVAL, "goal_distance: null pointer or negative n");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::goal_distance_kernel<<<grid_for(n, 256, s->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(a, b, n, d);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+int pnp_probe_fp32_peak(double* tflops_out, double* ms_out) {
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  float* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = s->sm_count * 8, threads = 256, iters = 4096;
+  pnp::fp32_peak_kernel<<<blocks, threads>>>(d_out, 64, 0.999f, 0.001f);  // warm-up
+  CUDA_TRY(cudaEventRecord(e0));
+  pnp::fp32_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999f, 0.001f);
+  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  g_launches += 2;
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  const double flop = 2.0 * 8 * 16 * (double)iters * (double)blocks * threads;
+  if (tflops_out) *tflops_out = flop / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return PNP_OK;
+}
+
+}  // extern "C"
+
+#include "pnp_host_api.inc"

@@ -1,0 +1,284 @@
+// Shared device-side definitions: constant-memory tree, scalar helpers, kinematics policies.
+//
+// Reference semantics implemented here (file:line under /root/reference):
+//   mj_kinematics for the EE chain          panda_mujoco_gym/skills/ik_solver.py:58
+//   mj_jacSite (hinge columns a x (p - c))  ik_solver.py:70-72
+//   mju_mat2Quat                            panda_mujoco_gym/envs/panda_env.py:337-342
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pnp_b200.h"
+#include "generated/spec_kinematics.cuh"
+
+namespace pnp {
+
+constexpr int NJ = PNP_NJOINT;
+
+// Device copy of PnpTree in the compute precision.
+template <typename T>
+struct TreeDev {
+  T link_pos[NJ * 3];
+  T link_rot[NJ * 9];
+  T ee_pos[3];
+  T ee_rot[9];
+  T lower[NJ];
+  T upper[NJ];
+  T qref[NJ];
+};
+
+__constant__ TreeDev<float> c_tree_f32;
+__constant__ TreeDev<double> c_tree_f64;
+
+template <typename T>
+__device__ __forceinline__ const TreeDev<T>& ctree();
+template <>
+__device__ __forceinline__ const TreeDev<float>& ctree<float>() { return c_tree_f32; }
+template <>
+__device__ __forceinline__ const TreeDev<double>& ctree<double>() { return c_tree_f64; }
+
+// ---------------------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ float clamp_t(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ double clamp_t(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// Generic kinematics: any 7-hinge chain, tree read from __constant__ memory.
+// J layout: J[r * 7 + j], rows 0-2 = jacp, rows 3-5 = jacr (fk_full only).
+// ---------------------------------------------------------------------------------------------
+struct GenericKin {
+  static constexpr bool kSpecialized = false;
+
+  template <typename T>
+  static __device__ __forceinline__ T lower(int i) { return ctree<T>().lower[i]; }
+  template <typename T>
+  static __device__ __forceinline__ T upper(int i) { return ctree<T>().upper[i]; }
+  template <typename T>
+  static __device__ __forceinline__ T qref(int i) { return ctree<T>().qref[i]; }
+
+  template <typename T, bool kWantJ, bool kWantRot>
+  static __device__ __forceinline__ void chain(const T* __restrict__ s, const T* __restrict__ c,
+                                               T* __restrict__ p_out, T* __restrict__ J,
+                                               T* __restrict__ R_out) {
+    const TreeDev<T>& t = ctree<T>();
+    T R[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
+    T p[3] = {T(0), T(0), T(0)};
+    T anc[NJ][3], axs[NJ][3];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const T* lp = t.link_pos + 3 * i;
+      const T* lr = t.link_rot + 9 * i;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        p[r] = p[r] + (R[3 * r] * lp[0] + R[3 * r + 1] * lp[1] + R[3 * r + 2] * lp[2]);
+      T N[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          N[3 * r + j] = R[3 * r] * lr[j] + R[3 * r + 1] * lr[3 + j] + R[3 * r + 2] * lr[6 + j];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        anc[i][r] = p[r];
+        axs[i][r] = N[3 * r + 2];
+        const T x = N[3 * r], y = N[3 * r + 1];
+        R[3 * r] = c[i] * x + s[i] * y;       // frame * Rz(q): x' = c x + s y
+        R[3 * r + 1] = c[i] * y - s[i] * x;   //                y' = c y - s x
+        R[3 * r + 2] = N[3 * r + 2];
+      }
+    }
+    T pe[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      pe[r] = p[r] + (R[3 * r] * t.ee_pos[0] + R[3 * r + 1] * t.ee_pos[1] + R[3 * r + 2] * t.ee_pos[2]);
+      p_out[r] = pe[r];
+    }
+    if (kWantJ) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const T rx = pe[0] - anc[j][0], ry = pe[1] - anc[j][1], rz = pe[2] - anc[j][2];
+        J[0 * 7 + j] = axs[j][1] * rz - axs[j][2] * ry;
+        J[1 * 7 + j] = axs[j][2] * rx - axs[j][0] * rz;
+        J[2 * 7 + j] = axs[j][0] * ry - axs[j][1] * rx;
+        if (kWantRot) {
+          J[3 * 7 + j] = axs[j][0];
+          J[4 * 7 + j] = axs[j][1];
+          J[5 * 7 + j] = axs[j][2];
+        }
+      }
+    }
+    if (kWantRot) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          R_out[3 * r + j] = R[3 * r] * t.ee_rot[j] + R[3 * r + 1] * t.ee_rot[3 + j] + R[3 * r + 2] * t.ee_rot[6 + j];
+    }
+  }
+
+  template <typename T>
+  static __device__ __forceinline__ void fk_pos(const T* s, const T* c, T* p) {
+    chain<T, false, false>(s, c, p, nullptr, nullptr);
+  }
+  template <typename T>
+  static __device__ __forceinline__ void fk_jacp(const T* s, const T* c, T* p, T* J) {
+    chain<T, true, false>(s, c, p, J, nullptr);
+  }
+  template <typename T>
+  static __device__ __forceinline__ void fk_full(const T* s, const T* c, T* p, T* J, T* R) {
+    chain<T, true, true>(s, c, p, J, R);
+  }
+  // A (upper triangle a00 a01 a02 a11 a12 a22) = Jp Jp^T
+  template <typename T>
+  static __device__ __forceinline__ void jjt(const T* J, T* A) {
+    const int rr[6] = {0, 0, 0, 1, 1, 2}, ss[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      T acc = T(0);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc = acc + J[rr[k] * 7 + j] * J[ss[k] * 7 + j];
+      A[k] = acc;
+    }
+  }
+  template <typename T>
+  static __device__ __forceinline__ void jty(const T* J, const T* y, T* dq) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) dq[j] = (J[j] * y[0] + J[7 + j] * y[1]) + J[14 + j] * y[2];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Specialised kinematics: straight-line code generated for the packaged Panda tree
+// (tools/gen_spec_kinematics.py).  Selected when the uploaded tree is bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct SpecKin {
+  static constexpr bool kSpecialized = true;
+
+  template <typename T>
+  static __device__ __forceinline__ T lower(int i) { return pnp_spec::spec_lower<T>(i); }
+  template <typename T>
+  static __device__ __forceinline__ T upper(int i) { return pnp_spec::spec_upper<T>(i); }
+  template <typename T>
+  static __device__ __forceinline__ T qref(int i) { return pnp_spec::spec_qref<T>(i); }
+
+  template <typename T>
+  static __device__ __forceinline__ void fk_pos(const T* s, const T* c, T* p) { pnp_spec::spec_fk_pos<T>(s, c, p); }
+  template <typename T>
+  static __device__ __forceinline__ void fk_jacp(const T* s, const T* c, T* p, T* J) {
+    pnp_spec::spec_fk_jacp<T>(s, c, p, J);
+  }
+  template <typename T>
+  static __device__ __forceinline__ void fk_full(const T* s, const T* c, T* p, T* J, T* R) {
+#pragma unroll
+    for (int k = 0; k < 42; ++k) J[k] = T(0);  // structural zeros are not written by the generator
+    pnp_spec::spec_fk_full<T>(s, c, p, J, R);
+  }
+  template <typename T>
+  static __device__ __forceinline__ void jjt(const T* J, T* A) { pnp_spec::spec_jjt<T>(J, A); }
+  template <typename T>
+  static __device__ __forceinline__ void jty(const T* J, const T* y, T* dq) { pnp_spec::spec_jty<T>(J, y, dq); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// mju_mat2Quat (engine_util_spatial.c), wxyz, normalised.  R row-major.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void mat2quat(const T* m, T* q) {
+  const T half = T(0.5), quarter = T(0.25), one = T(1);
+  if (m[0] + m[4] + m[8] > T(0)) {
+    q[0] = half * sqrt_t(one + m[0] + m[4] + m[8]);
+    const T k = quarter / q[0];
+    q[1] = k * (m[7] - m[5]);
+    q[2] = k * (m[2] - m[6]);
+    q[3] = k * (m[3] - m[1]);
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    q[1] = half * sqrt_t(one + m[0] - m[4] - m[8]);
+    const T k = quarter / q[1];
+    q[0] = k * (m[7] - m[5]);
+    q[2] = k * (m[1] + m[3]);
+    q[3] = k * (m[2] + m[6]);
+  } else if (m[4] > m[8]) {
+    q[2] = half * sqrt_t(one - m[0] + m[4] - m[8]);
+    const T k = quarter / q[2];
+    q[0] = k * (m[2] - m[6]);
+    q[1] = k * (m[1] + m[3]);
+    q[3] = k * (m[5] + m[7]);
+  } else {
+    q[3] = half * sqrt_t(one - m[0] - m[4] + m[8]);
+    const T k = quarter / q[3];
+    q[0] = k * (m[3] - m[1]);
+    q[1] = k * (m[2] + m[6]);
+    q[2] = k * (m[5] + m[7]);
+  }
+  const T n = sqrt_t(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const T inv = one / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One damped-least-squares evaluation (ik_solver.py:58-81) at joint angles q:
+//   p  = FK(q)                      (mj_kinematics, :58-59)
+//   n2 = |target - p|^2             (:60-61; caller takes the sqrt / compares)
+//   qn = clip(q + clip(J^T (J J^T + damping I)^-1 e, +-step), lower, upper)   (:70-81)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct IkConst {
+  T pos_thresh, damping, step_limit;
+  int max_iters;
+};
+
+template <typename T, typename Kin>
+__device__ __forceinline__ void ik_eval_and_step(const T (&q)[NJ], const T (&tgt)[3], const IkConst<T>& k,
+                                                 T (&p)[3], T& n2, T (&qn)[NJ]) {
+  T s[NJ], c[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) sincos_t(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
+  T J[21];
+  Kin::template fk_jacp<T>(s, c, p, J);
+  const T e0 = tgt[0] - p[0], e1 = tgt[1] - p[1], e2 = tgt[2] - p[2];
+  n2 = (e0 * e0 + e1 * e1) + e2 * e2;
+  T A[6];
+  Kin::template jjt<T>(J, A);
+  // (J J^T + damping I) y = e by LDL^T (the matrix is SPD for damping > 0)
+  const T a00 = A[0] + k.damping, a11 = A[3] + k.damping, a22 = A[5] + k.damping;
+  const T i0 = rcp_t(a00);
+  const T l10 = A[1] * i0, l20 = A[2] * i0;
+  const T d1 = a11 - l10 * A[1];
+  const T u12 = A[4] - l10 * A[2];
+  const T i1 = rcp_t(d1);
+  const T l21 = u12 * i1;
+  const T d2 = a22 - l20 * A[2] - l21 * u12;
+  const T i2 = rcp_t(d2);
+  const T z1 = e1 - l10 * e0;
+  const T z2 = e2 - l20 * e0 - l21 * z1;
+  T y[3];
+  y[2] = z2 * i2;
+  y[1] = z1 * i1 - l21 * y[2];
+  y[0] = e0 * i0 - l10 * y[1] - l20 * y[2];
+  T dq[NJ];
+  Kin::template jty<T>(J, y, dq);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const T d = clamp_t(dq[i], -k.step_limit, k.step_limit);                              // :80
+    qn[i] = clamp_t(q[i] + d, Kin::template lower<T>(i), Kin::template upper<T>(i));      // :81
+  }
+}
+
+// FK only (final_pos of a solve, ik_solver.py:88)
+template <typename T, typename Kin>
+__device__ __forceinline__ void fk_position(const T (&q)[NJ], T (&p)[3]) {
+  T s[NJ], c[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) sincos_t(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
+  Kin::template fk_pos<T>(s, c, p);
+}
+
+}  // namespace pnp

@@ -1,0 +1,335 @@
+"""Thin Python layer over the C ABI: torch tensors (device memory, streams) in, tensors out.
+
+PyTorch is plumbing here (allocation, current stream); every computation is a kernel of
+libpnp_b200.so.  Functions taking CUDA tensors launch on ``torch.cuda.current_stream()`` and
+return without synchronising.  Functions with a ``_host`` suffix take NumPy arrays / CPU
+tensors and go through the library's own H2D -> kernel -> D2H pipeline (``pnp_*_host``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KINEMATICS, PnpIkParams, PnpRewardParams
+from .tree import KinematicTree, PnpTreeStruct
+
+_uploaded: Dict[int, bytes] = {}  # device index -> bytes of the PnpTree currently in constant memory
+_host_ctx: Dict[Tuple[int, int], ctypes.c_void_p] = {}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _lib.PnpLibraryError("no CUDA device: mujoco_panda_pnp_b200 has no CPU path")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def set_tree(tree: KinematicTree) -> bool:
+    """Upload ``tree`` to the current device's constant memory (no-op if already there).
+
+    Returns True when the library will use its build-time specialised kinematics for it."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    s = tree.to_struct()
+    blob = bytes(s)
+    if _uploaded.get(dev) != blob:
+        _lib.check(lib.pnp_set_tree(ctypes.byref(s)), "pnp_set_tree")
+        _uploaded[dev] = blob
+    return bool(lib.pnp_tree_is_specialized())
+
+
+def specialized_tree() -> KinematicTree:
+    """The tree the specialised kernels were generated for (from the library itself)."""
+    s = PnpTreeStruct()
+    _lib.check(_lib.load().pnp_get_specialized_tree(ctypes.byref(s)), "pnp_get_specialized_tree")
+    return KinematicTree(
+        link_pos=np.array(s.link_pos[:]).reshape(7, 3),
+        link_rot=np.array(s.link_rot[:]).reshape(7, 3, 3),
+        ee_pos=np.array(s.ee_pos[:]),
+        ee_rot=np.array(s.ee_rot[:]).reshape(3, 3),
+        lower=np.array(s.lower[:]),
+        upper=np.array(s.upper[:]),
+        qref=np.array(s.qref[:]),
+    )
+
+
+def ik_params(max_iters=100, pos_thresh=1e-3, damping=1e-2, step_limit=0.1, kinematics="auto") -> PnpIkParams:
+    return PnpIkParams(int(max_iters), KINEMATICS[kinematics], float(pos_thresh), float(damping), float(step_limit))
+
+
+def reward_params(reward_type="dense", n_tasks=3, initial_object_height=0.001, distance_threshold=0.05,
+                  high_pick_z=0.35, threshold_report_tol=1e-6) -> PnpRewardParams:
+    if reward_type not in ("dense", "sparse"):
+        raise ValueError(f"reward_type must be 'dense' or 'sparse', got {reward_type!r}")
+    return PnpRewardParams(int(reward_type == "sparse"), int(n_tasks), float(initial_object_height),
+                           float(distance_threshold), float(high_pick_z), float(threshold_report_tol))
+
+
+def _check_cuda(name: str, t: torch.Tensor, dtype, shape_tail) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"{name} must have shape (N, {', '.join(map(str, shape_tail))}), got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# FK + Jacobian
+# ---------------------------------------------------------------------------------------------
+def fk_jac(q: torch.Tensor, want_quat=True, want_jac=True, kinematics="auto"):
+    """q[N,7] (cuda, f32|f64) -> pos[N,3], quat[N,4] wxyz | None, jac[N,6,7] | None."""
+    lib = _lib.load()
+    if q.dtype not in (torch.float32, torch.float64):
+        raise ValueError("q must be float32 or float64")
+    q = _check_cuda("q", q, q.dtype, (7,))
+    n = q.shape[0]
+    pos = torch.empty((n, 3), dtype=q.dtype, device=q.device)
+    quat = torch.empty((n, 4), dtype=q.dtype, device=q.device) if want_quat else None
+    jac = torch.empty((n, 6, 7), dtype=q.dtype, device=q.device) if want_jac else None
+    fn = lib.pnp_fk_jac_f32 if q.dtype == torch.float32 else lib.pnp_fk_jac_f64
+    with torch.cuda.device(q.device):
+        _lib.check(fn(_ptr(q), n, _ptr(pos), _ptr(quat), _ptr(jac), KINEMATICS[kinematics], _stream()), "pnp_fk_jac")
+    return pos, quat, jac
+
+
+# ---------------------------------------------------------------------------------------------
+# batched IK
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class BatchIKResult:
+    """Batched IKResult (ik_solver.py:16-24): same fields, one row per query."""
+
+    success: torch.Tensor  # bool[N]
+    q: torch.Tensor  # [N,7]
+    final_pos: torch.Tensor  # [N,3]
+    pos_error: torch.Tensor  # [N]
+    iterations: torch.Tensor  # int32[N]
+    converged: torch.Tensor  # bool[N]
+    counters: Optional[torch.Tensor] = None  # uint64-as-int64[4]: n, converged, success, sum(iterations)
+
+    def __len__(self) -> int:
+        return int(self.q.shape[0])
+
+
+def ik_solve(targets: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams, counters: Optional[torch.Tensor] = None,
+             want_aux: bool = True) -> BatchIKResult:
+    """Device path: targets[N,3], q_init[N,7] or [7] (cuda, same float dtype)."""
+    lib = _lib.load()
+    dt = targets.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("targets must be float32 or float64")
+    targets = _check_cuda("targets", targets, dt, (3,))
+    n = targets.shape[0]
+    if q_init.dim() == 1:
+        if q_init.shape != (7,):
+            raise ValueError("broadcast q_init must have shape (7,)")
+        stride = 0
+        q_init = q_init.to(device=targets.device, dtype=dt).contiguous()
+    else:
+        q_init = _check_cuda("q_init", q_init, dt, (7,))
+        if q_init.shape[0] != n:
+            raise ValueError("q_init and targets disagree on N")
+        stride = 7
+    dev = targets.device
+    q = torch.empty((n, 7), dtype=dt, device=dev)
+    fpos = torch.empty((n, 3), dtype=dt, device=dev) if want_aux else None
+    err = torch.empty((n,), dtype=dt, device=dev) if want_aux else None
+    iters = torch.empty((n,), dtype=torch.int32, device=dev) if want_aux else None
+    flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+    if counters is not None and (counters.dtype != torch.int64 or counters.numel() < 4 or not counters.is_cuda):
+        raise ValueError("counters must be a CUDA int64 tensor with >= 4 elements")
+    fn = lib.pnp_ik_solve_f32 if dt == torch.float32 else lib.pnp_ik_solve_f64
+    with torch.cuda.device(dev):
+        _lib.check(
+            fn(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q), _ptr(fpos), _ptr(err),
+               _ptr(iters), _ptr(flags), _ptr(counters), _stream()),
+            "pnp_ik_solve",
+        )
+    return BatchIKResult(
+        success=(flags & 2).bool(), q=q, final_pos=fpos, pos_error=err, iterations=iters,
+        converged=(flags & 1).bool(), counters=counters,
+    )
+
+
+def ik_waypoints(q_start: torch.Tensor, goal: torch.Tensor, n_steps: int, params: PnpIkParams,
+                 step_size: float = 0.01, counters: Optional[torch.Tensor] = None):
+    """cfg4: per-env warm-started waypoint sequences (float32 device tensors)."""
+    lib = _lib.load()
+    q_start = _check_cuda("q_start", q_start, torch.float32, (7,))
+    goal = _check_cuda("goal", goal, torch.float32, (3,))
+    n = q_start.shape[0]
+    if goal.shape[0] != n:
+        raise ValueError("q_start and goal disagree on N")
+    dev = q_start.device
+    q = torch.empty((n, 7), dtype=torch.float32, device=dev)
+    pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    acc = torch.empty((n,), dtype=torch.int32, device=dev)
+    its = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.pnp_ik_waypoints_f32(_ptr(q_start), _ptr(goal), n, int(n_steps), float(step_size),
+                                     ctypes.byref(params), _ptr(q), _ptr(pos), _ptr(acc), _ptr(its),
+                                     _ptr(counters), _stream()),
+            "pnp_ik_waypoints",
+        )
+    return dict(q=q, pos=pos, n_accepted=acc, iters_total=its)
+
+
+# ---------------------------------------------------------------------------------------------
+# reward
+# ---------------------------------------------------------------------------------------------
+def reward(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, want_success=True,
+           counters: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           out_success: Optional[torch.Tensor] = None):
+    """Device path: rows as CUDA tensors (f32 or f64 storage), reward float32[N]."""
+    lib = _lib.load()
+    dt = ag.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("achieved_goal must be float32 or float64")
+    ag = _check_cuda("achieved_goal", ag, dt, (3,))
+    dg = _check_cuda("desired_goal", dg, dt, (3,))
+    ee_pos = _check_cuda("ee_pos", ee_pos, dt, (3,))
+    ee_quat = _check_cuda("ee_quat", ee_quat, dt, (4,))
+    width = _check_cuda("fingers_width", width, dt, ())
+    task_index = _check_cuda("task_index", task_index, torch.int32, ())
+    n = ag.shape[0]
+    for name, t in (("desired_goal", dg), ("ee_pos", ee_pos), ("ee_quat", ee_quat), ("fingers_width", width),
+                    ("task_index", task_index)):
+        if t.shape[0] != n:
+            raise ValueError(f"{name} disagrees with achieved_goal on N")
+    dev = ag.device
+    rew = out if out is not None else torch.empty((n,), dtype=torch.float32, device=dev)
+    succ = out_success if out_success is not None else (
+        torch.empty((n,), dtype=torch.float32, device=dev) if want_success else None)
+    fn = lib.pnp_reward_f32 if dt == torch.float32 else lib.pnp_reward_f64
+    with torch.cuda.device(dev):
+        _lib.check(
+            fn(_ptr(ag), _ptr(dg), _ptr(ee_pos), _ptr(ee_quat), _ptr(width), _ptr(task_index), n,
+               ctypes.byref(params), _ptr(rew), _ptr(succ), _ptr(counters), _stream()),
+            "pnp_reward",
+        )
+    return rew, succ
+
+
+def goal_distance(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    a = _check_cuda("a", a, torch.float64, (3,))
+    b = _check_cuda("b", b, torch.float64, (3,))
+    if a.shape != b.shape:
+        raise ValueError("a and b must have the same shape")
+    d = torch.empty((a.shape[0],), dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.pnp_goal_distance_f64(_ptr(a), _ptr(b), a.shape[0], _ptr(d), _stream()), "pnp_goal_distance")
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer path (library-owned copy/compute pipeline)
+# ---------------------------------------------------------------------------------------------
+def host_ctx(chunk_rows: int = 0) -> ctypes.c_void_p:
+    _require_cuda()
+    key = (torch.cuda.current_device(), int(chunk_rows))
+    if key not in _host_ctx:
+        ctx = ctypes.c_void_p()
+        _lib.check(_lib.load().pnp_host_ctx_create(ctypes.byref(ctx), int(chunk_rows)), "pnp_host_ctx_create")
+        _host_ctx[key] = ctx
+    return _host_ctx[key]
+
+
+def _np_ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+def _as_host(name: str, a, dtype, shape_tail) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise ValueError(f"{name}: host path got a CUDA tensor")
+        a = a.numpy()
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape[1:] != tuple(shape_tail):
+        raise ValueError(f"{name} must have shape (N, {', '.join(map(str, shape_tail))}), got {a.shape}")
+    return a
+
+
+def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out: Optional[dict] = None) -> dict:
+    """Host path: NumPy / CPU-tensor inputs (float32), NumPy outputs.  ``out`` may supply
+    preallocated (ideally pinned) output arrays: q, final_pos, pos_error, iterations, flags."""
+    lib = _lib.load()
+    targets = _as_host("targets", targets, np.float32, (3,))
+    n = targets.shape[0]
+    if isinstance(q_init, torch.Tensor):
+        q_init = q_init.numpy()
+    q_init = np.ascontiguousarray(q_init, dtype=np.float32)
+    if q_init.shape == (7,):
+        stride = 0
+    elif q_init.shape == (n, 7):
+        stride = 7
+    else:
+        raise ValueError(f"q_init must have shape (7,) or ({n}, 7), got {q_init.shape}")
+    out = out or {}
+    q = out.get("q") if out.get("q") is not None else np.empty((n, 7), np.float32)
+    fpos = out.get("final_pos") if out.get("final_pos") is not None else np.empty((n, 3), np.float32)
+    err = out.get("pos_error") if out.get("pos_error") is not None else np.empty((n,), np.float32)
+    iters = out.get("iterations") if out.get("iterations") is not None else np.empty((n,), np.int32)
+    flags = out.get("flags") if out.get("flags") is not None else np.empty((n,), np.uint8)
+    counters = np.zeros(4, dtype=np.uint64)
+    _lib.check(
+        lib.pnp_ik_solve_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
+                                  ctypes.byref(params), _np_ptr(q), _np_ptr(fpos), _np_ptr(err), _np_ptr(iters),
+                                  _np_ptr(flags), _np_ptr(counters)),
+        "pnp_ik_solve_host",
+    )
+    return dict(q=q, final_pos=fpos, pos_error=err, iterations=iters, flags=flags,
+                converged=(flags & 1).astype(bool), success=(flags & 2).astype(bool), counters=counters)
+
+
+def reward_host(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, want_success=True,
+                chunk_rows: int = 0, out: Optional[np.ndarray] = None, out_success: Optional[np.ndarray] = None):
+    """Host path: NumPy rows (float32 or float64 storage) -> reward float32[N], success, counters."""
+    lib = _lib.load()
+    first = ag.numpy() if isinstance(ag, torch.Tensor) else np.asarray(ag)
+    dt = np.float32 if first.dtype == np.float32 else np.float64
+    ag = _as_host("achieved_goal", ag, dt, (3,))
+    dg = _as_host("desired_goal", dg, dt, (3,))
+    ee_pos = _as_host("ee_pos", ee_pos, dt, (3,))
+    ee_quat = _as_host("ee_quat", ee_quat, dt, (4,))
+    width = _as_host("fingers_width", width, dt, ())
+    task_index = _as_host("task_index", task_index, np.int32, ())
+    n = ag.shape[0]
+    for name, t in (("desired_goal", dg), ("ee_pos", ee_pos), ("ee_quat", ee_quat), ("fingers_width", width),
+                    ("task_index", task_index)):
+        if t.shape[0] != n:
+            raise ValueError(f"{name} disagrees with achieved_goal on N")
+    rew = out if out is not None else np.empty((n,), np.float32)
+    succ = out_success if out_success is not None else (np.empty((n,), np.float32) if want_success else None)
+    counters = np.zeros(4, dtype=np.uint64)
+    fn = lib.pnp_reward_host_f32 if dt == np.float32 else lib.pnp_reward_host_f64
+    _lib.check(
+        fn(host_ctx(chunk_rows), _np_ptr(ag), _np_ptr(dg), _np_ptr(ee_pos), _np_ptr(ee_quat), _np_ptr(width),
+           _np_ptr(task_index), n, ctypes.byref(params), _np_ptr(rew), _np_ptr(succ), _np_ptr(counters)),
+        "pnp_reward_host",
+    )
+    return rew, succ, counters
+
+
+def probe_fp32_peak() -> Tuple[float, float]:
+    """(TFLOP/s, ms) of the FFMA microbenchmark on the current device."""
+    _require_cuda()
+    t, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.load().pnp_probe_fp32_peak(ctypes.byref(t), ctypes.byref(ms)), "pnp_probe_fp32_peak")
+    return t.value, ms.value
