@@ -1,0 +1,62 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/pnp_b200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from mujoco_panda_pnp_b200 import _lib
+from mujoco_panda_pnp_b200.tree import KinematicTree, PnpTreeStruct
+
+HEADER = os.path.join(ROOT, "include", "pnp_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    decl = declared_functions()
+    assert len(decl) >= 20
+    assert sorted(_lib.SIGNATURES) == decl
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (pnp_[a-z0-9_]+)", out))
+    assert set(declared_functions()) <= exported
+    for name in declared_functions():
+        assert hasattr(cuda_lib, name)
+    assert cuda_lib.pnp_abi_version() == 1
+
+
+def test_struct_layouts_match_header(cuda_lib):
+    # sizeof(PnpTree) = 8 + (21+63+3+9+7+7+7)*8
+    assert ctypes.sizeof(PnpTreeStruct) == 8 + 117 * 8
+    assert ctypes.sizeof(_lib.PnpIkParams) == 32
+    assert ctypes.sizeof(_lib.PnpRewardParams) == 40
+    # the specialised tree baked into the library is the packaged asset's tree
+    s = PnpTreeStruct()
+    assert cuda_lib.pnp_get_specialized_tree(ctypes.byref(s)) == 0
+    assert bytes(s) == bytes(KinematicTree.from_mjcf().to_struct())
+
+
+def test_argument_errors_do_not_need_a_gpu(cuda_lib):
+    assert cuda_lib.pnp_set_tree(None) == -1
+    assert b"NULL" in cuda_lib.pnp_last_error()
+    assert cuda_lib.pnp_get_specialized_tree(None) == -1
+    assert cuda_lib.pnp_launch_count() >= 0
+
+
+def test_sass_is_sm100a_only():
+    """The shipped cubin targets sm_100a and nothing else (no multi-arch fat binary)."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.check_output([cuobjdump, "-lelf", _lib.LIB_PATH], text=True)
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs

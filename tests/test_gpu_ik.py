@@ -1,0 +1,250 @@
+"""GPU parity: batched JacobianIKController.solve vs the oracle / reference golden vectors.
+
+Tolerances (north_star): converged joint solutions must reproduce reference EE poses to
+1e-4 m.  The FP64 kernel follows the reference iteration for iteration (identical iteration
+counts, q within 1e-9); the FP32 kernel is the product path and is held to the stated EE
+tolerance, with iteration-count flips counted and bounded."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import NEUTRAL
+from mujoco_panda_pnp_b200 import KinematicData, KinematicTree, engine, synthetic
+from mujoco_panda_pnp_b200.skills import IKResult, JacobianIKController
+from oracle import c_oracle, ik_oracle, mj_oracle
+
+pytestmark = pytest.mark.gpu
+
+EE_TOL_M = 1e-4  # north_star: converged solutions reproduce reference EE poses to 1e-4 m
+
+
+@pytest.fixture(scope="module")
+def tree(cuda_lib):
+    t = KinematicTree.from_mjcf()
+    engine.set_tree(t)
+    return t
+
+
+def _kw(g, k):
+    return dict(max_iters=int(g["max_iters"][k]), pos_thresh=float(g["pos_thresh"][k]),
+                damping=float(g["damping"][k]), step_limit=float(g["step_limit"][k]))
+
+
+@pytest.mark.parametrize("kin", ["specialized", "generic"])
+def test_reference_golden_fp64_is_iteration_exact(kin_model, golden_ik, kin):
+    g = golden_ik
+    ctl = JacobianIKController(kin_model, KinematicData(kin_model), precision="fp64", kinematics=kin)
+    for k in range(len(g["tag"])):
+        r = ctl.solve(g["target"][k], g["q_init"][k], **_kw(g, k))
+        tag = str(g["tag"][k])
+        assert isinstance(r, IKResult)
+        assert r.iterations == g["iterations"][k], tag
+        assert r.converged == bool(g["converged"][k]) and r.success == bool(g["success"][k]), tag
+        # converged solves agree to 1e-9; the non-converged ones sit in a singular stretched-out
+        # pose for ~100 steps where the reference's 1e-17 Jacobian noise is amplified to ~1e-7
+        tol = 1e-9 if r.converged else 1e-6
+        np.testing.assert_allclose(r.q, g["q"][k], atol=tol, err_msg=tag)
+        np.testing.assert_allclose(r.final_pos, g["final_pos"][k], atol=tol, err_msg=tag)
+        assert abs(r.pos_error - g["pos_error"][k]) < tol, tag
+
+
+@pytest.mark.parametrize("kin", ["specialized", "generic"])
+def test_reference_golden_fp32(kin_model, golden_ik, oracle_chain, kin):
+    g = golden_ik
+    ctl = JacobianIKController(kin_model, KinematicData(kin_model), kinematics=kin)
+    flips = 0
+    for k in range(len(g["tag"])):
+        r = ctl.solve(g["target"][k], g["q_init"][k], **_kw(g, k))
+        tag = str(g["tag"][k])
+        assert r.converged == bool(g["converged"][k]), tag
+        flips += int(r.iterations != g["iterations"][k])
+        if r.converged and r.iterations == g["iterations"][k]:
+            # same number of DLS steps -> same joint solution up to FP32 rounding
+            np.testing.assert_allclose(r.q, g["q"][k], atol=2e-5, err_msg=tag)
+            ee = c_oracle.fk_jac(oracle_chain, r.q[None])[0][0]
+            assert np.linalg.norm(ee - g["final_pos"][k]) < EE_TOL_M, tag
+        if r.converged:
+            assert np.linalg.norm(r.final_pos - g["target"][k]) < g["pos_thresh"][k] + 1e-6
+    assert flips <= 2, flips  # threshold-adjacent cases may take one step more or less in FP32
+
+
+def test_controller_is_a_drop_in(kin_model):
+    """Same attributes / side effects as the reference class (ik_solver.py:27-33)."""
+    data = KinematicData(kin_model)
+    ctl = JacobianIKController(kin_model, data)
+    assert ctl.site_id == kin_model.site("ee_center_site").id
+    np.testing.assert_array_equal(ctl.joint_ids, np.arange(7))
+    np.testing.assert_array_equal(ctl.lower, kin_model.jnt_range[:7, 0])
+    np.testing.assert_array_equal(ctl.upper, kin_model.jnt_range[:7, 1])
+    assert ctl.specialized
+    r = ctl.solve(np.array([1.415, 0.0, 0.73]), NEUTRAL)  # positional, defaults: move.py:128
+    assert r.success and r.converged and r.iterations == 7 and r.q.shape == (7,) and r.q.dtype == np.float64
+    np.testing.assert_array_equal(data.qpos[:7], r.q)
+    np.testing.assert_array_equal(data.site_xpos[ctl.site_id], r.final_pos)
+    assert isinstance(r.pos_error, float) and isinstance(r.iterations, int) and isinstance(r.success, bool)
+    # test/ik_test.py:31-38 call pattern (keyword arguments)
+    r2 = ctl.solve(target_pos=np.array([1.33843967, 0.0, 0.49740014]), q_init=NEUTRAL, max_iters=100,
+                   pos_thresh=1e-4, damping=0.05)
+    assert r2.converged and r2.iterations == 10
+    with pytest.raises(ValueError):
+        ctl.solve(np.zeros(2), NEUTRAL)
+
+
+def _compare_with_oracle(res, ref, targets, oracle_chain, pos_thresh, flip_budget):
+    q = res.q.double().cpu().numpy()
+    conv = res.converged.cpu().numpy()
+    iters = res.iterations.cpu().numpy()
+    assert np.array_equal(res.success.cpu().numpy(), conv)  # App. D.2
+    flips = int((iters != ref["iterations"]).sum())
+    conv_flips = int((conv != ref["converged"]).sum())
+    assert flips <= flip_budget, (flips, flip_budget)
+    assert conv_flips <= max(1, flip_budget // 4)
+    same = conv & ref["converged"] & (iters == ref["iterations"])
+    # reference FK of the GPU's joint solution vs the reference's own final EE position
+    ee = c_oracle.fk_jac(oracle_chain, q, nthreads=8)[0]
+    assert np.linalg.norm(ee[same] - ref["final_pos"][same], axis=1).max() < EE_TOL_M
+    # every converged GPU solution really is within pos_thresh of its target under reference FK
+    assert np.linalg.norm(ee[conv] - targets[conv], axis=1).max() < pos_thresh + 1e-5
+    # limits respected
+    lo, hi = np.array(oracle_chain.lower[:]), np.array(oracle_chain.upper[:])
+    assert (q >= lo - 1e-6).all() and (q <= hi + 1e-6).all()
+    return flips
+
+
+@pytest.mark.parametrize("kin", ["specialized", "generic"])
+def test_cfg2_4096_cold_targets_vs_oracle(tree, oracle_chain, kin):
+    """BASELINE cfg2: 4096 reachable targets, cold start from neutral, defaults."""
+    n = 4096
+    qstar = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=0, dtype=torch.float64).numpy()
+    targets = c_oracle.fk_jac(oracle_chain, qstar, nthreads=8)[0]
+    ref = c_oracle.ik_solve(oracle_chain, targets, NEUTRAL, nthreads=8)
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    res = engine.ik_solve(torch.tensor(targets, dtype=torch.float32, device="cuda"),
+                          torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"),
+                          engine.ik_params(kinematics=kin), counters=cnt)
+    ref32 = c_oracle.ik_solve(oracle_chain, targets.astype(np.float32).astype(np.float64), NEUTRAL, nthreads=8)
+    _compare_with_oracle(res, ref32, targets, oracle_chain, 1e-3, flip_budget=8)
+    c = cnt.cpu().numpy()
+    assert c[0] == n and c[1] == int(res.converged.sum()) and c[2] == c[1] and c[3] == int(res.iterations.sum())
+    # workload statistics of SURVEY 8d (success ~99.7 %, mean iterations ~16)
+    assert 0.99 < c[1] / n < 1.0 and 15 < c[3] / n < 17.5
+    assert ref["converged"].mean() == pytest.approx(c[1] / n, abs=2e-3)
+
+
+def test_fp64_kernel_matches_oracle_on_cfg2(tree, oracle_chain):
+    n = 4096
+    qstar = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=0, dtype=torch.float64).numpy()
+    targets = c_oracle.fk_jac(oracle_chain, qstar, nthreads=8)[0]
+    ref = c_oracle.ik_solve(oracle_chain, targets, NEUTRAL, nthreads=8)
+    res = engine.ik_solve(torch.tensor(targets, device="cuda"), torch.tensor(NEUTRAL, device="cuda"), engine.ik_params())
+    iters = res.iterations.cpu().numpy()
+    assert (iters != ref["iterations"]).sum() <= 1  # exact-threshold ties only
+    same = iters == ref["iterations"]
+    conv = ref["converged"] & same
+    np.testing.assert_allclose(res.q.cpu().numpy()[conv], ref["q"][conv], atol=1e-7)
+    np.testing.assert_allclose(res.final_pos.cpu().numpy()[conv], ref["final_pos"][conv], atol=1e-8)
+
+
+def test_per_query_init_ragged_sizes_and_edge_cases(tree, oracle_chain):
+    rng = np.random.default_rng(21)
+    lo, hi = tree.lower, tree.upper
+    for n in (1, 2, 31, 33, 1000):
+        q0 = np.clip(NEUTRAL + rng.uniform(-0.3, 0.3, (n, 7)), lo, hi)
+        targets = c_oracle.fk_jac(oracle_chain, np.clip(q0 + rng.uniform(-0.1, 0.1, (n, 7)), lo, hi))[0]
+        ref = c_oracle.ik_solve(oracle_chain, targets, q0)
+        res = engine.ik_solve(torch.tensor(targets, device="cuda"), torch.tensor(q0, device="cuda"), engine.ik_params())
+        assert np.array_equal(res.iterations.cpu().numpy(), ref["iterations"])
+        np.testing.assert_allclose(res.q.cpu().numpy(), ref["q"], atol=1e-8)
+    # empty batch
+    res = engine.ik_solve(torch.empty((0, 3), device="cuda"), torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"),
+                          engine.ik_params())
+    assert len(res) == 0 and res.iterations.shape == (0,)
+    # max_iters = 0: no pass runs, iterations 0, final_pos = FK(q_init), not converged (ik_solver.py:54-57,88)
+    res = engine.ik_solve(torch.tensor([[1.3, 0.0, 0.6]], device="cuda", dtype=torch.float64),
+                          torch.tensor(NEUTRAL, device="cuda"), engine.ik_params(max_iters=0))
+    assert int(res.iterations[0]) == 0 and not bool(res.converged[0])
+    np.testing.assert_allclose(res.final_pos[0].cpu().numpy(), [1.23843967, 0, 0.49740014], atol=1e-8)
+    np.testing.assert_allclose(res.q[0].cpu().numpy(), NEUTRAL)
+    # argument validation
+    with pytest.raises(ValueError):
+        engine.ik_solve(torch.zeros((4, 3), device="cuda"), torch.zeros((3, 7), device="cuda"), engine.ik_params())
+    with pytest.raises(ValueError, match="damping"):
+        engine.ik_solve(torch.zeros((4, 3), device="cuda"), torch.zeros(7, device="cuda"), engine.ik_params(damping=0.0))
+
+
+def test_unreachable_targets_run_out_of_iterations(tree, oracle_chain):
+    targets = np.array([[2.5, 0.0, 0.5], [0.6, 0.0, -0.5], [1.415, 0, 0.73]])
+    ref = c_oracle.ik_solve(oracle_chain, targets, NEUTRAL, max_iters=40)
+    res = engine.ik_solve(torch.tensor(targets, dtype=torch.float32, device="cuda"),
+                          torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"), engine.ik_params(max_iters=40))
+    assert res.converged.tolist() == [False, False, True] == ref["converged"].tolist()
+    assert res.iterations.tolist() == [40, 40, 7]
+    np.testing.assert_allclose(res.pos_error.cpu().numpy(), ref["pos_error"], atol=2e-6)
+    np.testing.assert_allclose(res.q.double().cpu().numpy(), ref["q"], atol=1e-3)
+
+
+def test_large_batch_properties(tree, oracle_chain):
+    """2^22 cold targets (cfg5 scale): size-independent properties + a sampled oracle check."""
+    n = 1 << 22
+    q = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=1234, device="cuda")
+    targets = engine.fk_jac(q, want_quat=False, want_jac=False)[0]
+    del q
+    neutral = torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    res = engine.ik_solve(targets, neutral, engine.ik_params(), counters=cnt)
+    c = cnt.cpu().numpy()
+    assert c[0] == n and c[1] == int(res.converged.sum()) and c[3] == int(res.iterations.long().sum())
+    assert 0.995 < c[1] / n < 1.0 and 15.5 < c[3] / n < 16.5
+    it = res.iterations
+    assert int(it.min()) >= 1 and int(it.max()) == 100
+    assert bool(((it == 100) | res.converged).all()) and bool((res.pos_error[res.converged] < 1e-3).all())
+    # final_pos is FK(q) (ik_solver.py:88): recompute with the FK kernel
+    fk = engine.fk_jac(res.q, want_quat=False, want_jac=False)[0]
+    assert float((fk - res.final_pos).abs().max()) < 2e-6
+    # idempotence: a converged solution is a fixed point - re-solving from it takes 1 iteration
+    idx = torch.nonzero(res.converged)[:65536, 0]
+    again = engine.ik_solve(targets[idx], res.q[idx], engine.ik_params())
+    assert bool((again.iterations == 1).all()) and torch.equal(again.q, res.q[idx])
+    # determinism despite dynamic lane refill
+    res2 = engine.ik_solve(targets, neutral, engine.ik_params())
+    assert torch.equal(res.q, res2.q) and torch.equal(res.iterations, res2.iterations)
+    # sampled oracle comparison (first 16384 queries)
+    m = 16384
+    th = targets[:m].double().cpu().numpy()
+    ref = c_oracle.ik_solve(oracle_chain, th, NEUTRAL, nthreads=8)
+    sub = engine.BatchIKResult(success=res.success[:m], q=res.q[:m], final_pos=res.final_pos[:m],
+                               pos_error=res.pos_error[:m], iterations=res.iterations[:m], converged=res.converged[:m])
+    flips = _compare_with_oracle(sub, ref, th, oracle_chain, 1e-3, flip_budget=32)
+    print(f"iteration-count flips FP32 vs FP64 oracle: {flips}/{m}")
+
+
+def test_waypoint_sequences_vs_oracle(tree, oracle_model, oracle_chain):
+    """cfg4 (MoveIKSkill inner loop, move.py:106-137) on a few envs vs a NumPy restatement."""
+    n, steps = 24, 50
+    w = synthetic.waypoint_envs(n, seed=5, dtype=torch.float64)
+    q0, goal = w["q_start"].numpy(), w["goal"].numpy()
+    out = engine.ik_waypoints(torch.tensor(q0, dtype=torch.float32, device="cuda"),
+                              torch.tensor(goal, dtype=torch.float32, device="cuda"), steps, engine.ik_params())
+    ctl = ik_oracle.JacobianIKController(oracle_model, mj_oracle.MjData(oracle_model))
+    data = mj_oracle.MjData(oracle_model)
+    for e in range(n):
+        q = q0[e].astype(np.float32).astype(np.float64)
+        g = goal[e].astype(np.float32).astype(np.float64)
+        pos = ik_oracle.fk_site(oracle_model, data, q)[0]
+        accepted = fails = 0
+        for _ in range(steps):
+            direction = g - pos
+            dist = np.linalg.norm(direction)
+            if not dist > 0.01:
+                break
+            step = min(min(0.01, dist * 0.1), 0.02) * (0.5 if fails > 0 else 1.0)
+            nxt = pos + direction * step / dist if dist > step else g.copy()
+            r = ctl.solve(nxt, q)
+            if r.success and r.pos_error < 0.02:
+                pos, q, fails = r.final_pos, r.q, 0
+                accepted += 1
+            else:
+                fails += 1
+        assert int(out["n_accepted"][e]) == accepted
+        np.testing.assert_allclose(out["pos"][e].cpu().numpy(), pos, atol=5e-5)
+        np.testing.assert_allclose(out["q"][e].cpu().numpy(), q, atol=2e-3)
