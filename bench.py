@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""bench.py - Panda IK solves/s and HER reward evals/s on B200, beside the host-CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # reference arm = CPU oracle port
+
+Headline line (one JSON object on stdout, rank 0):
+  metric  panda_ik_converged_solves_per_s          (BASELINE.json: "Panda IK solves/s ...")
+  step    one pass of the IK hot path over the rank's batch: 2^24 cold reachable targets per
+          GPU from the neutral pose, reference defaults (BASELINE cfg5 sweep point; the cfg2
+          batch of 4096 is a latency case and is reported under "cfg2").  Weak scaling.
+  value   converged solves of all ranks / max-over-ranks device time, inputs resident in HBM
+  e2e     same metric through the host-buffer C-ABI operator (pnp_ik_solve_host_f32): pinned host
+          inputs -> H2D -> kernel -> D2H of every IKResult field, all inside the timed region
+  roofline     IK kernel vs the FP32 CUDA-core peak (measured live by pnp_probe_fp32_peak;
+               MEASURED_PEAKS.json has no FP32 entry) - the schema's "hbm"/"tensor" do not apply
+  reward       the second half of the metric (HER reward evals/s, cfg3: 16 777 216 rows, FP32
+               storage, 64 B/row) with its own value / e2e / HBM roofline / cpu_baseline
+  cpu_baseline the C oracle port on all host cores over a bounded sample of the same workload
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+IK_FLOP_PER_ITER = 500.0  # algorithmic FLOP per DLS iteration (position mode)
+IK_FLOP_PER_SOLVE = 216.0  # + one FK per solve
+REWARD_BYTES_PER_ROW = 64.0  # 60 B in + 4 B out (FP32 storage)
+LOG2_N_IK = 24
+LOG2_N_REWARD = 24
+REWARD_KEYS = ("achieved_goal", "desired_goal", "ee_pos", "ee_quat", "fingers_width", "task_index")
+NEUTRAL = np.array([0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79])
+
+
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample NVML during the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, gpu_index: int, period_s: float = 0.005):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.idx < len(ids) and ids[self.idx].isdigit():
+                    phys = int(ids[self.idx])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self._nvml = None
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            return self
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def _run(self):
+        nv = self._nvml
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self._h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        sm = self.sm
+        # "under load": drop idle-clock samples from before the first kernel ramps the clocks
+        loaded = [x for x in sm if self.max_mhz and x >= 0.5 * self.max_mhz] or sm
+        return {
+            "sm_mhz": int(statistics.median(loaded)) if loaded else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(sm),
+        }
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json (burst copy)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port) - used only as the reported baseline / reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_ik_setup():
+    from oracle import c_oracle, mj_oracle
+
+    c_oracle.build()
+    asset = os.path.join(ROOT, "mujoco_panda_pnp_b200", "assets", "panda_shelf_kinematic.xml")
+    model = mj_oracle.MjModel.from_xml_path(asset)
+    return c_oracle, c_oracle.chain_from_model(model), model
+
+
+def cpu_ik_targets(c_oracle, chain, model, n, seed=1234):
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(model.jnt_range[:7, 0], model.jnt_range[:7, 1], size=(n, 7))
+    return c_oracle.fk_jac(chain, q, nthreads=host_cores())[0]
+
+
+def cpu_ik_baseline(budget_s: float = 12.0) -> dict:
+    """Bounded sample of the bench workload on all host cores (C oracle port, FP64)."""
+    c_oracle, chain, model = cpu_ik_setup()
+    cores = host_cores()
+    calib = cpu_ik_targets(c_oracle, chain, model, 4096 * max(1, cores // 4))
+    t0 = time.perf_counter()
+    c_oracle.ik_solve(chain, calib, NEUTRAL, nthreads=cores)
+    rate = len(calib) / (time.perf_counter() - t0)
+    n = int(min(max(rate * budget_s, 8192), 1 << 22))
+    targets = cpu_ik_targets(c_oracle, chain, model, n)
+    t0 = time.perf_counter()
+    r = c_oracle.ik_solve(chain, targets, NEUTRAL, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {
+        "value": float(r["converged"].sum() / dt), "unit": "solves/s", "cores": cores, "kind": "port",
+        "sample": f"{n} cold targets (same generator as the GPU batch), {dt:.1f} s, FP64 C restatement of "
+                  "ik_solver.py:50-101 without mj_forward's collision stages (faster than the real reference)",
+        "mean_iterations": float(r["iterations"].mean()),
+    }
+
+
+def cpu_reward_rows(n, seed=0):
+    import torch
+
+    from mujoco_panda_pnp_b200 import synthetic
+
+    rows = synthetic.reward_rows(n, seed=seed, device="cpu", dtype=torch.float32)
+    return [rows[k].double().numpy() if rows[k].dtype != torch.int32 else rows[k].numpy() for k in REWARD_KEYS]
+
+
+def cpu_reward_baseline(budget_s: float = 8.0) -> dict:
+    from oracle import c_oracle
+
+    c_oracle.build()
+    cores = host_cores()
+    n = 1 << 22
+    h = cpu_reward_rows(n)
+    c_oracle.reward(*[x[: 1 << 16] for x in h], nthreads=cores)
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s or reps == 0:
+        c_oracle.reward(*h, reward_type="dense", nthreads=cores)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": float(n * reps / dt), "unit": "rows/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x {n} rows (first 2^22 of the cfg3 generator), {dt:.1f} s, FP64 C restatement of "
+                      "panda_env.py:205-245"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    c_oracle, chain, model = cpu_ik_setup()
+    cores = host_cores()
+    calib = cpu_ik_targets(c_oracle, chain, model, 8192)
+    t0 = time.perf_counter()
+    c_oracle.ik_solve(chain, calib, NEUTRAL, nthreads=cores)
+    rate = len(calib) / (time.perf_counter() - t0)
+    budget = min(3.0, 150.0 / max(1, args.steps + args.warmup))  # whole run within a few minutes
+    n = int(min(max(rate * budget, 4096), 1 << 22))
+    targets = cpu_ik_targets(c_oracle, chain, model, n)
+    for _ in range(args.warmup):
+        c_oracle.ik_solve(chain, targets, NEUTRAL, nthreads=cores)
+    conv = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = c_oracle.ik_solve(chain, targets, NEUTRAL, nthreads=cores)
+        conv += int(r["converged"].sum())
+    dt = time.perf_counter() - t0
+    value = conv / dt
+    rw = cpu_reward_baseline(budget_s=5.0)
+    sample = (f"each step = {n} cold reachable targets from neutral (bounded sample of the 2^{LOG2_N_IK}-per-GPU "
+              f"workload), {cores} threads")
+    line = {
+        "impl": "reference", "metric": "panda_ik_converged_solves_per_s", "value": value, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg5 cold IK, 2^{LOG2_N_IK} reachable targets per GPU from the neutral pose, "
+                               "max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reward": {"metric": "her_reward_evals_per_s", "value": rw["value"], "unit": "rows/s", "cpu_baseline": rw},
+        "note": "reference arm = oracle port (C, FP64, all host threads): mujoco is not installable in this image, "
+                "see DESIGN.md; it omits mj_forward's collision/constraint work and is faster than the real reference",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def cuda_time_steps(fn, steps, torch):
+    """Per-launch CUDA-event durations (ms) on the current stream."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for e0, e1 in evs:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    total = evs[0][0].elapsed_time(evs[-1][1])  # whole timed region, first launch to last completion
+    return total, [e0.elapsed_time(e1) for e0, e1 in evs]
+
+
+def run_ours(args) -> int:
+    import torch
+
+    from mujoco_panda_pnp_b200 import KinematicTree, _lib, engine, synthetic
+    from mujoco_panda_pnp_b200 import distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    rank, local_rank, world = D.init_process_group("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    tree = KinematicTree.from_mjcf()
+    specialized = engine.set_tree(tree)
+    K, W = args.steps, args.warmup
+
+    # ---------------- inputs, resident in HBM (generated per rank on device) ----------------
+    n_ik = 1 << args.log2_n_ik
+    qstar = synthetic.random_joint_configs(n_ik, tree.lower, tree.upper, seed=1234 + rank, device=dev)
+    targets = engine.fk_jac(qstar, want_quat=False, want_jac=False)[0]
+    del qstar
+    neutral = torch.tensor(NEUTRAL, dtype=torch.float32, device=dev)
+    params = engine.ik_params()
+    ik_counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    # preallocated outputs (allocation is not part of a step)
+    ik_out = dict(q=torch.empty((n_ik, 7), device=dev), fpos=torch.empty((n_ik, 3), device=dev),
+                  err=torch.empty(n_ik, device=dev), it=torch.empty(n_ik, dtype=torch.int32, device=dev),
+                  fl=torch.empty(n_ik, dtype=torch.uint8, device=dev))
+    import ctypes
+
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def ik_step(counters=None):
+        _lib.check(lib.pnp_ik_solve_f32(targets.data_ptr(), neutral.data_ptr(), 0, n_ik, ctypes.byref(params),
+                                        ik_out["q"].data_ptr(), ik_out["fpos"].data_ptr(), ik_out["err"].data_ptr(),
+                                        ik_out["it"].data_ptr(), ik_out["fl"].data_ptr(),
+                                        counters.data_ptr() if counters is not None else None, stream), "ik")
+
+    n_rw = 1 << args.log2_n_reward
+    rows = synthetic.reward_rows(n_rw, seed=rank, device=dev, dtype=torch.float32)
+    rw_args = [rows[k] for k in REWARD_KEYS]
+    rw_params = engine.reward_params("dense")
+    rw_out = torch.empty(n_rw, dtype=torch.float32, device=dev)
+    rw_counters = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def rw_step(counters=None):
+        engine.reward(*rw_args, rw_params, want_success=False, counters=counters, out=rw_out)
+
+    fp32_peak, _ = engine.probe_fp32_peak()
+    fp32_peak = max(fp32_peak, engine.probe_fp32_peak()[0])
+    peaks = measured_peaks()
+
+    sampler = ClockSampler(local_rank).start()
+
+    # ---------------- IK: device-resident timing ------------------------------------------
+    for _ in range(W):
+        ik_step()
+    ik_step(ik_counters)  # one counted pass (also untimed): per-step workload statistics
+    torch.cuda.synchronize()
+    D.barrier()
+    launches0 = lib.pnp_launch_count()
+    ik_total, t_ik = cuda_time_steps(ik_step, K, torch)
+    launches_ik = lib.pnp_launch_count() - launches0
+    D.barrier()
+    ik_ms_total = D.reduce_max(ik_total, dev)
+    ik_kernel_ms = sum(t_ik) / K
+    c = D.reduce_counters(ik_counters).cpu().numpy()
+    c_local = ik_counters.cpu().numpy()
+    ik_value = float(c[1]) * K / (ik_ms_total * 1e-3)
+    ik_flop_launch = IK_FLOP_PER_ITER * float(c_local[3]) + IK_FLOP_PER_SOLVE * float(c_local[0])
+    ik_tflops = ik_flop_launch / (ik_kernel_ms * 1e-3) / 1e12
+
+    # ---------------- reward: device-resident timing --------------------------------------
+    for _ in range(W):
+        rw_step()
+    rw_step(rw_counters)
+    torch.cuda.synchronize()
+    D.barrier()
+    rw_total, t_rw = cuda_time_steps(rw_step, K, torch)
+    D.barrier()
+    rw_ms_total = D.reduce_max(rw_total, dev)
+    rw_kernel_ms = sum(t_rw) / K
+    rw_value = float(n_rw) * world * K / (rw_ms_total * 1e-3)
+    rw_gbs = REWARD_BYTES_PER_ROW * n_rw / (rw_kernel_ms * 1e-3) / 1e9
+
+    # ---------------- e2e: host buffers through the C-ABI host operators --------------------
+    h_targets = targets.cpu().pin_memory()
+    h_neutral = NEUTRAL.astype(np.float32)
+    h_out = dict(q=torch.empty((n_ik, 7)).pin_memory().numpy(), final_pos=torch.empty((n_ik, 3)).pin_memory().numpy(),
+                 pos_error=torch.empty(n_ik).pin_memory().numpy(),
+                 iterations=torch.empty(n_ik, dtype=torch.int32).pin_memory().numpy(),
+                 flags=torch.empty(n_ik, dtype=torch.uint8).pin_memory().numpy())
+    Ke = max(3, min(K, 10))
+    for _ in range(2):
+        engine.ik_solve_host(h_targets, h_neutral, params, out=h_out)
+    D.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    conv_e2e = 0
+    for _ in range(Ke):
+        r = engine.ik_solve_host(h_targets, h_neutral, params, out=h_out)  # blocks until outputs are on the host
+        conv_e2e += int(r["counters"][1])
+    ik_e2e_s = D.reduce_max(time.perf_counter() - t0, dev)
+    conv_e2e_total = int(D.reduce_counters(torch.tensor([conv_e2e, 0, 0, 0], dtype=torch.int64, device=dev))[0])
+    ik_e2e = conv_e2e_total / ik_e2e_s
+    ik_h2d = n_ik * 12 + 28
+    ik_d2h = n_ik * (28 + 12 + 4 + 4 + 1) + 32
+
+    h_rows = [rows[k].cpu().pin_memory() for k in REWARD_KEYS]
+    h_rw = torch.empty(n_rw, dtype=torch.float32).pin_memory().numpy()
+    for _ in range(2):
+        engine.reward_host(*h_rows, rw_params, want_success=False, out=h_rw)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        engine.reward_host(*h_rows, rw_params, want_success=False, out=h_rw)
+    rw_e2e_s = D.reduce_max(time.perf_counter() - t0, dev)
+    rw_e2e = n_rw * world * Ke / rw_e2e_s
+
+    # ---------------- side configs (rank 0 only, short) ---------------------------------
+    side = {}
+    if rank == 0:
+        t4096 = targets[:4096].contiguous()
+        f = lambda: engine.ik_solve(t4096, neutral, params)  # noqa: E731
+        for _ in range(3):
+            f()
+        _, ts = cuda_time_steps(f, 20, torch)
+        side["cfg2"] = {"workload": "4096 cold targets, 1 launch", "ms_per_launch": statistics.median(ts),
+                        "solves_per_s": 4096 / (statistics.median(ts) * 1e-3)}
+        n_env = 1 << 20
+        w = synthetic.waypoint_envs(n_env, seed=0, device=dev)
+        cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+        engine.ik_waypoints(w["q_start"], w["goal"], 50, params, counters=cnt)
+        torch.cuda.synchronize()
+        cw = cnt.cpu().numpy()
+        _, ts = cuda_time_steps(lambda: engine.ik_waypoints(w["q_start"], w["goal"], 50, params), 3, torch)
+        side["cfg4"] = {"workload": "2^20 envs x 50 warm-started waypoint solves, 1 launch",
+                        "ms_per_launch": min(ts), "warm_solves_per_s": float(cw[0]) / (min(ts) * 1e-3),
+                        "mean_iterations": float(cw[3]) / max(1.0, float(cw[0]))}
+    clocks = sampler.stop()
+
+    # ---------------- CPU baselines (rank 0, N=1 only) ----------------------------------
+    cpu_ik = cpu_rw = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_ik = cpu_ik_baseline()
+        cpu_rw = cpu_reward_baseline()
+    D.barrier()
+
+    if rank == 0:
+        line = {
+            "metric": "panda_ik_converged_solves_per_s", "value": ik_value, "unit": "solves/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ik_ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"cfg5 cold IK, 2^{args.log2_n_ik} reachable targets per GPU from the neutral pose, "
+                            "max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1",
+                "l2_hygiene": f"inputs+outputs per step {n_ik * 61 / 1e6:.0f} MB (IK) / {n_rw * 64 / 1e6:.0f} MB (reward) "
+                              "> 126 MB L2, no flush needed",
+                "kinematics": "specialized" if specialized else "generic",
+                "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
+                "parallelism": f"batch-index shards x{world}, NCCL all_reduce of 4 counters",
+            },
+            "e2e": {"value": ik_e2e, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": ik_d2h,
+                    "steps": Ke, "api": "pnp_ik_solve_host_f32 (pinned host buffers, 3-stream chunk pipeline)"},
+            "gpu_launches": int(launches_ik),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ik_tflops / fp32_peak, "traffic": None,
+                "kernel": "ik_solve_kernel<float,SpecKin>" if specialized else "ik_solve_kernel<float,GenericKin>",
+                "kernel_ms": ik_kernel_ms,
+                "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json)",
+                "algorithmic": f"{IK_FLOP_PER_ITER:.0f} FLOP x iterations + {IK_FLOP_PER_SOLVE:.0f} per solve (SURVEY 8d)",
+            },
+            "cpu_baseline": cpu_ik,
+            "reward": {
+                "metric": "her_reward_evals_per_s", "value": rw_value, "unit": "rows/s",
+                "workload": f"cfg3 dense reward, 2^{args.log2_n_reward} HER-relabelled rows per GPU, FP32 storage",
+                "ms_per_step": rw_ms_total / K,
+                "e2e": {"value": rw_e2e, "unit": "rows/s", "h2d_bytes_per_step": n_rw * 60, "d2h_bytes_per_step": n_rw * 4,
+                        "api": "pnp_reward_host_f32"},
+                "roofline": {"bound": "hbm", "achieved": rw_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": rw_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": "reward_kernel<float,true>",
+                             "kernel_ms": rw_kernel_ms, "peak_source": peaks["source"],
+                             "algorithmic": "64 B/row (60 in + 4 out)"},
+                "cpu_baseline": cpu_rw,
+                "threshold_adjacent_rows": int(rw_counters[3].item()),
+            },
+            **side,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--log2-n-ik", type=int, default=LOG2_N_IK)
+    ap.add_argument("--log2-n-reward", type=int, default=LOG2_N_REWARD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

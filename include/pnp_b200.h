@@ -132,6 +132,13 @@ int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double
 int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err,
                      int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
+/* Same solve with PACKED outputs (the fast path: 3 x 128-bit stores per query instead of 13):
+ *   out_q8  [n][8] float = q0..q6, pos_error
+ *   out_aux4[n][4] float = final_pos xyz, then a 32-bit word (iterations | flags << 24)
+ * Both 16-byte aligned.  n < 2^31 per call for all IK entry points. */
+int pnp_ik_solve_packed_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                            const PnpIkParams* params, float* out_q8, float* out_aux4,
+                            unsigned long long* counters, void* stream);
 int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err,
                      int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
@@ -175,6 +182,10 @@ int pnp_ik_solve_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_
                           int32_t q_init_stride, int64_t n, const PnpIkParams* params, float* q_out,
                           float* final_pos, float* pos_err, int32_t* iters, uint8_t* flags,
                           unsigned long long* counters);
+/* Packed-output variant (see pnp_ik_solve_packed_f32): out_q8[n][8], out_aux4[n][4] on the host. */
+int pnp_ik_solve_packed_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_init,
+                                 int32_t q_init_stride, int64_t n, const PnpIkParams* params,
+                                 float* out_q8, float* out_aux4, unsigned long long* counters);
 int pnp_reward_host_f32(PnpHostCtx* ctx, const float* ag, const float* dg, const float* ee_pos,
                         const float* ee_quat, const float* width, const int32_t* task_index,
                         int64_t n, const PnpRewardParams* params, float* reward, float* is_success,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "pnp_fk_jac_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int32, _P]),
     "pnp_fk_jac_f64": (c_int, [_P, c_int64, _P, _P, _P, c_int32, _P]),
     "pnp_ik_solve_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
+    "pnp_ik_solve_packed_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P]),
     "pnp_ik_solve_f64": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_ik_waypoints_f32": (c_int, [_P, _P, c_int64, c_int32, c_double, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),
     "pnp_reward_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "pnp_host_ctx_create": (c_int, [POINTER(c_void_p), c_int64]),
     "pnp_host_ctx_destroy": (c_int, [c_void_p]),
     "pnp_ik_solve_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),
+    "pnp_ik_solve_packed_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P]),
     "pnp_reward_host_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P]),
     "pnp_reward_host_f64": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P]),
     "pnp_probe_fp32_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),

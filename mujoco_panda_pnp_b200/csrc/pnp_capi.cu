@@ -1,6 +1,7 @@
 // C ABI of libpnp_b200.so (declared in include/pnp_b200.h).  Host-side glue only: argument
 // checks, constant-memory upload, launch geometry, the host-buffer pipeline.
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <new>
 #include <cstdio>
@@ -20,7 +21,7 @@ struct DeviceState {
   bool specialized = false;
   PnpTree tree{};
   int sm_count = 0;
-  unsigned long long* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
+  unsigned* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
   unsigned ticket_seq = 0;
   int occ_ik[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -152,24 +153,42 @@ int fk_jac_impl(const T* q, int64_t n, T* pos, T* quat, T* jac, int32_t kinemati
   return PNP_OK;
 }
 
-template <typename T, typename Kin>
-int ik_occupancy(DeviceState* s, int slot, int block) {
+template <typename T, typename Kin, bool kPacked>
+int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t st) {
+  const int slot = (sizeof(T) == 8 ? 4 : 0) + (Kin::kSpecialized ? 2 : 0) + (kPacked ? 1 : 0);
   if (s->occ_ik[slot] == 0) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_kernel<T, Kin>, block, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_kernel<T, Kin, kPacked>,
+                                                                  pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
-  return s->occ_ik[slot];
+  // Persistent grid: every resident lane keeps pulling queries.  Small batches use 32-lane
+  // blocks so the few warps spread over as many SMs as possible (latency bound).
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int grid = small ? (int)((a.n + 31u) / 32u) : grid_for(a.n, block, s->sm_count, s->occ_ik[slot]);
+  // queries reserved per ticket atomic: ~1/16 of a warp's share, within [32, 256]
+  pnp::IkArgs<T> args = a;
+  const long long warps = (long long)grid * (block / 32);
+  long long chunk = (long long)a.n / (warps * 16);
+  chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : chunk);
+  args.chunk = (unsigned)(chunk & ~31ll);
+  pnp::ik_solve_kernel<T, Kin, kPacked><<<grid, block, 0, st>>>(args);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
 }
 
-template <typename T>
+template <typename T, bool kPacked>
 int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int64_t n, const PnpIkParams* params,
                   T* q_out, T* final_pos, T* pos_err, int32_t* iters, uint8_t* flags, unsigned long long* counters,
                   void* stream) {
   int rc = check_ik_params(params);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!targets || !q_init || !q_out))) return fail(PNP_EINVAL, "ik_solve: null pointer or negative n");
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_solve: n must be < 2^31 per call (split the batch)");
   if (q_init_stride != 0 && q_init_stride != PNP_NJOINT) return fail(PNP_EINVAL, "q_init_stride must be 0 or 7");
+  if (kPacked && n > 0 && (!final_pos || !aligned16(q_out) || !aligned16(final_pos)))
+    return fail(PNP_EINVAL, "ik_solve_packed: out_q8 / out_aux must be non-null and 16-byte aligned");
   DeviceState* s;
   if ((rc = current_state(&s))) return rc;
   bool spec;
@@ -177,37 +196,45 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   if (n == 0) return PNP_OK;
   cudaStream_t st = (cudaStream_t)stream;
 
-  unsigned long long* ticket;
+  unsigned* ticket;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
   }
-  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
 
   pnp::IkArgs<T> a;
-  a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = n;
+  a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
   a.counters = counters; a.ticket = ticket;
-
-  // Persistent grid: every resident lane keeps pulling queries.  Small batches use 32-lane
-  // blocks so the few warps spread over as many SMs as possible (latency bound).
-  const int slot = (sizeof(T) == 8 ? 2 : 0) + (spec ? 1 : 0);
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  const int block = small ? 32 : pnp::IK_BLOCK;
-  int grid;
-  if (spec) {
-    const int occ = ik_occupancy<T, pnp::SpecKin>(s, slot, pnp::IK_BLOCK);
-    grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
-    pnp::ik_solve_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
-  } else {
-    const int occ = ik_occupancy<T, pnp::GenericKin>(s, slot, pnp::IK_BLOCK);
-    grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
-    pnp::ik_solve_kernel<T, pnp::GenericKin><<<grid, block, 0, st>>>(a);
-  }
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
-  return PNP_OK;
+  return spec ? launch_ik<T, pnp::SpecKin, kPacked>(s, a, small, st)
+              : launch_ik<T, pnp::GenericKin, kPacked>(s, a, small, st);
+}
+
+// Smallest double s >= 0 with sqrt(s) >= t (sqrt is correctly rounded, hence monotone): the
+// reference's `sqrt(s) < t` is exactly `s < sqrt_preimage(t)`.
+double sqrt_preimage(double t) {
+  if (!(t > 0.0)) return 0.0;  // sqrt(s) < t is never true for t <= 0 (or NaN)
+  if (std::isinf(t)) return t;
+  double s = t * t;
+  while (s > 0.0 && std::sqrt(s) >= t) s = std::nextafter(s, -INFINITY);
+  while (std::sqrt(s) < t) s = std::nextafter(s, INFINITY);
+  return s;
+}
+
+// [lo, hi) in the squared domain such that  |fl(d - thr)| < tol  <=>  lo <= d*d(rounded sum) < hi
+void adjacency_window(double thr, double tol, double* lo, double* hi) {
+  if (!(tol > 0.0) || !(thr > 0.0)) { *lo = INFINITY; *hi = -INFINITY; return; }
+  double d_lo = thr - tol, d_hi = thr + tol;
+  // walk to the exact first / last doubles satisfying the reference-style predicate
+  for (int i = 0; i < 64 && std::fabs(std::nextafter(d_lo, -INFINITY) - thr) < tol; ++i) d_lo = std::nextafter(d_lo, -INFINITY);
+  for (int i = 0; i < 64 && !(std::fabs(d_lo - thr) < tol); ++i) d_lo = std::nextafter(d_lo, INFINITY);
+  for (int i = 0; i < 64 && std::fabs(std::nextafter(d_hi, INFINITY) - thr) < tol; ++i) d_hi = std::nextafter(d_hi, INFINITY);
+  for (int i = 0; i < 64 && !(std::fabs(d_hi - thr) < tol); ++i) d_hi = std::nextafter(d_hi, -INFINITY);
+  *lo = sqrt_preimage(d_lo);
+  *hi = sqrt_preimage(std::nextafter(d_hi, INFINITY));
 }
 
 pnp::RewardConst make_reward_const(const PnpRewardParams* p) {
@@ -215,9 +242,17 @@ pnp::RewardConst make_reward_const(const PnpRewardParams* p) {
   k.sparse = p->sparse;
   k.n_tasks = (double)p->n_tasks;
   k.h0 = p->initial_object_height;
-  k.thr = p->distance_threshold;
   k.high_z = p->high_pick_z;
-  k.tol = p->threshold_report_tol;
+  k.s_place_lt = sqrt_preimage(p->distance_threshold);
+  k.s_reach_lt = sqrt_preimage(0.05);
+  adjacency_window(p->distance_threshold, p->threshold_report_tol, &k.s_place_adj_lo, &k.s_place_adj_hi);
+  adjacency_window(0.05, p->threshold_report_tol, &k.s_reach_adj_lo, &k.s_reach_adj_hi);
+  // (double)w < 0.045  <=>  w < W, W = smallest float whose value is >= 0.045
+  float w = (float)0.045;
+  if ((double)w < 0.045) w = std::nextafterf(w, INFINITY);
+  k.width_lt_f32 = w;
+  k.n_bonus = p->n_tasks < 16 ? p->n_tasks : 16;
+  for (int i = 0; i < 16; ++i) k.bonus[i] = 0.5 * ((double)i / (double)p->n_tasks);  // panda_env.py:244
   return k;
 }
 
@@ -284,7 +319,16 @@ int pnp_set_tree(const PnpTree* t) {
   fill_tree_dev(*t, &td);
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f32, &tf, sizeof tf));
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
-  if (!s->tickets) CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned long long)));
+  if (!s->tickets) {
+    CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned)));
+    // (sin, cos)(k * 2*pi/1024) for the FP32 IK kernels' table trig, evaluated in FP64
+    static float2 tab[pnp::kTrigTabN];
+    for (int k = 0; k < pnp::kTrigTabN; ++k) {
+      const double x = (double)k * (6.283185307179586476925286766559 / pnp::kTrigTabN);
+      tab[k] = make_float2((float)std::sin(x), (float)std::cos(x));
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(pnp::g_trig_tab, tab, sizeof tab));
+  }
   s->tree = *t;
   s->have_tree = true;
   s->specialized = tree_matches_spec(*t);
@@ -331,14 +375,20 @@ int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double
 int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err, int32_t* iters,
                      uint8_t* flags, unsigned long long* counters, void* stream) {
-  return ik_solve_impl<float>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters, flags,
-                              counters, stream);
+  return ik_solve_impl<float, false>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
+                                     flags, counters, stream);
+}
+int pnp_ik_solve_packed_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                            const PnpIkParams* params, float* out_q8, float* out_aux4,
+                            unsigned long long* counters, void* stream) {
+  return ik_solve_impl<float, true>(targets, q_init, q_init_stride, n, params, out_q8, out_aux4, nullptr, nullptr,
+                                    nullptr, counters, stream);
 }
 int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err, int32_t* iters,
                      uint8_t* flags, unsigned long long* counters, void* stream) {
-  return ik_solve_impl<double>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters, flags,
-                               counters, stream);
+  return ik_solve_impl<double, false>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
+                                      flags, counters, stream);
 }
 
 int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int32_t n_steps, double step_size,

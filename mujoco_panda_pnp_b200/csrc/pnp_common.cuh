@@ -43,6 +43,55 @@ __device__ __forceinline__ const TreeDev<double>& ctree<double>() { return c_tre
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+
+// ---------------------------------------------------------------------------------------------
+// Trig for the IK inner loop.  FP32: table + second-order correction.  x = k*delta + r with
+// delta = 2*pi/1024, k = rint(x/delta) by magic-number rounding, r by a 2-term Cody-Waite
+// reduction (|r| <= delta/2 = 3.07e-3), (sin,cos)(k*delta) from a 1024-entry float2 table held
+// in shared memory, then sin r ~ r (error r^3/6 = 4.8e-9), cos r ~ 1 - r^2/2:
+//     sin x = sk + (ck*r - sk*h),  cos x = ck - (sk*r + ck*h),  h = r*r/2
+// 12 instructions for the pair (sincosf: ~27 plus a Payne-Hanek branch), no F2I/I2F, no state.
+// Max abs error 9.1e-8 (1.5 ulp), rms 2.5e-8 for |x| < 2.5e4 rad, measured against float64
+// (tools/check_trig.py).  The magic-number quadrant needs |x| * 163 < 2^22: the FP32 IK kernels
+// document |q| < 2.5e4 rad as their domain (FP64 kernels call sincos()).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrigTabN = 1024;
+__device__ float2 g_trig_tab[kTrigTabN];  // (sin, cos)(k * 2*pi/1024), filled by pnp_set_tree
+
+template <typename T>
+struct Trig;
+
+template <>
+struct Trig<float> {
+  static constexpr bool kUsesTable = true;
+  const float2* tab;  // shared-memory copy of g_trig_tab
+  __device__ __forceinline__ void operator()(float x, float* s, float* c) const {
+    const float t = fmaf(x, 162.974655f, 12582912.0f);
+    const int ji = __float_as_int(t);
+    const float k = t - 12582912.0f;
+    float r = fmaf(k, -0.0061359233222901821f, x);
+    r = fmaf(k, 1.7074761049507003e-10f, r);
+    const float2 e = tab[ji & (kTrigTabN - 1)];
+    const float h = (0.5f * r) * r;
+    *s = fmaf(e.y, r, fmaf(-e.x, h, e.x));
+    *c = fmaf(-e.x, r, fmaf(-e.y, h, e.y));
+  }
+};
+
+template <>
+struct Trig<double> {
+  static constexpr bool kUsesTable = false;
+  const float2* tab;  // unused
+  __device__ __forceinline__ void operator()(double x, double* s, double* c) const { sincos(x, s, c); }
+};
+
+// Cooperative load of the trig table into shared memory (call by every thread of the block).
+__device__ __forceinline__ void load_trig_table(float2* s_tab) {
+  const float4* src = reinterpret_cast<const float4*>(g_trig_tab);
+  float4* dst = reinterpret_cast<float4*>(s_tab);
+  for (int i = threadIdx.x; i < kTrigTabN / 2; i += blockDim.x) dst[i] = src[i];
+}
+
 __device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
@@ -237,10 +286,10 @@ struct IkConst {
 
 template <typename T, typename Kin>
 __device__ __forceinline__ void ik_eval_and_step(const T (&q)[NJ], const T (&tgt)[3], const IkConst<T>& k,
-                                                 T (&p)[3], T& n2, T (&qn)[NJ]) {
+                                                 const Trig<T>& trig, T (&p)[3], T& n2, T (&qn)[NJ]) {
   T s[NJ], c[NJ];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) sincos_t(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
+  for (int i = 0; i < NJ; ++i) trig(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
   T J[21];
   Kin::template fk_jacp<T>(s, c, p, J);
   const T e0 = tgt[0] - p[0], e1 = tgt[1] - p[1], e2 = tgt[2] - p[2];

@@ -53,101 +53,153 @@ __global__ void __launch_bounds__(128) fk_jac_kernel(const T* __restrict__ q, lo
 // query.  Control flow per query is exactly ik_solver.py:57-101:
 //   pass i (< max_iters): FK -> test -> (converged: iterations=i+1, stop) | update, i+1
 //   pass i == max_iters : FK only -> final_pos, converged=false, iterations=max_iters
+//
+// Output layouts.  kPacked = false: the five separate arrays of pnp_ik_solve_*.  kPacked = true
+// (pnp_ik_solve_packed_f32): two 16-byte aligned records per query,
+//   out_q8  [n][8] = q0..q6, pos_error            (2 x 128-bit stores)
+//   out_aux [n][4] = final_pos xyz, bits(iterations | flags << 24)   (1 x 128-bit store)
+// which cuts the per-finish store sequence from 13 STG.32 to 3 STG.128.
 // =============================================================================================
 template <typename T>
 struct IkArgs {
   const T* targets;
   const T* q_init;
   int q_init_stride;  // 0 = broadcast
-  long long n;
+  unsigned n;         // < 2^31 (checked on the host): 32-bit index arithmetic in the hot loop
   IkConst<T> k;
-  T* q_out;
-  T* final_pos;
+  T* q_out;           // packed: out_q8
+  T* final_pos;       // packed: out_aux
   T* pos_err;
   int32_t* iters;
   uint8_t* flags;
   unsigned long long* counters;
-  unsigned long long* ticket;  // zeroed before launch
+  unsigned* ticket;   // zeroed before launch
+  unsigned chunk;     // queries a warp reserves per ticket atomic (>= 32)
 };
 
-template <typename T, typename Kin>
+// convergence test (ik_solver.py:61-64).  FP64 follows the reference literally (sqrt, then
+// compare); FP32 compares squared norms and takes the sqrt only when a lane finishes.
+__device__ __forceinline__ bool below_thresh(double n2, const IkConst<double>& k) { return sqrt(n2) < k.pos_thresh; }
+__device__ __forceinline__ bool below_thresh(float n2, const IkConst<float>& k) { return n2 < k.pos_thresh * k.pos_thresh; }
+__device__ __forceinline__ double finish_sqrt(double n2) { return sqrt(n2); }
+__device__ __forceinline__ float finish_sqrt(float n2) { return n2 > 0.0f ? n2 * rsqrtf(n2) : 0.0f; }
+
+template <typename T, typename Kin, bool kPacked>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) T s_q0[8];  // broadcast q_init: refills read it from shared memory
+  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
+  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  if (a.q_init_stride == 0 && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
+  __syncthreads();
+  const Trig<T> trig{s_tab};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+
   T q[NJ], tgt[3];
   int it = 0;
-  long long idx = -1;
+  unsigned idx = 0;
   bool active = false, exhausted = false;
-  unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
+  unsigned c_n = 0, c_conv = 0;  // per lane: < 2^31 queries
+  unsigned long long c_iter = 0;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) q[i] = T(0);
   tgt[0] = tgt[1] = tgt[2] = T(0);
+
+  // Warp-local pool of reserved query indices [pool_next, pool_end): one ticket atomic reserves
+  // a.chunk consecutive queries, lanes then draw from the pool without touching global memory.
+  // (A per-refill atomic on the single ticket address serialises in L2 at ~1 op/clk and capped
+  // the whole kernel at ~3.3 G solves/s regardless of its instruction count.)
+  unsigned pool_next = 0, pool_end = 0;
 
   while (true) {
     // ---- refill idle lanes -------------------------------------------------------------
     const unsigned need = __ballot_sync(FULL, !active && !exhausted);
     if (need) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if (lane == (unsigned)leader) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL, base, leader);
+      const unsigned count = (unsigned)__popc(need);
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {  // warp-uniform
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
+      }
       if (!active && !exhausted) {
-        idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+        const unsigned rank = (unsigned)__popc(need & lanemask_lt);
+        idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
         if (idx < a.n) {
-          tgt[0] = a.targets[idx * 3 + 0];
-          tgt[1] = a.targets[idx * 3 + 1];
-          tgt[2] = a.targets[idx * 3 + 2];
-          const T* qi = a.q_init + (long long)a.q_init_stride * idx;
+          const T* tp = a.targets + (size_t)idx * 3u;
+          tgt[0] = tp[0]; tgt[1] = tp[1]; tgt[2] = tp[2];
+          if (a.q_init_stride == 0) {
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+            for (int i = 0; i < NJ; ++i) q[i] = s_q0[i];
+          } else {
+            const T* qi = a.q_init + (size_t)idx * NJ;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+          }
           it = 0;
           active = true;
         } else {
           exhausted = true;
         }
       }
+      if (count > avail) {
+        pool_next = fresh + (count - avail);
+        pool_end = fresh + a.chunk;
+      } else {
+        pool_next += count;
+      }
     }
     if (!__any_sync(FULL, active)) break;
 
     // ---- one DLS pass for all lanes ----------------------------------------------------
     T p[3], n2, qn[NJ];
-    ik_eval_and_step<T, Kin>(q, tgt, a.k, p, n2, qn);
-    const T err = sqrt_t(n2);                                   // ik_solver.py:61
-    const bool last = it >= a.k.max_iters;                      // loop ran out (:57)
-    const bool conv = !last && (err < a.k.pos_thresh);          // :64
+    ik_eval_and_step<T, Kin>(q, tgt, a.k, trig, p, n2, qn);
+    const bool last = it >= a.k.max_iters;                      // loop ran out (ik_solver.py:57)
+    const bool conv = !last && below_thresh(n2, a.k);           // :61-64
     if (active && (conv || last)) {
+      const T err = finish_sqrt(n2);
       const int iterations = conv ? it + 1 : it;                // :66 / :85
       // :88-92  final_pos = FK(q) = p; final_error = err; success = conv && err < 2*thresh
       const bool success = conv && (err < a.k.pos_thresh * T(2));
+      const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+      if (kPacked) {
+        float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)idx * 2u;
+        oq[0] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        oq[1] = make_float4((float)q[4], (float)q[5], (float)q[6], (float)err);
+        reinterpret_cast<float4*>(a.final_pos)[idx] =
+            make_float4((float)p[0], (float)p[1], (float)p[2], __int_as_float((int)((unsigned)iterations | (fl << 24))));
+      } else {
+        T* qo = a.q_out + (size_t)idx * NJ;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) a.q_out[idx * NJ + i] = q[i];
-      if (a.final_pos) {
-        a.final_pos[idx * 3 + 0] = p[0];
-        a.final_pos[idx * 3 + 1] = p[1];
-        a.final_pos[idx * 3 + 2] = p[2];
+        for (int i = 0; i < NJ; ++i) qo[i] = q[i];
+        if (a.final_pos) {
+          T* fp = a.final_pos + (size_t)idx * 3u;
+          fp[0] = p[0]; fp[1] = p[1]; fp[2] = p[2];
+        }
+        if (a.pos_err) a.pos_err[idx] = err;
+        if (a.iters) a.iters[idx] = iterations;
+        if (a.flags) a.flags[idx] = (uint8_t)fl;
       }
-      if (a.pos_err) a.pos_err[idx] = err;
-      if (a.iters) a.iters[idx] = iterations;
-      if (a.flags) a.flags[idx] = (uint8_t)((conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u));
-      c_n += 1;
-      c_conv += conv ? 1 : 0;
-      c_iter += (unsigned long long)iterations;
+      c_n += 1u;
+      c_conv += conv ? 1u : 0u;
+      c_iter += (unsigned)iterations;
       active = false;
-    } else {
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) q[i] = qn[i];                // :81-82
-      ++it;                                                     // :85
     }
+    // unconditional update: a lane that just finished is idle and gets overwritten by the
+    // refill at the top of the next pass (:81-85)
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) q[i] = qn[i];
+    ++it;
   }
 
   if (a.counters) {
-    c_n = warp_sum(c_n);
-    c_conv = warp_sum(c_conv);
-    c_iter = warp_sum(c_iter);
+    const unsigned long long w_n = warp_sum((unsigned long long)c_n), w_conv = warp_sum((unsigned long long)c_conv),
+                             w_iter = warp_sum(c_iter);
     if (lane == 0) {
-      atomicAdd(a.counters + PNP_IK_CNT_N, c_n);
-      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, c_conv);
-      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, c_conv);  // success == converged
-      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, c_iter);
+      atomicAdd(a.counters + PNP_IK_CNT_N, w_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, w_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, w_conv);  // success == converged
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, w_iter);
     }
   }
 }
@@ -175,6 +227,10 @@ struct WaypointArgs {
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
+  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __syncthreads();
+  const Trig<T> trig{s_tab};
   unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
   for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < a.n;
        base += (long long)gridDim.x * blockDim.x) {
@@ -207,13 +263,14 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
       int it = 0;
       bool conv = false, done = !moving;
       while (__any_sync(FULL, !done)) {
-        T n2, qn[NJ];
-        ik_eval_and_step<T, Kin>(qs, tgt, a.k, p, n2, qn);
+        T n2, qn[NJ], pp[3];
+        ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
         if (!done) {
-          err = sqrt_t(n2);
           const bool last = it >= a.k.max_iters;
-          conv = !last && (err < a.k.pos_thresh);
+          conv = !last && below_thresh(n2, a.k);
           if (conv || last) {
+            err = finish_sqrt(n2);
+            p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
             it = conv ? it + 1 : it;
             done = true;
           } else {
@@ -268,47 +325,74 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
 // Arithmetic: FP64 with explicit _rn intrinsics (never contracted to FMA), the reference's
 // operation order, one final round-to-nearest cast -> bit-exact with NumPy/Python float64.
 // =============================================================================================
+// Host-prepared constants.  The two distance tests of the reference compare a correctly
+// rounded FP64 sqrt against a threshold: sqrt_rn(s) < t.  sqrt_rn is monotone, so the test is
+// EXACTLY equivalent to s < S with S = min{s : sqrt_rn(s) >= t}, found on the host by a
+// nextafter search (pnp_capi.cu: sqrt_preimage).  That removes one FP64 sqrt per row (d_place is
+// only ever compared) and makes the other one conditional (d_reach is needed as a value only
+// when it is below 0.05).  The +-1e-6 "threshold adjacent" report uses the same trick.
 struct RewardConst {
   int sparse;
+  int n_bonus;            // entries of bonus[] that are valid (task indices 0..n_bonus-1)
   double n_tasks;
-  double h0, thr, high_z, tol;
+  double h0, high_z;
+  double s_place_lt;      // d_place < distance_threshold  <=>  s_place < s_place_lt
+  double s_reach_lt;      // d_reach < 0.05                <=>  s_reach < s_reach_lt
+  double s_place_adj_lo, s_place_adj_hi;  // |d_place - thr| < tol  <=>  lo <= s_place < hi
+  double s_reach_adj_lo, s_reach_adj_hi;
+  float width_lt_f32;     // (double)w < 0.045 <=> w < width_lt_f32 for FP32 storage
+  double bonus[16];       // 0.5 * (task / n_tasks), evaluated in FP64 on the host (:244)
 };
 
-__device__ __forceinline__ double norm3_rn(double x, double y, double z) {
-  // np.linalg.norm(v, axis=-1): sqrt(add.reduce(v*v)) -> ((x*x + y*y) + z*z), separate mul/add
-  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+__device__ __forceinline__ double sumsq3_rn(double x, double y, double z) {
+  // np.linalg.norm(v, axis=-1)**2 part: add.reduce(v*v) -> ((x*x + y*y) + z*z), separate mul/add
+  return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
 }
+__device__ __forceinline__ double norm3_rn(double x, double y, double z) { return __dsqrt_rn(sumsq3_rn(x, y, z)); }
 
-__device__ __forceinline__ float reward_row(const double* ag, const double* dg, const double* ee, const double* eq,
-                                            double width, int task, const RewardConst& k, float* success,
-                                            unsigned& placed_o, unsigned& gripped_o, unsigned& adjacent_o) {
-  const double d_reach = norm3_rn(__dsub_rn(ee[0], ag[0]), __dsub_rn(ee[1], ag[1]), __dsub_rn(ee[2], ag[2]));  // :211
-  const double d_place = norm3_rn(__dsub_rn(ag[0], dg[0]), __dsub_rn(ag[1], dg[1]), __dsub_rn(ag[2], dg[2]));  // :212
-  const bool gripped = (width < 0.045) && (d_reach < 0.05);                          // :214-216
-  const bool lifted = gripped && (__dsub_rn(ag[2], k.h0) > 0.04);                    // :219
-  const bool placed = d_place < k.thr;                                               // :220
+__device__ __forceinline__ bool width_closed(float w, const RewardConst& k) { return w < k.width_lt_f32; }
+__device__ __forceinline__ bool width_closed(double w, const RewardConst&) { return w < 0.045; }
+
+// One row of panda_env.py:205-245 (+ :303-306).  TIn is the storage type of the row; every
+// value is widened to FP64 exactly, all arithmetic uses _rn intrinsics (never contracted).
+template <typename TIn>
+__device__ __forceinline__ float reward_row(const TIn* ag_, const TIn* dg_, const TIn* ee_, const TIn* eq_, TIn width,
+                                            int task, const RewardConst& k, float* success, unsigned& placed_o,
+                                            unsigned& gripped_o, unsigned& adjacent_o) {
+  const double ag0 = (double)ag_[0], ag1 = (double)ag_[1], ag2 = (double)ag_[2];
+  const double s_reach = sumsq3_rn(__dsub_rn((double)ee_[0], ag0), __dsub_rn((double)ee_[1], ag1),
+                                   __dsub_rn((double)ee_[2], ag2));                           // :211 (squared)
+  const double s_place = sumsq3_rn(__dsub_rn(ag0, (double)dg_[0]), __dsub_rn(ag1, (double)dg_[1]),
+                                   __dsub_rn(ag2, (double)dg_[2]));                           // :212 (squared)
+  const bool near = s_reach < k.s_reach_lt;                                          // d_reach < 0.05
+  const bool placed = s_place < k.s_place_lt;                                        // :220
+  const bool gripped = width_closed(width, k) && near;                               // :214-216
   *success = placed ? 1.0f : 0.0f;                                                   // :303-306
-  placed_o = placed; gripped_o = gripped;
-  adjacent_o = (fabs(__dsub_rn(d_place, k.thr)) < k.tol) || (fabs(__dsub_rn(d_reach, 0.05)) < k.tol);
+  placed_o = placed;
+  gripped_o = gripped;
+  adjacent_o = ((s_place >= k.s_place_adj_lo) && (s_place < k.s_place_adj_hi)) ||
+               ((s_reach >= k.s_reach_adj_lo) && (s_reach < k.s_reach_adj_hi));
   if (k.sparse) return placed ? -0.0f : -1.0f;                                       // :227-228
-  // need_q: HORIZONTAL_QUAT = euler2quat([-pi/2,0,0]) evaluated in float64; VERTICAL = [1,0,-0,0]
-  const bool horiz = ag[2] > k.high_z;                                               // :223
-  const double n0 = horiz ? 0.7071067811865476 : 1.0;
-  const double n1 = horiz ? -0.7071067811865475 : 0.0;
-  const double n2 = horiz ? 0.0 : -0.0;
-  double dot = __dadd_rn(__dmul_rn(eq[0], n0), __dmul_rn(eq[1], n1));
-  dot = __dadd_rn(dot, __dmul_rn(eq[2], n2));
-  dot = __dadd_rn(dot, __dmul_rn(eq[3], 0.0));
-  const double ori_err = __dsub_rn(1.0, fabs(dot));                                  // :224
-  double r = -0.003;                                                                 // :231
-  r = __dadd_rn(r, -((0.05 < d_reach) ? 0.05 : d_reach));                            // :232
+  // :231-232  reward = -0.003; reward += -min(d_reach, 0.05)
+  double r = __dadd_rn(-0.003, near ? -__dsqrt_rn(s_reach) : -0.05);
   if (gripped) {                                                                     // :234-236
+    // :223-224 need_q = HORIZONTAL [0.70710678118654757, -0.70710678118654746, 0, 0] if ag.z >
+    // high_pick_z else VERTICAL [1, 0, -0, 0]; the z / w products are +-0 for finite inputs and
+    // vanish under abs(), so only two components are widened.
+    const bool horiz = ag2 > k.high_z;
+    const double n0 = horiz ? 0.7071067811865476 : 1.0;
+    const double n1 = horiz ? -0.7071067811865475 : 0.0;
+    const double dot = __dadd_rn(__dmul_rn((double)eq_[0], n0), __dmul_rn((double)eq_[1], n1));
+    const double ori_err = __dsub_rn(1.0, fabs(dot));
     r = __dadd_rn(r, 2.0);
     r = __dadd_rn(r, __dsub_rn(1.0, ori_err));
+    if (__dsub_rn(ag2, k.h0) > 0.04) r = __dadd_rn(r, 4.0);                          // :219, :238-239
   }
-  if (lifted) r = __dadd_rn(r, 4.0);                                                 // :238-239
   if (placed) r = __dadd_rn(r, 10.0);                                                // :241-242
-  r = __dadd_rn(r, __dmul_rn(0.5, __ddiv_rn((double)task, k.n_tasks)));              // :244
+  const double bonus = ((unsigned)task < (unsigned)k.n_bonus)
+                           ? k.bonus[task]
+                           : __dmul_rn(0.5, __ddiv_rn((double)task, k.n_tasks));     // :244
+  r = __dadd_rn(r, bonus);
   return __double2float_rn(r);                                                       // :245
 }
 
@@ -402,12 +486,8 @@ __global__ void __launch_bounds__(256) reward_kernel(const RewardArgs<TIn> a) {
     float rw[R], sc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      double dag[3] = {(double)ag[r * 3], (double)ag[r * 3 + 1], (double)ag[r * 3 + 2]};
-      double ddg[3] = {(double)dg[r * 3], (double)dg[r * 3 + 1], (double)dg[r * 3 + 2]};
-      double dee[3] = {(double)ee[r * 3], (double)ee[r * 3 + 1], (double)ee[r * 3 + 2]};
-      double deq[4] = {(double)eq[r * 4], (double)eq[r * 4 + 1], (double)eq[r * 4 + 2], (double)eq[r * 4 + 3]};
       unsigned pl, gr, ad;
-      rw[r] = reward_row(dag, ddg, dee, deq, (double)wd[r], tk[r], a.k, &sc[r], pl, gr, ad);
+      rw[r] = reward_row<TIn>(ag + r * 3, dg + r * 3, ee + r * 3, eq + r * 4, wd[r], tk[r], a.k, &sc[r], pl, gr, ad);
       if (row0 + r < a.n) { c_placed += pl; c_gripped += gr; c_adj += ad; }
     }
     if (full) {

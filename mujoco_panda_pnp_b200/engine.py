@@ -9,7 +9,6 @@ tensors and go through the library's own H2D -> kernel -> D2H pipeline (``pnp_*_
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -110,25 +109,75 @@ def fk_jac(q: torch.Tensor, want_quat=True, want_jac=True, kinematics="auto"):
 # ---------------------------------------------------------------------------------------------
 # batched IK
 # ---------------------------------------------------------------------------------------------
-@dataclass
 class BatchIKResult:
-    """Batched IKResult (ik_solver.py:16-24): same fields, one row per query."""
+    """Batched IKResult (ik_solver.py:16-24): same fields, one row per query (device tensors).
 
-    success: torch.Tensor  # bool[N]
-    q: torch.Tensor  # [N,7]
-    final_pos: torch.Tensor  # [N,3]
-    pos_error: torch.Tensor  # [N]
-    iterations: torch.Tensor  # int32[N]
-    converged: torch.Tensor  # bool[N]
-    counters: Optional[torch.Tensor] = None  # uint64-as-int64[4]: n, converged, success, sum(iterations)
+    With the packed kernel ``q`` / ``final_pos`` / ``pos_error`` are views into the two output
+    buffers and ``iterations`` / ``converged`` / ``success`` are decoded lazily from the packed
+    word (iterations | flags << 24) on first access, so a solve launches exactly one kernel."""
+
+    def __init__(self, success=None, q=None, final_pos=None, pos_error=None, iterations=None, converged=None,
+                 counters=None, word=None):
+        self.q, self.final_pos, self.pos_error, self.counters = q, final_pos, pos_error, counters
+        self._success, self._iterations, self._converged, self._word = success, iterations, converged, word
+
+    @property
+    def iterations(self):
+        if self._iterations is None:
+            self._iterations = self._word & 0xFFFFFF
+        return self._iterations
+
+    @property
+    def converged(self):
+        if self._converged is None:
+            self._converged = (self._word & (1 << 24)) != 0
+        return self._converged
+
+    @property
+    def success(self):
+        if self._success is None:
+            self._success = (self._word & (2 << 24)) != 0
+        return self._success
 
     def __len__(self) -> int:
         return int(self.q.shape[0])
 
 
+class HostIKResult(dict):
+    """Host-side result of ik_solve_host: a dict whose derived entries (iterations, flags,
+    converged, success) are decoded from the packed word only when first asked for."""
+
+    def __missing__(self, key):
+        word = dict.__getitem__(self, "aux4")[:, 3].view(np.int32)
+        if key == "iterations":
+            val = word & 0xFFFFFF
+        elif key == "flags":
+            val = (word >> 24).astype(np.uint8)
+        elif key == "converged":
+            val = (word & (1 << 24)) != 0
+        elif key == "success":
+            val = (word & (2 << 24)) != 0
+        else:
+            raise KeyError(key)
+        self[key] = val
+        return val
+
+
+def unpack_ik(out_q8, out_aux4):
+    """Views into the packed IK outputs (torch tensors or NumPy arrays alike):
+    q[N,7], pos_error[N], final_pos[N,3], packed word[N] int32 (iterations | flags << 24)."""
+    word = out_aux4[:, 3].view(torch.int32) if isinstance(out_aux4, torch.Tensor) else out_aux4[:, 3].view(np.int32)
+    return out_q8[:, :7], out_q8[:, 7], out_aux4[:, :3], word
+
+
 def ik_solve(targets: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams, counters: Optional[torch.Tensor] = None,
-             want_aux: bool = True) -> BatchIKResult:
-    """Device path: targets[N,3], q_init[N,7] or [7] (cuda, same float dtype)."""
+             packed: Optional[bool] = None, out_q8: Optional[torch.Tensor] = None,
+             out_aux4: Optional[torch.Tensor] = None) -> BatchIKResult:
+    """Device path: targets[N,3], q_init[N,7] or [7] (cuda, same float dtype).
+
+    float32 uses the packed-output kernel (pnp_ik_solve_packed_f32) by default: the result fields
+    are views into two [N,8] / [N,4] buffers.  ``packed=False`` selects the separate-array entry
+    point (pnp_ik_solve_f32); float64 always uses separate arrays."""
     lib = _lib.load()
     dt = targets.dtype
     if dt not in (torch.float32, torch.float64):
@@ -146,23 +195,38 @@ def ik_solve(targets: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams, c
             raise ValueError("q_init and targets disagree on N")
         stride = 7
     dev = targets.device
-    q = torch.empty((n, 7), dtype=dt, device=dev)
-    fpos = torch.empty((n, 3), dtype=dt, device=dev) if want_aux else None
-    err = torch.empty((n,), dtype=dt, device=dev) if want_aux else None
-    iters = torch.empty((n,), dtype=torch.int32, device=dev) if want_aux else None
-    flags = torch.empty((n,), dtype=torch.uint8, device=dev)
     if counters is not None and (counters.dtype != torch.int64 or counters.numel() < 4 or not counters.is_cuda):
         raise ValueError("counters must be a CUDA int64 tensor with >= 4 elements")
-    fn = lib.pnp_ik_solve_f32 if dt == torch.float32 else lib.pnp_ik_solve_f64
+    if packed is None:
+        packed = dt == torch.float32
+    if packed and dt != torch.float32:
+        raise ValueError("packed outputs exist for float32 only")
     with torch.cuda.device(dev):
-        _lib.check(
-            fn(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q), _ptr(fpos), _ptr(err),
-               _ptr(iters), _ptr(flags), _ptr(counters), _stream()),
-            "pnp_ik_solve",
-        )
+        if packed:
+            q8 = out_q8 if out_q8 is not None else torch.empty((n, 8), dtype=dt, device=dev)
+            aux = out_aux4 if out_aux4 is not None else torch.empty((n, 4), dtype=dt, device=dev)
+            _lib.check(
+                lib.pnp_ik_solve_packed_f32(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q8),
+                                            _ptr(aux), _ptr(counters), _stream()),
+                "pnp_ik_solve_packed",
+            )
+            q, err, fpos, word = unpack_ik(q8, aux)
+            return BatchIKResult(q=q, final_pos=fpos, pos_error=err, word=word, counters=counters)
+        else:
+            q = torch.empty((n, 7), dtype=dt, device=dev)
+            fpos = torch.empty((n, 3), dtype=dt, device=dev)
+            err = torch.empty((n,), dtype=dt, device=dev)
+            iters = torch.empty((n,), dtype=torch.int32, device=dev)
+            flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+            fn = lib.pnp_ik_solve_f32 if dt == torch.float32 else lib.pnp_ik_solve_f64
+            _lib.check(
+                fn(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q), _ptr(fpos), _ptr(err),
+                   _ptr(iters), _ptr(flags), _ptr(counters), _stream()),
+                "pnp_ik_solve",
+            )
     return BatchIKResult(
-        success=(flags & 2).bool(), q=q, final_pos=fpos, pos_error=err, iterations=iters,
-        converged=(flags & 1).bool(), counters=counters,
+        success=(flags & 2) != 0, q=q, final_pos=fpos, pos_error=err, iterations=iters,
+        converged=(flags & 1) != 0, counters=counters,
     )
 
 
@@ -266,9 +330,14 @@ def _as_host(name: str, a, dtype, shape_tail) -> np.ndarray:
     return a
 
 
-def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out: Optional[dict] = None) -> dict:
-    """Host path: NumPy / CPU-tensor inputs (float32), NumPy outputs.  ``out`` may supply
-    preallocated (ideally pinned) output arrays: q, final_pos, pos_error, iterations, flags."""
+def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out: Optional[dict] = None,
+                  packed: bool = True) -> dict:
+    """Host path: NumPy / CPU-tensor inputs (float32), NumPy outputs.
+
+    packed=True (default) goes through pnp_ik_solve_packed_host_f32: the device writes two packed
+    records per query and the returned q / final_pos / pos_error / iterations are views into the
+    host copies ``out["q8"]`` [N,8] and ``out["aux4"]`` [N,4] (preallocate them pinned for full
+    copy/compute overlap).  packed=False uses the separate-array operator."""
     lib = _lib.load()
     targets = _as_host("targets", targets, np.float32, (3,))
     n = targets.shape[0]
@@ -282,12 +351,22 @@ def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out
     else:
         raise ValueError(f"q_init must have shape (7,) or ({n}, 7), got {q_init.shape}")
     out = out or {}
+    counters = np.zeros(4, dtype=np.uint64)
+    if packed:
+        q8 = out.get("q8") if out.get("q8") is not None else np.empty((n, 8), np.float32)
+        aux = out.get("aux4") if out.get("aux4") is not None else np.empty((n, 4), np.float32)
+        _lib.check(
+            lib.pnp_ik_solve_packed_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
+                                             ctypes.byref(params), _np_ptr(q8), _np_ptr(aux), _np_ptr(counters)),
+            "pnp_ik_solve_packed_host",
+        )
+        q, err, fpos, _ = unpack_ik(q8, aux)
+        return HostIKResult(q=q, final_pos=fpos, pos_error=err, q8=q8, aux4=aux, counters=counters)
     q = out.get("q") if out.get("q") is not None else np.empty((n, 7), np.float32)
     fpos = out.get("final_pos") if out.get("final_pos") is not None else np.empty((n, 3), np.float32)
     err = out.get("pos_error") if out.get("pos_error") is not None else np.empty((n,), np.float32)
     iters = out.get("iterations") if out.get("iterations") is not None else np.empty((n,), np.int32)
     flags = out.get("flags") if out.get("flags") is not None else np.empty((n,), np.uint8)
-    counters = np.zeros(4, dtype=np.uint64)
     _lib.check(
         lib.pnp_ik_solve_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
                                   ctypes.byref(params), _np_ptr(q), _np_ptr(fpos), _np_ptr(err), _np_ptr(iters),

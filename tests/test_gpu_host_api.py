@@ -18,8 +18,8 @@ def test_ik_host_pipeline_equals_device_path(cuda_lib, oracle_chain):
     targets = c_oracle.fk_jac(oracle_chain, qstar, nthreads=8)[0].astype(np.float32)
     p = engine.ik_params()
     dev = engine.ik_solve(torch.tensor(targets, device="cuda"), torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"), p)
-    for chunk in (0, 1000):  # 1 chunk / 51 chunks over 3 streams
-        r = engine.ik_solve_host(targets, NEUTRAL.astype(np.float32), p, chunk_rows=chunk)
+    for chunk, packed in ((0, True), (1000, True), (1000, False)):  # 1 chunk / 51 chunks over 3 streams
+        r = engine.ik_solve_host(targets, NEUTRAL.astype(np.float32), p, chunk_rows=chunk, packed=packed)
         np.testing.assert_array_equal(r["q"], dev.q.cpu().numpy())
         np.testing.assert_array_equal(r["iterations"], dev.iterations.cpu().numpy())
         np.testing.assert_array_equal(r["final_pos"], dev.final_pos.cpu().numpy())
@@ -29,9 +29,9 @@ def test_ik_host_pipeline_equals_device_path(cuda_lib, oracle_chain):
         assert r["counters"][3] == int(dev.iterations.sum())
     # per-query q_init through the host path + pinned, preallocated outputs
     q0 = np.clip(NEUTRAL + np.random.default_rng(0).uniform(-0.2, 0.2, (n, 7)), tree.lower, tree.upper).astype(np.float32)
-    out = dict(q=torch.empty((n, 7)).pin_memory().numpy())
+    out = dict(q8=torch.empty((n, 8)).pin_memory().numpy(), aux4=torch.empty((n, 4)).pin_memory().numpy())
     r = engine.ik_solve_host(torch.tensor(targets).pin_memory(), q0, p, chunk_rows=7777, out=out)
-    assert r["q"] is out["q"]
+    assert r["q8"] is out["q8"] and np.shares_memory(r["q"], out["q8"]) and np.shares_memory(r["final_pos"], out["aux4"])
     dev2 = engine.ik_solve(torch.tensor(targets, device="cuda"), torch.tensor(q0, device="cuda"), p)
     np.testing.assert_array_equal(r["q"], dev2.q.cpu().numpy())
     with pytest.raises(ValueError):

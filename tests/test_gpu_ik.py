@@ -179,7 +179,9 @@ def test_unreachable_targets_run_out_of_iterations(tree, oracle_chain):
                           torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"), engine.ik_params(max_iters=40))
     assert res.converged.tolist() == [False, False, True] == ref["converged"].tolist()
     assert res.iterations.tolist() == [40, 40, 7]
-    np.testing.assert_allclose(res.pos_error.cpu().numpy(), ref["pos_error"], atol=2e-6)
+    # non-converged solves end in a stretched-out (near-singular) pose after 40 clipped steps: FP32
+    # rounding is amplified there; converged solves are held to the tight tolerance elsewhere
+    np.testing.assert_allclose(res.pos_error.cpu().numpy(), ref["pos_error"], rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(res.q.double().cpu().numpy(), ref["q"], atol=1e-3)
 
 
@@ -197,7 +199,8 @@ def test_large_batch_properties(tree, oracle_chain):
     assert 0.995 < c[1] / n < 1.0 and 15.5 < c[3] / n < 16.5
     it = res.iterations
     assert int(it.min()) >= 1 and int(it.max()) == 100
-    assert bool(((it == 100) | res.converged).all()) and bool((res.pos_error[res.converged] < 1e-3).all())
+    # the FP32 kernel tests |e|^2 < thresh^2, so the reported sqrt may round onto the threshold itself
+    assert bool(((it == 100) | res.converged).all()) and bool((res.pos_error[res.converged] <= 1.0000002e-3).all())
     # final_pos is FK(q) (ik_solver.py:88): recompute with the FK kernel
     fk = engine.fk_jac(res.q, want_quat=False, want_jac=False)[0]
     assert float((fk - res.final_pos).abs().max()) < 2e-6
@@ -216,6 +219,23 @@ def test_large_batch_properties(tree, oracle_chain):
                                pos_error=res.pos_error[:m], iterations=res.iterations[:m], converged=res.converged[:m])
     flips = _compare_with_oracle(sub, ref, th, oracle_chain, 1e-3, flip_budget=32)
     print(f"iteration-count flips FP32 vs FP64 oracle: {flips}/{m}")
+
+
+def test_packed_and_separate_outputs_agree(tree):
+    """pnp_ik_solve_packed_f32 (the default) and pnp_ik_solve_f32 write the same results."""
+    n = 100_003
+    q = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=77, device="cuda")
+    targets = engine.fk_jac(q, want_quat=False, want_jac=False)[0]
+    q0 = (torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda") + 0.1 * torch.randn((n, 7), device="cuda")).contiguous()
+    for qi in (torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda"), q0):
+        a = engine.ik_solve(targets, qi, engine.ik_params(), packed=True)
+        b = engine.ik_solve(targets, qi, engine.ik_params(), packed=False)
+        assert a.q.shape == (n, 7) and a.final_pos.shape == (n, 3) and a.iterations.dtype == torch.int32
+        assert torch.equal(a.q, b.q) and torch.equal(a.final_pos, b.final_pos) and torch.equal(a.pos_error, b.pos_error)
+        assert torch.equal(a.iterations, b.iterations) and torch.equal(a.converged, b.converged)
+        assert torch.equal(a.success, b.success)
+    with pytest.raises(ValueError):
+        engine.ik_solve(targets.double(), qi.double(), engine.ik_params(), packed=True)
 
 
 def test_waypoint_sequences_vs_oracle(tree, oracle_model, oracle_chain):

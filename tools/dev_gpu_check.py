@@ -72,9 +72,7 @@ tgh = tg[:n].cpu().pin_memory() if tg.shape[0] >= n else None
 qs = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=1234, device=dev)
 tgd, _, _ = engine.fk_jac(qs, want_quat=False, want_jac=False)
 tgh = tgd.cpu().pin_memory()
-outs = dict(q=torch.empty((n, 7), dtype=torch.float32).pin_memory().numpy(), final_pos=torch.empty((n, 3)).pin_memory().numpy(),
-            pos_error=torch.empty(n).pin_memory().numpy(), iterations=torch.empty(n, dtype=torch.int32).pin_memory().numpy(),
-            flags=torch.empty(n, dtype=torch.uint8).pin_memory().numpy())
+outs = dict(q8=torch.empty((n, 8), dtype=torch.float32).pin_memory().numpy(), aux4=torch.empty((n, 4)).pin_memory().numpy())
 p = engine.ik_params()
 for _ in range(2): engine.ik_solve_host(tgh, np.array(synthetic.NEUTRAL_Q, dtype=np.float32), p, out=outs)
 t0 = time.perf_counter(); r = engine.ik_solve_host(tgh, np.array(synthetic.NEUTRAL_Q, dtype=np.float32), p, out=outs); t1 = time.perf_counter()
