@@ -10,7 +10,7 @@ Headline line (one JSON object on stdout, rank 0):
           GPU from the neutral pose, reference defaults (BASELINE cfg5 sweep point; the cfg2
           batch of 4096 is a latency case and is reported under "cfg2").  Weak scaling.
   value   converged solves of all ranks / max-over-ranks device time, inputs resident in HBM
-  e2e     same metric through the host-buffer C-ABI operator (pnp_ik_solve_host_f32): pinned host
+  e2e     same metric through the host-buffer C-ABI operator (pnp_ik_solve_packed_host_f32): pinned host
           inputs -> H2D -> kernel -> D2H of every IKResult field, all inside the timed region
   roofline     IK kernel vs the FP32 CUDA-core peak (measured live by pnp_probe_fp32_peak;
                MEASURED_PEAKS.json has no FP32 entry) - the schema's "hbm"/"tensor" do not apply
@@ -281,18 +281,15 @@ def run_ours(args) -> int:
     params = engine.ik_params()
     ik_counters = torch.zeros(4, dtype=torch.int64, device=dev)
     # preallocated outputs (allocation is not part of a step)
-    ik_out = dict(q=torch.empty((n_ik, 7), device=dev), fpos=torch.empty((n_ik, 3), device=dev),
-                  err=torch.empty(n_ik, device=dev), it=torch.empty(n_ik, dtype=torch.int32, device=dev),
-                  fl=torch.empty(n_ik, dtype=torch.uint8, device=dev))
+    ik_out = dict(q8=torch.empty((n_ik, 8), device=dev), aux4=torch.empty((n_ik, 4), device=dev))
     import ctypes
 
     stream = torch.cuda.current_stream().cuda_stream
 
     def ik_step(counters=None):
-        _lib.check(lib.pnp_ik_solve_f32(targets.data_ptr(), neutral.data_ptr(), 0, n_ik, ctypes.byref(params),
-                                        ik_out["q"].data_ptr(), ik_out["fpos"].data_ptr(), ik_out["err"].data_ptr(),
-                                        ik_out["it"].data_ptr(), ik_out["fl"].data_ptr(),
-                                        counters.data_ptr() if counters is not None else None, stream), "ik")
+        _lib.check(lib.pnp_ik_solve_packed_f32(targets.data_ptr(), neutral.data_ptr(), 0, n_ik, ctypes.byref(params),
+                                               ik_out["q8"].data_ptr(), ik_out["aux4"].data_ptr(),
+                                               counters.data_ptr() if counters is not None else None, stream), "ik")
 
     n_rw = 1 << args.log2_n_reward
     rows = synthetic.reward_rows(n_rw, seed=rank, device=dev, dtype=torch.float32)
@@ -344,10 +341,7 @@ def run_ours(args) -> int:
     # ---------------- e2e: host buffers through the C-ABI host operators --------------------
     h_targets = targets.cpu().pin_memory()
     h_neutral = NEUTRAL.astype(np.float32)
-    h_out = dict(q=torch.empty((n_ik, 7)).pin_memory().numpy(), final_pos=torch.empty((n_ik, 3)).pin_memory().numpy(),
-                 pos_error=torch.empty(n_ik).pin_memory().numpy(),
-                 iterations=torch.empty(n_ik, dtype=torch.int32).pin_memory().numpy(),
-                 flags=torch.empty(n_ik, dtype=torch.uint8).pin_memory().numpy())
+    h_out = dict(q8=torch.empty((n_ik, 8)).pin_memory().numpy(), aux4=torch.empty((n_ik, 4)).pin_memory().numpy())
     Ke = max(3, min(K, 10))
     for _ in range(2):
         engine.ik_solve_host(h_targets, h_neutral, params, out=h_out)
@@ -362,7 +356,7 @@ def run_ours(args) -> int:
     conv_e2e_total = int(D.reduce_counters(torch.tensor([conv_e2e, 0, 0, 0], dtype=torch.int64, device=dev))[0])
     ik_e2e = conv_e2e_total / ik_e2e_s
     ik_h2d = n_ik * 12 + 28
-    ik_d2h = n_ik * (28 + 12 + 4 + 4 + 1) + 32
+    ik_d2h = n_ik * (32 + 16) + 32  # packed records: q0..q6,pos_error | final_pos xyz, iterations|flags
 
     h_rows = [rows[k].cpu().pin_memory() for k in REWARD_KEYS]
     h_rw = torch.empty(n_rw, dtype=torch.float32).pin_memory().numpy()
@@ -412,20 +406,20 @@ def run_ours(args) -> int:
             "config": {
                 "workload": f"cfg5 cold IK, 2^{args.log2_n_ik} reachable targets per GPU from the neutral pose, "
                             "max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1",
-                "l2_hygiene": f"inputs+outputs per step {n_ik * 61 / 1e6:.0f} MB (IK) / {n_rw * 64 / 1e6:.0f} MB (reward) "
+                "l2_hygiene": f"inputs+outputs per step {n_ik * 60 / 1e6:.0f} MB (IK) / {n_rw * 64 / 1e6:.0f} MB (reward) "
                               "> 126 MB L2, no flush needed",
                 "kinematics": "specialized" if specialized else "generic",
                 "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
                 "parallelism": f"batch-index shards x{world}, NCCL all_reduce of 4 counters",
             },
             "e2e": {"value": ik_e2e, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": ik_d2h,
-                    "steps": Ke, "api": "pnp_ik_solve_host_f32 (pinned host buffers, 3-stream chunk pipeline)"},
+                    "steps": Ke, "api": "pnp_ik_solve_packed_host_f32 (pinned host buffers, 3-stream chunk pipeline)"},
             "gpu_launches": int(launches_ik),
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ik_tflops / fp32_peak, "traffic": None,
-                "kernel": "ik_solve_kernel<float,SpecKin>" if specialized else "ik_solve_kernel<float,GenericKin>",
+                "kernel": "ik_solve_kernel<float,SpecKin,packed>" if specialized else "ik_solve_kernel<float,GenericKin,packed>",
                 "kernel_ms": ik_kernel_ms,
                 "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json)",
                 "algorithmic": f"{IK_FLOP_PER_ITER:.0f} FLOP x iterations + {IK_FLOP_PER_SOLVE:.0f} per solve (SURVEY 8d)",
