@@ -13,6 +13,7 @@
  *   pnp_ik_solve_*         JacobianIKController.solve (ik_solver.py:35-101), batched
  *   pnp_ik_waypoints_*     the warm-started solve sequence of MoveIKSkill.reset
  *                          (skills/move.py:106-137), fixed number of waypoints per env
+ *   pnp_get_obs_*          FrankaEnv._get_obs (envs/panda_env.py:279-301) from kinematic state
  *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
  *                          (envs/panda_env.py:205-245, 303-306, 311-315), row-wise
  *   pnp_*_host             the same operators taking HOST buffers (what a Python/ctypes
@@ -170,6 +171,19 @@ int pnp_reward_f64(const double* ag, const double* dg, const double* ee_pos, con
                    unsigned long long* counters, void* stream);
 /* goal_distance (panda_env.py:311-315): a[n,3], b[n,3] -> d[n] (FP64 math) */
 int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream);
+
+/* ---- FrankaEnv._get_obs from kinematic state (envs/panda_env.py:279-301) ------------------ */
+/* Per env: q_arm[n,7], qvel_arm[n,7], fingers[n,2] (qpos of finger_joint1/2), the current target
+ * cube's free-joint state obj_pos[n,3], obj_quat[n,4] wxyz, obj_vel[n,6] (linear world, angular
+ * body-local: MuJoCo's free-joint qvel), goal[n,3] (goal_stride 3) or one goal[3] (stride 0).
+ * dt = opt.timestep * n_substeps (0.002 * 25).  out[n,25] = observation[19] (ee_pos3, ee_vel3,
+ * fingers_width, obj_pos3, obj_rot3 euler, obj_velp3, obj_velr3) | achieved_goal[3] | desired_goal[3]. */
+int pnp_get_obs_f32(const float* q_arm, const float* qvel_arm, const float* fingers, const float* obj_pos,
+                    const float* obj_quat, const float* obj_vel, const float* goal, int32_t goal_stride,
+                    int64_t n, double dt, float* out, int32_t kinematics, void* stream);
+int pnp_get_obs_f64(const double* q_arm, const double* qvel_arm, const double* fingers, const double* obj_pos,
+                    const double* obj_quat, const double* obj_vel, const double* goal, int32_t goal_stride,
+                    int64_t n, double dt, double* out, int32_t kinematics, void* stream);
 
 /* ---- host-buffer operators (end-to-end path: copies inside) ----------------------------- */
 typedef struct PnpHostCtx PnpHostCtx;

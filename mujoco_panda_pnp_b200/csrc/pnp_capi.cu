@@ -153,6 +153,33 @@ int fk_jac_impl(const T* q, int64_t n, T* pos, T* quat, T* jac, int32_t kinemati
   return PNP_OK;
 }
 
+template <typename T>
+int get_obs_impl(const T* q_arm, const T* qvel_arm, const T* fingers, const T* obj_pos, const T* obj_quat,
+                 const T* obj_vel, const T* goal, int32_t goal_stride, int64_t n, double dt, T* out,
+                 int32_t kinematics, void* stream) {
+  if (n < 0 || (n > 0 && (!q_arm || !qvel_arm || !fingers || !obj_pos || !obj_quat || !obj_vel || !goal || !out)))
+    return fail(PNP_EINVAL, "get_obs: null pointer or negative n");
+  if (goal_stride != 0 && goal_stride != 3) return fail(PNP_EINVAL, "goal_stride must be 0 or 3");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::ObsArgs<T> a;
+  a.q_arm = q_arm; a.qvel_arm = qvel_arm; a.fingers = fingers; a.obj_pos = obj_pos; a.obj_quat = obj_quat;
+  a.obj_vel = obj_vel; a.goal = goal; a.goal_stride = goal_stride; a.n = n; a.dt = (T)dt; a.out = out;
+  const int grid = grid_for(n, 128, s->sm_count, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spec)
+    pnp::get_obs_kernel<T, pnp::SpecKin><<<grid, 128, 0, st>>>(a);
+  else
+    pnp::get_obs_kernel<T, pnp::GenericKin><<<grid, 128, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
 template <typename T, typename Kin, bool kPacked>
 int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t st) {
   const int slot = (sizeof(T) == 8 ? 4 : 0) + (Kin::kSpecialized ? 2 : 0) + (kPacked ? 1 : 0);
@@ -432,6 +459,19 @@ int pnp_reward_f64(const double* ag, const double* dg, const double* ee_pos, con
                    float* reward, float* is_success, unsigned long long* counters, void* stream) {
   return reward_impl<double>(ag, dg, ee_pos, ee_quat, width, task_index, n, params, reward, is_success, counters,
                              stream);
+}
+
+int pnp_get_obs_f32(const float* q_arm, const float* qvel_arm, const float* fingers, const float* obj_pos,
+                    const float* obj_quat, const float* obj_vel, const float* goal, int32_t goal_stride, int64_t n,
+                    double dt, float* out, int32_t kinematics, void* stream) {
+  return get_obs_impl<float>(q_arm, qvel_arm, fingers, obj_pos, obj_quat, obj_vel, goal, goal_stride, n, dt, out,
+                             kinematics, stream);
+}
+int pnp_get_obs_f64(const double* q_arm, const double* qvel_arm, const double* fingers, const double* obj_pos,
+                    const double* obj_quat, const double* obj_vel, const double* goal, int32_t goal_stride,
+                    int64_t n, double dt, double* out, int32_t kinematics, void* stream) {
+  return get_obs_impl<double>(q_arm, qvel_arm, fingers, obj_pos, obj_quat, obj_vel, goal, goal_stride, n, dt, out,
+                              kinematics, stream);
 }
 
 int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream) {

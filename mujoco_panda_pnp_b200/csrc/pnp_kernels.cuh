@@ -44,6 +44,84 @@ __global__ void __launch_bounds__(128) fk_jac_kernel(const T* __restrict__ q, lo
 }
 
 // =============================================================================================
+// FrankaEnv._get_obs from kinematic state (panda_env.py:279-301): one lane per env.
+//   ee_pos  = site_xpos(ee_center_site)                       (:285)  FK(q)
+//   ee_vel  = (jacp @ qvel) * dt                              (:286)  only arm dofs 0..6 are non-zero
+//   obj_pos = cube site = free-joint position                 (:290)
+//   obj_rot = mat2euler(site_xmat)                            (:291)  gymnasium_robotics convention
+//   obj_velp = free-joint linear velocity * dt                (:292)  site sits at the body origin
+//   obj_velr = R(obj_quat) * local angular velocity * dt      (:293)  jacr columns = body axes
+//   fingers_width = qpos(finger_joint1) + qpos(finger_joint2) (:296, :348-352)
+// Output row [25] = observation[19] | achieved_goal[3] (= obj_pos) | desired_goal[3] (:297-301).
+// =============================================================================================
+__device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
+
+template <typename T>
+struct ObsArgs {
+  const T *q_arm, *qvel_arm, *fingers, *obj_pos, *obj_quat, *obj_vel, *goal;
+  int goal_stride;  // 3 = per env, 0 = one broadcast goal
+  long long n;
+  T dt;
+  T* out;  // [n][25]
+};
+
+template <typename T, typename Kin>
+__global__ void __launch_bounds__(128) get_obs_kernel(const ObsArgs<T> a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    T s[NJ], c[NJ], qv[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      sincos_t(a.q_arm[i * NJ + k] - Kin::template qref<T>(k), &s[k], &c[k]);
+      qv[k] = a.qvel_arm[i * NJ + k];
+    }
+    T p[3], J[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) J[k] = T(0);
+    Kin::template fk_jacp<T>(s, c, p, J);
+    T o[25];
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T acc = T(0);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * qv[j];
+      o[3 + r] = acc * a.dt;
+    }
+    o[6] = a.fingers[i * 2] + a.fingers[i * 2 + 1];
+    // free-joint body pose: mj_kinematics normalises the quaternion, xmat = quat2mat
+    T w = a.obj_quat[i * 4], x = a.obj_quat[i * 4 + 1], y = a.obj_quat[i * 4 + 2], z = a.obj_quat[i * 4 + 3];
+    const T nrm = sqrt_t(w * w + x * x + y * y + z * z);
+    if (nrm < T(1e-15)) { w = T(1); x = y = z = T(0); } else { w = w / nrm; x = x / nrm; y = y / nrm; z = z / nrm; }
+    const T q00 = w * w, q01 = w * x, q02 = w * y, q03 = w * z, q11 = x * x, q12 = x * y, q13 = x * z;
+    const T q22 = y * y, q23 = y * z, q33 = z * z;
+    const T m00 = q00 + q11 - q22 - q33, m01 = T(2) * (q12 - q03), m02 = T(2) * (q13 + q02);
+    const T m10 = T(2) * (q12 + q03), m11 = q00 - q11 + q22 - q33, m12 = T(2) * (q23 - q01);
+    const T m20 = T(2) * (q13 - q02), m21 = T(2) * (q23 + q01), m22 = q00 - q11 - q22 + q33;
+    o[7] = a.obj_pos[i * 3]; o[8] = a.obj_pos[i * 3 + 1]; o[9] = a.obj_pos[i * 3 + 2];
+    // rotations.mat2euler
+    const T cy = sqrt_t(m22 * m22 + m12 * m12);
+    const bool cond = cy > T(4.0 * 2.220446049250313e-16);
+    o[12] = cond ? -atan2_t(m01, m00) : -atan2_t(-m10, m11);
+    o[11] = -atan2_t(-m02, cy);
+    o[10] = cond ? -atan2_t(m12, m22) : T(0);
+    const T vx = a.obj_vel[i * 6], vy = a.obj_vel[i * 6 + 1], vz = a.obj_vel[i * 6 + 2];
+    const T wx = a.obj_vel[i * 6 + 3], wy = a.obj_vel[i * 6 + 4], wz = a.obj_vel[i * 6 + 5];
+    o[13] = vx * a.dt; o[14] = vy * a.dt; o[15] = vz * a.dt;
+    o[16] = (m00 * wx + m01 * wy + m02 * wz) * a.dt;
+    o[17] = (m10 * wx + m11 * wy + m12 * wz) * a.dt;
+    o[18] = (m20 * wx + m21 * wy + m22 * wz) * a.dt;
+    o[19] = o[7]; o[20] = o[8]; o[21] = o[9];
+    const T* g = a.goal + (long long)a.goal_stride * i;
+    o[22] = g[0]; o[23] = g[1]; o[24] = g[2];
+    T* dst = a.out + i * 25;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) dst[k] = o[k];
+  }
+}
+
+// =============================================================================================
 // Batched JacobianIKController.solve: one LANE per query, persistent warps with lane refill.
 //
 // Every pass of the loop evaluates FK/J/DLS once for all 32 lanes.  A lane whose query

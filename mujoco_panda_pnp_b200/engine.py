@@ -290,6 +290,47 @@ def reward(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, 
     return rew, succ
 
 
+OBS_DIM = 19  # observation width with block_gripper=False (panda_env.py:297)
+
+
+def get_obs(q_arm, qvel_arm, fingers, obj_pos, obj_quat, obj_vel, goal, dt: float = 0.05, kinematics="auto"):
+    """Batched FrankaEnv._get_obs from kinematic state (CUDA tensors, f32 or f64).
+
+    Returns rows[N,25] = observation[19] | achieved_goal[3] | desired_goal[3]."""
+    lib = _lib.load()
+    dt_ = q_arm.dtype
+    if dt_ not in (torch.float32, torch.float64):
+        raise ValueError("q_arm must be float32 or float64")
+    q_arm = _check_cuda("q_arm", q_arm, dt_, (7,))
+    n = q_arm.shape[0]
+    qvel_arm = _check_cuda("qvel_arm", qvel_arm, dt_, (7,))
+    fingers = _check_cuda("fingers", fingers, dt_, (2,))
+    obj_pos = _check_cuda("obj_pos", obj_pos, dt_, (3,))
+    obj_quat = _check_cuda("obj_quat", obj_quat, dt_, (4,))
+    obj_vel = _check_cuda("obj_vel", obj_vel, dt_, (6,))
+    for name, t in (("qvel_arm", qvel_arm), ("fingers", fingers), ("obj_pos", obj_pos), ("obj_quat", obj_quat),
+                    ("obj_vel", obj_vel)):
+        if t.shape[0] != n:
+            raise ValueError(f"{name} disagrees with q_arm on N")
+    if goal.dim() == 1:
+        if goal.shape != (3,):
+            raise ValueError("broadcast goal must have shape (3,)")
+        goal, stride = goal.to(device=q_arm.device, dtype=dt_).contiguous(), 0
+    else:
+        goal, stride = _check_cuda("goal", goal, dt_, (3,)), 3
+        if goal.shape[0] != n:
+            raise ValueError("goal disagrees with q_arm on N")
+    out = torch.empty((n, 25), dtype=dt_, device=q_arm.device)
+    fn = lib.pnp_get_obs_f32 if dt_ == torch.float32 else lib.pnp_get_obs_f64
+    with torch.cuda.device(q_arm.device):
+        _lib.check(
+            fn(_ptr(q_arm), _ptr(qvel_arm), _ptr(fingers), _ptr(obj_pos), _ptr(obj_quat), _ptr(obj_vel), _ptr(goal),
+               stride, n, float(dt), _ptr(out), KINEMATICS[kinematics], _stream()),
+            "pnp_get_obs",
+        )
+    return out
+
+
 def goal_distance(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     a = _check_cuda("a", a, torch.float64, (3,))

@@ -67,6 +67,7 @@ class FrankaRewardModel:
         self.fingers_width = 0.0
         self.device = torch.device(device) if device is not None else None
         self.last_counters: Optional[np.ndarray] = None
+        self.dt = 0.002 * 25  # MujocoRobotEnv.dt = opt.timestep * n_substeps (shelf_pnp.py:19, shelf_pnp.xml:4)
 
     # ---- hidden-state getters (panda_env.py:337-352) -----------------------------------
     def get_ee_position(self):
@@ -177,6 +178,36 @@ class FrankaRewardModel:
         """Batched: (reward float32[N], is_success float32[N]) from one pass over the rows."""
         st = self._state_from_info(info, int(achieved_goal.shape[0]))
         return self._run(achieved_goal, desired_goal, st, want_success=True)
+
+    def _get_obs(self, state: Mapping[str, Any], tree=None, precision: str = "fp32"):
+        """Batched FrankaEnv._get_obs (panda_env.py:279-301) from kinematic state.
+
+        The reference reads the live simulator; here ``state`` carries what it reads, one row
+        per env: ``q_arm[N,7]``, ``qvel_arm[N,7]``, ``fingers[N,2]`` (finger_joint1/2 qpos) and,
+        for the current target cube, ``obj_pos[N,3]``, ``obj_quat[N,4]`` (wxyz), ``obj_vel[N,6]``
+        (free-joint qvel: linear world, angular body-local), plus ``goal[N,3]`` or ``[3]``.
+        Returns the reference's dict: ``observation`` (N,19), ``achieved_goal`` (N,3),
+        ``desired_goal`` (N,3); CUDA tensors in -> CUDA tensors out, NumPy in -> NumPy out."""
+        from ..tree import KinematicTree
+
+        keys = ("q_arm", "qvel_arm", "fingers", "obj_pos", "obj_quat", "obj_vel", "goal")
+        missing = [k for k in keys if k not in state]
+        if missing:
+            raise ValueError(f"_get_obs state lacks {missing}")
+        on_gpu = isinstance(state["q_arm"], torch.Tensor) and state["q_arm"].is_cuda
+        dt_t = torch.float32 if precision == "fp32" else torch.float64
+        if not torch.cuda.is_available():
+            raise engine._lib.PnpLibraryError("no CUDA device: _get_obs has no CPU path")
+        dev = state["q_arm"].device if on_gpu else (self.device or torch.device("cuda", torch.cuda.current_device()))
+        with torch.cuda.device(dev):
+            engine.set_tree(tree or KinematicTree.from_mjcf())
+            args = [torch.as_tensor(np.asarray(state[k]) if not isinstance(state[k], torch.Tensor) else state[k])
+                    .to(device=dev, dtype=dt_t) for k in keys]
+            rows = engine.get_obs(*args, dt=self.dt)
+        out = {"observation": rows[:, :19], "achieved_goal": rows[:, 19:22], "desired_goal": rows[:, 22:25]}
+        if not on_gpu:
+            out = {k: v.double().cpu().numpy() for k, v in out.items()}
+        return out
 
     def _is_success(self, achieved_goal, desired_goal):
         """np.float32(1.0 if ||ag - dg|| < distance_threshold else 0.0) (panda_env.py:303-306)."""

@@ -170,6 +170,46 @@ def gen_reward():
              int((out["reward_sparse"].view(np.uint32) == 0x80000000).sum())))
 
 
+def random_obs_states(n, model, seed=11):
+    """Kinematic states for _get_obs: arm inside its limits, joint velocities, open/closed fingers,
+    a free cube with arbitrary pose (incl. near-gimbal orientations) and twist."""
+    rng = np.random.default_rng(seed)
+    lo, hi = model.jnt_range[:7, 0], model.jnt_range[:7, 1]
+    st = dict(
+        q_arm=rng.uniform(lo, hi, (n, 7)), qvel_arm=rng.normal(0, 0.5, (n, 7)),
+        fingers=rng.uniform(0, 0.04, (n, 2)), obj_pos=rng.normal([1.3, 0, 0.6], 0.3, (n, 3)),
+        obj_quat=rng.normal(size=(n, 4)), obj_vel=rng.normal(0, 0.3, (n, 6)),
+        goal=np.array([[1.0, -0.1, 0.3], [1.0, 0.0, 0.3], [1.0, 0.1, 0.3]])[rng.integers(0, 3, n)],
+        obj_index=rng.integers(0, 3, n),
+    )
+    st["obj_quat"] /= np.linalg.norm(st["obj_quat"], axis=1, keepdims=True)
+    # pitch = +-90 deg rows exercise mat2euler's degenerate branch (cy ~ 0)
+    s = np.sqrt(0.5)
+    st["obj_quat"][:4] = [[s, 0, s, 0], [s, 0, -s, 0], [1, 0, 0, 0], [0, 1, 0, 0]]
+    st["qvel_arm"][4] = 0.0
+    return st
+
+
+def gen_obs(model):
+    from . import obs_oracle
+
+    env_mod = ref_harness.reference_env_module()
+    data = mj_oracle.MjData(model)
+    probe = ref_harness.ObsProbe(env_mod, model, data)
+    n = 256
+    st = random_obs_states(n, model)
+    obs, ag, dg = np.empty((n, 19)), np.empty((n, 3)), np.empty((n, 3))
+    for i in range(n):
+        name = f"cube{int(st['obj_index'][i]) + 1}"
+        obs_oracle.set_state(model, data, st["q_arm"][i], st["qvel_arm"][i], st["fingers"][i], name,
+                             st["obj_pos"][i], st["obj_quat"][i], st["obj_vel"][i])
+        o = probe.get_obs(name, st["goal"][i].copy())
+        obs[i], ag[i], dg[i] = o["observation"], o["achieved_goal"], o["desired_goal"]
+    np.savez(os.path.join(OUT, "obs_reference_golden.npz"), **st, observation=obs, achieved_goal=ag,
+             desired_goal=dg, dt=0.05)
+    print("obs_reference_golden: %d states; |obs| max %.3f" % (n, np.abs(obs).max()))
+
+
 def gen_vecnormalize():
     class _Stub:
         def __init__(self, *a, **k):
@@ -209,6 +249,7 @@ def main():
     gen_fk(model)
     gen_ik(model)
     gen_reward()
+    gen_obs(model)
     gen_vecnormalize()
 
 

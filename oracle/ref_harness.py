@@ -67,6 +67,9 @@ def _install_stubs() -> None:
     gr_utils = types.ModuleType("gymnasium_robotics.utils")
     gr_rot = types.ModuleType("gymnasium_robotics.utils.rotations")
     gr_rot.euler2quat = reward_oracle.euler2quat
+    from . import obs_oracle
+
+    gr_rot.mat2euler = obs_oracle.mat2euler
     gr_utils.rotations = gr_rot
     for name, mod in [
         ("gymnasium_robotics", gr),
@@ -145,3 +148,28 @@ class RewardProbe:
 
     def success(self, ag, dg):
         return self._cls._is_success(self, ag, dg)
+
+
+class ObsProbe:
+    """Minimal ``self`` for the reference's unbound ``FrankaEnv._get_obs`` (panda_env.py:279-301):
+    model/data (restated engine), ``_utils`` (restated mujoco_utils), dt, goal and the current
+    target object - exactly the attributes that method reads."""
+
+    def __init__(self, env_mod, model, data, dt=0.05):
+        from . import obs_oracle
+
+        self._cls = env_mod.FrankaEnv
+        self.model, self.data = model, data
+        self._utils = obs_oracle.MujocoUtils
+        self.dt = dt
+        self.block_gripper = False
+        self.current_target_object = "cube1"
+        self.goal = None
+
+    def get_fingers_width(self):
+        return self._cls.get_fingers_width(self)
+
+    def get_obs(self, current_obj, goal):
+        self.current_target_object = current_obj
+        self.goal = goal
+        return self._cls._get_obs(self)

@@ -185,3 +185,32 @@ def test_reference_code_still_reproduces_golden(oracle_model, golden_ik, golden_
         r = probe.reward(g["achieved_goal"][i], g["desired_goal"][i], g["ee_pos"][i], g["ee_quat"][i],
                          g["fingers_width"][i], g["task_index"][i])
         assert np.float32(r).view(np.uint32) == g["reward_dense"][i].view(np.uint32)
+
+
+# ------------------------------------------------------------------ _get_obs
+def test_obs_oracle_bit_identical_to_reference_code(oracle_model):
+    from oracle import obs_oracle
+
+    g = np.load(os.path.join(GOLDEN, "obs_reference_golden.npz"))
+    data = mj_oracle.MjData(oracle_model)
+    for i in range(len(g["q_arm"])):
+        name = f"cube{int(g['obj_index'][i]) + 1}"
+        obs_oracle.set_state(oracle_model, data, g["q_arm"][i], g["qvel_arm"][i], g["fingers"][i], name,
+                             g["obj_pos"][i], g["obj_quat"][i], g["obj_vel"][i])
+        o = obs_oracle.get_obs(oracle_model, data, name, g["goal"][i], dt=float(g["dt"]))
+        np.testing.assert_array_equal(o["observation"], g["observation"][i])
+        np.testing.assert_array_equal(o["achieved_goal"], g["achieved_goal"][i])
+        np.testing.assert_array_equal(o["desired_goal"], g["desired_goal"][i])
+    obs = g["observation"]
+    assert obs.shape == (256, 19)
+    # layout pins (panda_env.py:297): width = f1 + f2 at [6], obj_pos at [7:10] = achieved_goal
+    np.testing.assert_array_equal(obs[:, 6], g["fingers"].sum(axis=1))
+    np.testing.assert_array_equal(obs[:, 7:10], g["achieved_goal"])
+    np.testing.assert_array_equal(obs[:, 13:16], g["obj_vel"][:, :3] * 0.05)
+    # ee_vel = jacp @ qvel * dt agrees with a finite difference of FK along qvel
+    h = 1e-7
+    p0 = ik_oracle.fk_site(oracle_model, data, g["q_arm"][9])[0]
+    p1 = ik_oracle.fk_site(oracle_model, data, g["q_arm"][9] + h * g["qvel_arm"][9])[0]
+    np.testing.assert_allclose((p1 - p0) / h * 0.05, obs[9, 3:6], atol=1e-7)
+    # gimbal rows went through mat2euler's degenerate branch
+    assert abs(abs(obs[0, 11]) - np.pi / 2) < 1e-6 and obs[0, 10] == 0.0
