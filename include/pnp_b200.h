@@ -13,6 +13,7 @@
  *   pnp_ik_solve_*         JacobianIKController.solve (ik_solver.py:35-101), batched
  *   pnp_ik_waypoints_*     the warm-started solve sequence of MoveIKSkill.reset
  *                          (skills/move.py:106-137), fixed number of waypoints per env
+ *   pnp_move_ik_plan_*     the whole MoveIKSkill.reset planner (skills/move.py:76-191)
  *   pnp_get_obs_*          FrankaEnv._get_obs (envs/panda_env.py:279-301) from kinematic state
  *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
  *                          (envs/panda_env.py:205-245, 303-306, 311-315), row-wise
@@ -155,6 +156,31 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
                          double step_size, const PnpIkParams* params, float* q_out, float* pos_out,
                          int32_t* n_accepted, int32_t* iters_total, unsigned long long* counters,
                          void* stream);
+
+/* ---- full MoveIKSkill.reset trajectory planner (skills/move.py:76-191) -------------------- */
+typedef struct PnpMoveParams {
+  double pos_thresh;        /* 0.01  MoveIKSkill.pos_thresh (move.py:66) */
+  double step_size;         /* 0.01  MoveIKSkill.step_size */
+  int32_t max_traj_points;  /* 200   MoveIKSkill.max_traj_points */
+  int32_t max_outer;        /* bound on planner rounds; 0 = 4*max_traj_points + 64.  The reference
+                               has no bound and never returns for unreachable targets. */
+  int32_t traj_cap;         /* points of storage per env in traj (>= 2) */
+  int32_t reserved;
+} PnpMoveParams;
+#define PNP_MOVE_BROKE 1u      /* fallback strategies exhausted (reference `break`, move.py:178-180) */
+#define PNP_MOVE_CAPPED 2u     /* max_outer reached */
+#define PNP_MOVE_OVERFLOW 4u   /* more than traj_cap points: extra points dropped, traj_len still counts */
+/* Per env: q_start[n,7], target[n,3].  The whole adaptive-waypoint state machine (accept rule,
+ * failure counting incl. the double increment, fallback strategies 1-3, final-point append) runs
+ * on the device; every IK solve uses `params`.  Outputs: traj[n,traj_cap,3] = MoveIKSkill.pos_traj
+ * (first point = FK(q_start)), traj_len[n], q_final[n,7] (= q_current after the loop),
+ * n_solves[n] (nullable), status[n] (nullable, PNP_MOVE_* bits), counters[4] (nullable). */
+int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, const PnpMoveParams* move,
+                         const PnpIkParams* params, float* traj, int32_t* traj_len, float* q_final,
+                         int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream);
+int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n, const PnpMoveParams* move,
+                         const PnpIkParams* params, double* traj, int32_t* traj_len, double* q_final,
+                         int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream);
 
 /* ---- compute_reward / _is_success, row-wise --------------------------------------------- */
 /* Per row: achieved_goal[n,3], desired_goal[n,3], ee_pos[n,3], ee_quat[n,4] wxyz,

@@ -43,6 +43,17 @@ class PnpRewardParams(ctypes.Structure):
     ]
 
 
+class PnpMoveParams(ctypes.Structure):
+    _fields_ = [
+        ("pos_thresh", c_double),
+        ("step_size", c_double),
+        ("max_traj_points", c_int32),
+        ("max_outer", c_int32),
+        ("traj_cap", c_int32),
+        ("reserved", c_int32),
+    ]
+
+
 class PnpLibraryError(RuntimeError):
     pass
 
@@ -64,6 +75,8 @@ SIGNATURES = {
     "pnp_ik_solve_packed_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P]),
     "pnp_ik_solve_f64": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_ik_waypoints_f32": (c_int, [_P, _P, c_int64, c_int32, c_double, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),
+    "pnp_move_ik_plan_f32": (c_int, [_P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
+    "pnp_move_ik_plan_f64": (c_int, [_P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_reward_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
     "pnp_reward_f64": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
     "pnp_get_obs_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_double, _P, c_int32, _P]),

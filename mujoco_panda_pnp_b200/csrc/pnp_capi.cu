@@ -449,6 +449,61 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   return PNP_OK;
 }
 
+}  // extern "C"
+
+namespace {
+template <typename T>
+int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMoveParams* mp, const PnpIkParams* params,
+                   T* traj, int32_t* traj_len, T* q_final, int32_t* n_solves, int32_t* status,
+                   unsigned long long* counters, void* stream) {
+  int rc = check_ik_params(params);
+  if (rc) return rc;
+  if (!mp) return fail(PNP_EINVAL, "move params is NULL");
+  if (mp->traj_cap < 2 || mp->max_traj_points < 0 || !(mp->step_size > 0.0) || !(mp->pos_thresh >= 0.0))
+    return fail(PNP_EINVAL, "move params: need traj_cap >= 2, max_traj_points >= 0, step_size > 0, pos_thresh >= 0");
+  if (n < 0 || (n > 0 && (!q_start || !target || !traj || !traj_len || !q_final)))
+    return fail(PNP_EINVAL, "move_ik_plan: null pointer or negative n");
+  DeviceState* s;
+  if ((rc = current_state(&s))) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::MoveArgs<T> a;
+  a.q_start = q_start; a.target = target; a.n = n;
+  a.pos_thresh = (T)mp->pos_thresh; a.step_size = (T)mp->step_size;
+  a.max_traj_points = mp->max_traj_points;
+  a.max_outer = mp->max_outer > 0 ? mp->max_outer : 4 * mp->max_traj_points + 64;
+  a.traj_cap = mp->traj_cap;
+  a.k = make_ik_const<T>(params);
+  a.traj = traj; a.traj_len = traj_len; a.q_final = q_final; a.n_solves = n_solves; a.status = status;
+  a.counters = counters;
+  const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spec)
+    pnp::move_ik_plan_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
+  else
+    pnp::move_ik_plan_kernel<T, pnp::GenericKin><<<grid, block, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, const PnpMoveParams* mp,
+                         const PnpIkParams* params, float* traj, int32_t* traj_len, float* q_final,
+                         int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
+  return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, stream);
+}
+int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n, const PnpMoveParams* mp,
+                         const PnpIkParams* params, double* traj, int32_t* traj_len, double* q_final,
+                         int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
+  return move_plan_impl<double>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, stream);
+}
+
 int pnp_reward_f32(const float* ag, const float* dg, const float* ee_pos, const float* ee_quat, const float* width,
                    const int32_t* task_index, int64_t n, const PnpRewardParams* params, float* reward,
                    float* is_success, unsigned long long* counters, void* stream) {

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import KINEMATICS, PnpIkParams, PnpRewardParams
+from ._lib import KINEMATICS, PnpIkParams, PnpMoveParams, PnpRewardParams
 from .tree import KinematicTree, PnpTreeStruct
 
 _uploaded: Dict[int, bytes] = {}  # device index -> bytes of the PnpTree currently in constant memory
@@ -252,6 +252,38 @@ def ik_waypoints(q_start: torch.Tensor, goal: torch.Tensor, n_steps: int, params
             "pnp_ik_waypoints",
         )
     return dict(q=q, pos=pos, n_accepted=acc, iters_total=its)
+
+
+def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParams, pos_thresh: float = 0.01,
+                 max_traj_points: int = 200, step_size: float = 0.01, max_outer: int = 0, traj_cap: int = 256,
+                 counters: Optional[torch.Tensor] = None):
+    """Batched MoveIKSkill.reset planner (skills/move.py:76-191): CUDA tensors f32 or f64.
+
+    Returns dict(traj[N,traj_cap,3], traj_len[N], q_final[N,7], n_solves[N], status[N])."""
+    lib = _lib.load()
+    dt = q_start.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("q_start must be float32 or float64")
+    q_start = _check_cuda("q_start", q_start, dt, (7,))
+    target = _check_cuda("target", target, dt, (3,))
+    n = q_start.shape[0]
+    if target.shape[0] != n:
+        raise ValueError("q_start and target disagree on N")
+    dev = q_start.device
+    mp = PnpMoveParams(float(pos_thresh), float(step_size), int(max_traj_points), int(max_outer), int(traj_cap), 0)
+    traj = torch.zeros((n, traj_cap, 3), dtype=dt, device=dev)
+    tlen = torch.empty((n,), dtype=torch.int32, device=dev)
+    qf = torch.empty((n, 7), dtype=dt, device=dev)
+    solves = torch.empty((n,), dtype=torch.int32, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    fn = lib.pnp_move_ik_plan_f32 if dt == torch.float32 else lib.pnp_move_ik_plan_f64
+    with torch.cuda.device(dev):
+        _lib.check(
+            fn(_ptr(q_start), _ptr(target), n, ctypes.byref(mp), ctypes.byref(params), _ptr(traj), _ptr(tlen), _ptr(qf),
+               _ptr(solves), _ptr(status), _ptr(counters), _stream()),
+            "pnp_move_ik_plan",
+        )
+    return dict(traj=traj, traj_len=tlen, q_final=qf, n_solves=solves, status=status)
 
 
 # ---------------------------------------------------------------------------------------------

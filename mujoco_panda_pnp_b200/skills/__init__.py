@@ -1,1 +1,2 @@
 from .ik_solver import BatchIKResult, IKResult, IKSolver, JacobianIKController  # noqa: F401
+from .move import MoveIKSkill, plan_moves  # noqa: F401

@@ -241,9 +241,84 @@ static float reward_one(const OracleRewardParams* p, const double ag[3], const d
   return (float)r;                                                            /* :245 */
 }
 
+/* ------------------------------------------------------------------ skills/move.py:76-191
+ * MoveIKSkill.reset trajectory planner (adaptive step, accept rule, double failure increment,
+ * fallback strategies 1-3, final-point append).  max_outer bounds the while loop: the reference
+ * has no such bound and spins forever on unreachable targets (fallback 1 keeps succeeding with
+ * ever smaller steps without advancing point_count); 0 = unbounded like the reference. */
+typedef struct {
+  double pos_thresh;      /* 0.01 */
+  int32_t max_traj_points; /* 200 */
+  double step_size;       /* 0.01 */
+  int32_t max_outer;
+  int32_t traj_cap;       /* capacity of the output trajectory (points) */
+} OracleMoveParams;
+
+static void move_plan_one(const OracleChain* c, const OracleIkParams* ikp, const OracleMoveParams* mp,
+                          const double q_start[NARM], const double target[3], double* traj /*[cap][3]*/,
+                          int32_t* traj_len, double q_final[NARM], int32_t* n_solves, int32_t* status) {
+  double anchors[NARM][3], axes[NARM][3], xmat[9], pos[3], q[NARM];
+  memcpy(q, q_start, sizeof q);
+  chain_fk(c, q, pos, xmat, anchors, axes);                                   /* :91 start_pos */
+  int len = 0, solves = 0, st = 0;
+#define APPEND(P) do { if (len < mp->traj_cap) memcpy(traj + 3 * len, (P), 3 * sizeof(double)); else st |= 4; ++len; } while (0)
+  APPEND(pos);                                                                /* :98 */
+  int point_count = 0, cf = 0, outer = 0;
+  for (;;) {
+    double d[3] = {pos[0] - target[0], pos[1] - target[1], pos[2] - target[2]};
+    if (!(norm3(d) > mp->pos_thresh && point_count < mp->max_traj_points)) break;   /* :106-107 */
+    if (mp->max_outer > 0 && outer >= mp->max_outer) { st |= 2; break; }
+    ++outer;
+    double dir[3] = {target[0] - pos[0], target[1] - pos[1], target[2] - pos[2]};   /* :110 */
+    double dist = norm3(dir);                                                 /* :111 */
+    double step = fmin(mp->step_size, dist * 0.1);                            /* :114 */
+    step = fmin(step, 0.02);                                                  /* :117 */
+    if (cf > 0) step *= 0.5;                                                  /* :118-119 */
+    double next[3];
+    for (int k = 0; k < 3; ++k) next[k] = dist > step ? pos[k] + dir[k] * step / dist : target[k]; /* :122-125 */
+    double qs[NARM], fp[3], err; int32_t it; uint8_t fl;
+    ik_solve_one(c, ikp, next, q, qs, fp, &err, &it, &fl); ++solves;          /* :128 */
+    if ((fl & 2) && err < mp->step_size * 2) {                                /* :131 */
+      APPEND(fp); memcpy(pos, fp, sizeof fp); memcpy(q, qs, sizeof qs); cf = 0;
+    } else {
+      ++cf;                                                                   /* :142 */
+      if (cf >= 3) {                                                          /* :144 */
+        double smaller = step * 0.1;                                          /* :149 */
+        if (dist > smaller) {
+          double fb[3];
+          for (int k = 0; k < 3; ++k) fb[k] = pos[k] + dir[k] * smaller / dist;
+          ik_solve_one(c, ikp, fb, q, qs, fp, &err, &it, &fl); ++solves;      /* :152 */
+          if (fl & 2) { APPEND(fp); memcpy(pos, fp, sizeof fp); memcpy(q, qs, sizeof qs); cf = 0; continue; }
+        }
+        double alt[3] = {dir[0], 0.0, dir[2]};                                /* :163-164 */
+        double an = norm3(alt);
+        if (an > 0.001) {
+          double ap[3];
+          for (int k = 0; k < 3; ++k) ap[k] = pos[k] + (alt[k] / an) * step;
+          ik_solve_one(c, ikp, ap, q, qs, fp, &err, &it, &fl); ++solves;      /* :168 */
+          if (fl & 2) { APPEND(fp); memcpy(pos, fp, sizeof fp); memcpy(q, qs, sizeof qs); cf = 0; continue; }
+        }
+        st |= 1;                                                              /* :178-180 break */
+        break;
+      } else {
+        ++cf;                                                                 /* :183 */
+        continue;
+      }
+    }
+    ++point_count;                                                            /* :186 */
+  }
+  double d[3] = {pos[0] - target[0], pos[1] - target[1], pos[2] - target[2]};
+  if (norm3(d) > mp->pos_thresh) APPEND(target);                              /* :189-191 */
+#undef APPEND
+  *traj_len = len; *n_solves = solves; *status = st;
+  memcpy(q_final, q, sizeof q);
+}
+
 /* ------------------------------------------------------------------ threading */
 typedef struct {
-  int kind; /* 0 ik, 1 reward, 2 fk */
+  int kind; /* 0 ik, 1 reward, 2 fk, 3 move plan */
+  const OracleMoveParams* mvp; const double *mv_q, *mv_goal; double *mv_traj, *mv_qf;
+  int32_t *mv_len, *mv_solves, *mv_status;
   int64_t begin, end;
   const OracleChain* chain;
   const OracleIkParams* ikp;
@@ -264,6 +339,10 @@ static void* worker(void* arg) {
     } else if (j->kind == 1) {
       j->reward[i] = reward_one(j->rwp, j->ag + 3 * i, j->dg + 3 * i, j->ee + 3 * i, j->eq + 4 * i,
                                 j->width[i], j->task_idx[i], j->success ? j->success + i : NULL);
+    } else if (j->kind == 3) {
+      move_plan_one(j->chain, j->ikp, j->mvp, j->mv_q + NARM * i, j->mv_goal + 3 * i,
+                    j->mv_traj + (int64_t)3 * j->mvp->traj_cap * i, j->mv_len + i, j->mv_qf + NARM * i,
+                    j->mv_solves + i, j->mv_status + i);
     } else {
       double anchors[NARM][3], axes[NARM][3], jac[6][NARM];
       chain_fk(j->chain, j->fk_q + NARM * i, j->fk_pos + 3 * i, j->fk_mat + 9 * i, anchors, axes);
@@ -320,4 +399,13 @@ void oracle_reward(const OracleRewardParams* p, const double* ag, const double* 
   run_jobs(&j, n, nthreads);
 }
 
-int oracle_abi_version(void) { return 1; }
+void oracle_move_plan(const OracleChain* chain, const OracleIkParams* ikp, const OracleMoveParams* mp,
+                      const double* q_start, const double* goal, int64_t n, double* traj, int32_t* traj_len,
+                      double* q_final, int32_t* n_solves, int32_t* status, int nthreads) {
+  Job j; memset(&j, 0, sizeof j);
+  j.kind = 3; j.chain = chain; j.ikp = ikp; j.mvp = mp; j.mv_q = q_start; j.mv_goal = goal; j.mv_traj = traj;
+  j.mv_len = traj_len; j.mv_qf = q_final; j.mv_solves = n_solves; j.mv_status = status;
+  run_jobs(&j, n, nthreads);
+}
+
+int oracle_abi_version(void) { return 2; }

@@ -52,6 +52,16 @@ class OracleRewardParams(ctypes.Structure):
     ]
 
 
+class OracleMoveParams(ctypes.Structure):
+    _fields_ = [
+        ("pos_thresh", ctypes.c_double),
+        ("max_traj_points", ctypes.c_int32),
+        ("step_size", ctypes.c_double),
+        ("max_outer", ctypes.c_int32),
+        ("traj_cap", ctypes.c_int32),
+    ]
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "c", "pnp_oracle.c")
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
@@ -155,3 +165,23 @@ def reward(ag, dg, ee_pos, ee_quat, width, task_index, *, reward_type="dense", n
         ctypes.c_int64(n), _dp(out), _dp(succ) if want_success else None, int(nthreads),
     )
     return out, succ
+
+
+def move_plan(chain, q_start, goal, pos_thresh=0.01, max_traj_points=200, step_size=0.01, max_outer=0, traj_cap=256,
+              max_iters=100, ik_pos_thresh=1e-3, damping=1e-2, step_limit=0.1, nthreads=1):
+    """MoveIKSkill.reset planner (skills/move.py:76-191) for n envs.  status bits: 1 = fallback
+    strategies exhausted (reference `break`), 2 = max_outer reached, 4 = trajectory capacity hit."""
+    q_start = np.ascontiguousarray(q_start, dtype=np.float64).reshape(-1, 7)
+    goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1, 3)
+    n = len(q_start)
+    assert len(goal) == n
+    ikp = OracleIkParams(int(max_iters), float(ik_pos_thresh), float(damping), float(step_limit))
+    mp = OracleMoveParams(float(pos_thresh), int(max_traj_points), float(step_size), int(max_outer), int(traj_cap))
+    traj = np.zeros((n, traj_cap, 3))
+    tlen = np.empty(n, dtype=np.int32)
+    qf = np.empty((n, 7))
+    solves = np.empty(n, dtype=np.int32)
+    status = np.empty(n, dtype=np.int32)
+    lib().oracle_move_plan(ctypes.byref(chain), ctypes.byref(ikp), ctypes.byref(mp), _dp(q_start), _dp(goal),
+                           ctypes.c_int64(n), _dp(traj), _dp(tlen), _dp(qf), _dp(solves), _dp(status), int(nthreads))
+    return dict(traj=traj, traj_len=tlen, q_final=qf, n_solves=solves, status=status)

@@ -210,6 +210,49 @@ def gen_obs(model):
     print("obs_reference_golden: %d states; |obs| max %.3f" % (n, np.abs(obs).max()))
 
 
+def move_cases(model):
+    """Planner cases (q_start, target): ordinary reachable moves of different lengths, the BT demo
+    waypoints, a start already within 1 cm, and moves towards the workspace boundary whose IK
+    solves fail part of the way (step halving, double failure increment, fallback strategy 1) but
+    that still terminate because point_count reaches max_traj_points.  Unreachable targets are NOT
+    included: the reference loop never terminates on them (see oracle/c/pnp_oracle.c)."""
+    lo, hi = model.jnt_range[:7, 0], model.jnt_range[:7, 1]
+    rng = np.random.default_rng(3)
+    n = 3000
+    tg = rng.uniform([0.3, -0.8, -0.1], [1.75, 0.8, 1.5], (n, 3))
+    q0 = np.clip(NEUTRAL + rng.uniform(-0.4, 0.4, (n, 7)), lo, hi)
+    cases = [(NEUTRAL, np.array(t, float)) for t in
+             [(1.415, 0, 0.73), (1.415, 0, 1.03), (1.415, 0, 0.43), (1.2, 0.0, 0.78), (1.24, 0.0, 0.5), (1.0, -0.1, 0.36)]]
+    for i in (0, 1, 2, 3, 4, 10, 12, 19):        # ordinary random moves (all terminate)
+        cases.append((q0[i], tg[i]))
+    for i in (991, 592, 1184, 1026):             # failing solves on the way, terminate at 200 points
+        cases.append((q0[i], tg[i]))
+    return cases
+
+
+def gen_move(model):
+    import signal
+
+    def on_alarm(signum, frame):
+        raise TimeoutError("reference MoveIKSkill.reset did not terminate")
+
+    signal.signal(signal.SIGALRM, on_alarm)
+    cases = move_cases(model)
+    cap = 208
+    traj = np.zeros((len(cases), cap, 3))
+    lens = np.zeros(len(cases), dtype=np.int32)
+    for k, (q_start, target) in enumerate(cases):
+        signal.alarm(300)
+        t = ref_harness.reference_move_plan(model, q_start, target)
+        signal.alarm(0)
+        lens[k] = len(t)
+        traj[k, : len(t)] = t
+    np.savez(os.path.join(OUT, "move_reference_golden.npz"), q_start=np.array([c[0] for c in cases]),
+             target=np.array([c[1] for c in cases]), traj=traj, traj_len=lens,
+             pos_thresh=0.01, max_traj_points=200, step_size=0.01)
+    print("move_reference_golden: %d cases, trajectory lengths %s" % (len(cases), lens.tolist()))
+
+
 def gen_vecnormalize():
     class _Stub:
         def __init__(self, *a, **k):
@@ -251,6 +294,7 @@ def main():
     gen_reward()
     gen_obs(model)
     gen_vecnormalize()
+    gen_move(model)
 
 
 if __name__ == "__main__":

@@ -173,3 +173,42 @@ class ObsProbe:
         self.current_target_object = current_obj
         self.goal = goal
         return self._cls._get_obs(self)
+
+
+def reference_move_module():
+    """The reference's skills/move.py (MoveIKSkill), executed from /root/reference."""
+    _install_stubs()
+    return importlib.import_module("panda_mujoco_gym.skills.move")
+
+
+class MoveEnvStub:
+    """The slice of the gym env that MoveIKSkill.reset touches (move.py:81-93): ``unwrapped``
+    with model/data, get_ee_position, get_ee_orientation."""
+
+    def __init__(self, model, q_start):
+        self.model = model
+        self.data = mj_oracle.MjData(model)
+        self.data.qpos[:7] = q_start
+        mj_oracle.mj_forward(model, self.data)
+        self.unwrapped = self
+        self._sid = model.site("ee_center_site").id
+
+    def get_ee_position(self):
+        return self.data.site_xpos[self._sid]
+
+    def get_ee_orientation(self):
+        quat = np.empty(4)
+        mj_oracle.mju_mat2Quat(quat, self.data.site_xmat[self._sid])
+        return quat
+
+
+def reference_move_plan(model, q_start, target_pos, **kw):
+    """Run the reference's own MoveIKSkill.reset and return its pos_traj as an array."""
+    import contextlib
+    import io
+
+    move = reference_move_module()
+    skill = move.MoveIKSkill(MoveEnvStub(model, q_start), np.asarray(target_pos, float), **kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        skill.reset()
+    return np.array(skill.pos_traj)

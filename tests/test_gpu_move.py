@@ -1,0 +1,92 @@
+"""GPU parity: device-side MoveIKSkill.reset planner (skills/move.py:76-191) vs the trajectories
+of the reference's own code (tests/golden/move_reference_golden.npz) and the C oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, NEUTRAL
+from mujoco_panda_pnp_b200 import KinematicTree, engine, synthetic
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden(cuda_lib):
+    engine.set_tree(KinematicTree.from_mjcf())
+    return np.load(os.path.join(GOLDEN, "move_reference_golden.npz"))
+
+
+@pytest.mark.parametrize("kin", ["specialized", "generic"])
+def test_fp64_planner_reproduces_reference_trajectories(golden, kin):
+    g = golden
+    out = engine.move_ik_plan(torch.tensor(g["q_start"], device="cuda"), torch.tensor(g["target"], device="cuda"),
+                              engine.ik_params(kinematics=kin), traj_cap=g["traj"].shape[1])
+    np.testing.assert_array_equal(out["traj_len"].cpu().numpy(), g["traj_len"])
+    assert int(out["status"].abs().sum()) == 0
+    traj = out["traj"].cpu().numpy()
+    for k in range(len(g["traj_len"])):
+        L = int(g["traj_len"][k])
+        np.testing.assert_allclose(traj[k, :L], g["traj"][k, :L], atol=1e-8)
+
+
+def test_fp32_planner_follows_reference_trajectories(golden, oracle_chain):
+    """FP32 product path: same waypoint counts on the ordinary moves, every waypoint within 1e-4 m
+    (north_star EE tolerance); moves with failing solves may branch differently and are compared
+    on their structure (length, monotone approach) only."""
+    g = golden
+    out = engine.move_ik_plan(torch.tensor(g["q_start"], dtype=torch.float32, device="cuda"),
+                              torch.tensor(g["target"], dtype=torch.float32, device="cuda"), engine.ik_params(),
+                              traj_cap=g["traj"].shape[1])
+    tl, traj = out["traj_len"].cpu().numpy(), out["traj"].double().cpu().numpy()
+    ref = c_oracle.move_plan(oracle_chain, g["q_start"], g["target"], traj_cap=g["traj"].shape[1])
+    clean = ref["n_solves"] < ref["traj_len"]  # every solve accepted (points = start + solves [+ final target])
+    assert clean.sum() >= 12 and (~clean).sum() >= 4
+    for k in np.nonzero(clean)[0]:
+        L = int(g["traj_len"][k])
+        assert tl[k] == L
+        assert np.abs(traj[k, :L] - g["traj"][k, :L]).max() < 1e-4
+    for k in np.nonzero(~clean)[0]:
+        assert tl[k] == 202 and int(out["status"][k]) == 0
+    # q_final really is the joint solution of the last accepted waypoint
+    qf = out["q_final"].double().cpu().numpy()
+    ee = c_oracle.fk_jac(oracle_chain, qf)[0]
+    for k in range(len(tl)):
+        # the last accepted waypoint is the final point, or the one before an appended target
+        cands = [traj[k, tl[k] - 1]] + ([traj[k, tl[k] - 2]] if tl[k] > 1 else [])
+        assert min(np.linalg.norm(ee[k] - c) for c in cands) < 2e-5
+
+
+def test_planner_bounds_unreachable_targets_and_overflow(golden, oracle_chain):
+    q0 = torch.tensor(np.tile(NEUTRAL, (3, 1)), device="cuda")
+    tg = torch.tensor([[2.0, 0.0, 0.5], [1.415, 0.0, 0.73], [1.24, 0.0, 0.5]], dtype=torch.float64, device="cuda")
+    out = engine.move_ik_plan(q0, tg, engine.ik_params(), max_outer=300, traj_cap=64)
+    st, tl = out["status"].tolist(), out["traj_len"].tolist()
+    assert st[0] & 2 and st[0] & 4 and tl[0] > 64       # capped + overflow, like the bounded oracle
+    assert st[1] == 0 and tl[1] == 45 and st[2] == 0 and tl[2] == 1
+    ref = c_oracle.move_plan(oracle_chain, q0.cpu().numpy(), tg.cpu().numpy(), max_outer=300, traj_cap=64)
+    np.testing.assert_array_equal(out["traj_len"].cpu().numpy(), ref["traj_len"])
+    np.testing.assert_array_equal(out["n_solves"].cpu().numpy(), ref["n_solves"])
+    np.testing.assert_allclose(out["traj"].cpu().numpy()[:, :64], ref["traj"][:, :64], atol=1e-7)
+    with pytest.raises(ValueError):
+        engine.move_ik_plan(q0, tg, engine.ik_params(), traj_cap=1)
+
+
+def test_planner_batch_vs_c_oracle_fp64(golden, oracle_chain):
+    """2048 random shelf-box moves (BASELINE cfg4 distribution) through the whole state machine."""
+    n = 1024
+    w = synthetic.waypoint_envs(n, seed=11, dtype=torch.float64)
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    out = engine.move_ik_plan(w["q_start"].cuda(), w["goal"].cuda(), engine.ik_params(), counters=cnt)
+    # same bound as the device default (4*200+64): part of the shelf box is out of reach and the
+    # unbounded reference loop would never return there
+    ref = c_oracle.move_plan(oracle_chain, w["q_start"].numpy(), w["goal"].numpy(), max_outer=864, nthreads=8)
+    tl = out["traj_len"].cpu().numpy()
+    same = tl == ref["traj_len"]
+    assert same.mean() > 0.995
+    traj = out["traj"].cpu().numpy()
+    for k in np.nonzero(same)[0][:256]:
+        np.testing.assert_allclose(traj[k, : tl[k]], ref["traj"][k, : tl[k]], atol=1e-8)
+    assert int(cnt[0]) == int(out["n_solves"].sum())

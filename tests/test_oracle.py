@@ -214,3 +214,32 @@ def test_obs_oracle_bit_identical_to_reference_code(oracle_model):
     np.testing.assert_allclose((p1 - p0) / h * 0.05, obs[9, 3:6], atol=1e-7)
     # gimbal rows went through mat2euler's degenerate branch
     assert abs(abs(obs[0, 11]) - np.pi / 2) < 1e-6 and obs[0, 10] == 0.0
+
+
+# ------------------------------------------------------------------ MoveIKSkill planner
+def test_move_planner_oracles_match_reference_code(oracle_model, oracle_chain):
+    """tests/golden/move_reference_golden.npz = pos_traj of the reference's own MoveIKSkill.reset
+    (skills/move.py:76-191).  The NumPy restatement must be bit-identical on the short cases, the C
+    restatement within 1e-9 on all (incl. the ones whose IK solves fail on the way)."""
+    from oracle import move_oracle
+
+    g = np.load(os.path.join(GOLDEN, "move_reference_golden.npz"))
+    n = len(g["traj_len"])
+    assert n >= 18 and g["traj_len"].max() == 202 and g["traj_len"].min() == 1
+    r = c_oracle.move_plan(oracle_chain, g["q_start"], g["target"], traj_cap=g["traj"].shape[1], nthreads=4)
+    np.testing.assert_array_equal(r["traj_len"], g["traj_len"])
+    assert (r["status"] == 0).all()
+    for k in range(n):
+        L = int(g["traj_len"][k])
+        np.testing.assert_allclose(r["traj"][k, :L], g["traj"][k, :L], atol=1e-9)
+    assert (r["n_solves"] > r["traj_len"]).sum() >= 4  # the failing-solve cases really failed on the way
+    for k in range(6):  # NumPy restatement: bit-identical (kept to the short cases for run time)
+        o = move_oracle.plan(oracle_model, g["q_start"][k], g["target"][k])
+        np.testing.assert_array_equal(o["pos_traj"], g["traj"][k, : int(g["traj_len"][k])])
+
+
+def test_move_planner_never_terminates_on_unreachable_targets_without_a_bound(oracle_chain):
+    """Reference quirk: for an unreachable target fallback strategy 1 keeps succeeding with ever
+    smaller steps and never advances point_count; only an explicit bound stops the loop."""
+    r = c_oracle.move_plan(oracle_chain, NEUTRAL[None], np.array([[2.0, 0.0, 0.5]]), max_outer=400, traj_cap=64)
+    assert r["status"][0] & 2 and r["status"][0] & 4 and r["traj_len"][0] > 200
