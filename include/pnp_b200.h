@@ -17,6 +17,8 @@
  *   pnp_get_obs_*          FrankaEnv._get_obs (envs/panda_env.py:279-301) from kinematic state
  *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
  *                          (envs/panda_env.py:205-245, 303-306, 311-315), row-wise
+ *   pnp_her_relabel_f32    HER goal relabel + reward + VecNormalize over stored transitions
+ *                          (scripts/train.py:4,68,74-93; SB3 HerReplayBuffer semantics)
  *   pnp_*_host             the same operators taking HOST buffers (what a Python/ctypes
  *                          caller of the reference API holds): chunked H2D -> kernel -> D2H
  *                          pipeline on library-owned streams
@@ -195,6 +197,27 @@ int pnp_reward_f64(const double* ag, const double* dg, const double* ee_pos, con
                    const double* width, const int32_t* task_index, int64_t n,
                    const PnpRewardParams* params, float* reward, float* is_success,
                    unsigned long long* counters, void* stream);
+/* ---- HER relabel + obs assembly (what scripts/train.py:4 "TQC(+HER)" promises) ------------- */
+/* VecNormalize.normalize_obs parameters (scripts/checkpoints/tqc_dense_vecnormalize_*.pkl):
+ * rows are clip((x - mean) / sqrt(var + epsilon), +-clip_obs) per column of the 25-wide row. */
+typedef struct PnpNormalizeParams {
+  double mean[25];
+  double var[25];
+  double epsilon;   /* 1e-8 */
+  double clip_obs;  /* 10.0 */
+} PnpNormalizeParams;
+/* obs / next_obs: float[n,25] = observation[19] | achieved_goal[3] | desired_goal[3] (the layout
+ * pnp_get_obs_* writes).  Per transition i: new goal = next_obs[future_idx[i]].achieved_goal
+ * (future_idx[i] < 0 keeps the stored goal); both rows get the new desired_goal; reward[i] =
+ * compute_reward(next_obs[i].achieved_goal, new goal) with ee_pos = next_obs[i][0:3],
+ * fingers_width = next_obs[i][6], ee_quat[n,4] and task_index[n] from the side arrays (bit-exact,
+ * same arithmetic as pnp_reward_f32); is_success (nullable); rows optionally normalised (norm
+ * nullable = copy through).  Outputs must not alias inputs.  counters as pnp_reward_*. */
+int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* future_idx, const float* ee_quat,
+                        const int32_t* task_index, int64_t n, const PnpRewardParams* params,
+                        const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
+                        float* is_success, unsigned long long* counters, void* stream);
+
 /* goal_distance (panda_env.py:311-315): a[n,3], b[n,3] -> d[n] (FP64 math) */
 int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream);
 

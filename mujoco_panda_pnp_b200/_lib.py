@@ -54,6 +54,15 @@ class PnpMoveParams(ctypes.Structure):
     ]
 
 
+class PnpNormalizeParams(ctypes.Structure):
+    _fields_ = [
+        ("mean", c_double * 25),
+        ("var", c_double * 25),
+        ("epsilon", c_double),
+        ("clip_obs", c_double),
+    ]
+
+
 class PnpLibraryError(RuntimeError):
     pass
 
@@ -81,6 +90,8 @@ SIGNATURES = {
     "pnp_reward_f64": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
     "pnp_get_obs_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_double, _P, c_int32, _P]),
     "pnp_get_obs_f64": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_double, _P, c_int32, _P]),
+    "pnp_her_relabel_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), POINTER(PnpNormalizeParams),
+                                    _P, _P, _P, _P, _P, _P]),
     "pnp_goal_distance_f64": (c_int, [_P, _P, c_int64, _P, _P]),
     "pnp_host_ctx_create": (c_int, [POINTER(c_void_p), c_int64]),
     "pnp_host_ctx_destroy": (c_int, [c_void_p]),

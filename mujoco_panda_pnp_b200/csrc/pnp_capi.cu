@@ -529,6 +529,61 @@ int pnp_get_obs_f64(const double* q_arm, const double* qvel_arm, const double* f
                               kinematics, stream);
 }
 
+int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* future_idx, const float* ee_quat,
+                        const int32_t* task_index, int64_t n, const PnpRewardParams* params,
+                        const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
+                        float* is_success, unsigned long long* counters, void* stream) {
+  if (!params) return fail(PNP_EINVAL, "params is NULL");
+  if (params->n_tasks <= 0) return fail(PNP_EINVAL, "n_tasks must be > 0");
+  if (n < 0 || (n > 0 && (!obs || !next_obs || !future_idx || !ee_quat || !task_index || !out_obs || !out_next_obs || !reward)))
+    return fail(PNP_EINVAL, "her_relabel: null pointer or negative n");
+  if (n > 0 && (out_obs == obs || out_next_obs == next_obs || out_obs == next_obs || out_next_obs == obs))
+    return fail(PNP_EINVAL, "her_relabel: outputs must not alias inputs (future goals are gathered from next_obs)");
+  if (n > 0 && !aligned16(ee_quat)) return fail(PNP_EINVAL, "her_relabel: ee_quat must be 16-byte aligned");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::HerArgs a;
+  a.obs = obs; a.next_obs = next_obs; a.future_idx = future_idx; a.ee_quat = ee_quat; a.task = task_index;
+  a.n_total = n; a.k = make_reward_const(params);
+  a.out_obs = out_obs; a.out_next = out_next_obs; a.reward = reward; a.success = is_success; a.counters = counters;
+  a.normalize = norm ? 1 : 0;
+  a.clip = norm ? (float)norm->clip_obs : 0.f;
+  for (int k = 0; k < pnp::HER_ROW; ++k) {
+    a.mean_hi[k] = norm ? (float)norm->mean[k] : 0.f;
+    a.mean_lo[k] = norm ? (float)(norm->mean[k] - (double)a.mean_hi[k]) : 0.f;
+    a.inv_std[k] = norm ? (float)(1.0 / std::sqrt(norm->var[k] + norm->epsilon)) : 1.f;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem_bulk = 2 * 2 * pnp::HER_TILE_BYTES, smem_plain = 2 * pnp::HER_TILE_BYTES;
+  static bool attr_set[kMaxDevices] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(pnp::her_relabel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk));
+    attr_set[dev] = true;
+  }
+  const bool bulk_ok = aligned16(obs) && aligned16(next_obs) && aligned16(out_obs) && aligned16(out_next_obs);
+  const int64_t full = bulk_ok ? (n / pnp::HER_TILE) * pnp::HER_TILE : 0;
+  if (full > 0) {
+    a.row0 = 0; a.n = full;
+    const int grid = grid_for(full, pnp::HER_TILE, s->sm_count, 4);
+    pnp::her_relabel_kernel<true><<<grid, pnp::HER_TILE, smem_bulk, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (n - full > 0) {  // ragged tail (< 128 rows) or unaligned buffers: plain staged copies
+    pnp::HerArgs t = a;
+    t.row0 = full; t.n = n - full;  // each launch adds its own row count to counters[N]
+    const int grid = grid_for(n - full, pnp::HER_TILE, s->sm_count, 8);
+    pnp::her_relabel_kernel<false><<<grid, pnp::HER_TILE, smem_plain, st>>>(t);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return PNP_OK;
+}
+
 int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream) {
   if (n < 0 || (n > 0 && (!a || !b || !d))) return fail(PNP_EINVAL, "goal_distance: null pointer or negative n");
   DeviceState* s;

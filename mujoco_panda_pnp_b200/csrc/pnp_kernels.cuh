@@ -776,6 +776,198 @@ __global__ void __launch_bounds__(256) reward_kernel(const RewardArgs<TIn> a) {
   }
 }
 
+// =============================================================================================
+// HER relabel + obs assembly: what `train.py:4` promises ("TQC(+HER)") and SB3's
+// HerReplayBuffer would do per sampled transition - done in one streaming pass:
+//   new_goal   = next_obs[future_idx].achieved_goal   (future_idx < 0: keep the stored goal)
+//   obs.dg = next_obs.dg = new_goal
+//   reward     = compute_reward(next_obs.achieved_goal, new_goal, info)   (bit-exact, reward_row)
+//   is_success = ||ag - new_goal|| < distance_threshold
+//   rows      -> VecNormalize.normalize_obs: clip((x - mean) / sqrt(var + eps), +-clip_obs)  (optional)
+// Rows are the critic-ready layout [observation19 | achieved_goal3 | desired_goal3] in FP32
+// (100 B).  ee_pos and fingers_width come from the row itself (observation[0:3], [6]); ee_quat
+// and task_index are not part of the observation and ride in side arrays.
+//
+// Data movement: 100-byte rows are not 16-byte multiples, so tiles of 128 rows (12.8 KB per
+// array) are staged through shared memory.  Full tiles use the Blackwell/Hopper bulk-async-copy
+// engine (cp.async.bulk global->shared completing on an mbarrier, shared->global bulk store),
+// double buffered: one elected thread moves 51 KB per tile while the other 127 only compute.
+// Each lane owns one row of the tile in shared memory (stride 25 words: conflict-free).
+// Algorithmic traffic 464 B per transition: 200 read + 200 written + 64 reward stream.
+// =============================================================================================
+constexpr int HER_TILE = 128;
+constexpr int HER_ROW = 25;
+constexpr int HER_TILE_BYTES = HER_TILE * HER_ROW * 4;  // 12800
+
+struct HerArgs {
+  const float* obs;
+  const float* next_obs;
+  const int32_t* future_idx;
+  const float* ee_quat;
+  const int32_t* task;
+  long long n;          // rows handled by this launch
+  long long n_total;    // rows addressable through future_idx
+  long long row0;       // first row of this launch (tail launches start past the full tiles)
+  RewardConst k;
+  float* out_obs;
+  float* out_next;
+  float* reward;
+  float* success;
+  int normalize;
+  float clip;
+  float mean_hi[HER_ROW];  // mean = mean_hi + mean_lo (two-float split of the FP64 statistic: the
+  float mean_lo[HER_ROW];  // desired_goal columns have var ~1e-9, so x - mean must not lose the low bits)
+  float inv_std[HER_ROW];
+  unsigned long long* counters;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// relabel + reward + normalise one row held in shared memory (o = obs row, x = next_obs row)
+__device__ __forceinline__ void her_row(const HerArgs& a, long long row, float* o, float* x, unsigned& pl, unsigned& gr,
+                                        unsigned& ad) {
+  const int fi = a.future_idx[row];
+  float g[3] = {x[22], x[23], x[24]};
+  if (fi >= 0) {
+    const float* src = a.next_obs + (long long)fi * HER_ROW + 19;   // future achieved_goal (original rows)
+    g[0] = src[0]; g[1] = src[1]; g[2] = src[2];
+  }
+  const float ag[3] = {x[19], x[20], x[21]};
+  const float ee[3] = {x[0], x[1], x[2]};
+  const float4 qv = *reinterpret_cast<const float4*>(a.ee_quat + row * 4);
+  const float eq[4] = {qv.x, qv.y, qv.z, qv.w};
+  float succ;
+  const float r = reward_row<float>(ag, g, ee, eq, x[6], a.task[row], a.k, &succ, pl, gr, ad);
+  a.reward[row] = r;
+  if (a.success) a.success[row] = succ;
+  o[22] = g[0]; o[23] = g[1]; o[24] = g[2];
+  x[22] = g[0]; x[23] = g[1]; x[24] = g[2];
+  if (a.normalize) {
+#pragma unroll
+    for (int k = 0; k < HER_ROW; ++k) {
+      o[k] = fminf(fmaxf(((o[k] - a.mean_hi[k]) - a.mean_lo[k]) * a.inv_std[k], -a.clip), a.clip);
+      x[k] = fminf(fmaxf(((x[k] - a.mean_hi[k]) - a.mean_lo[k]) * a.inv_std[k], -a.clip), a.clip);
+    }
+  }
+}
+
+template <bool kBulk>
+__global__ void __launch_bounds__(HER_TILE) her_relabel_kernel(const HerArgs a) {
+  extern __shared__ __align__(128) unsigned char her_smem[];
+  float* buf = reinterpret_cast<float*>(her_smem);  // [stage][obs|next][HER_TILE*HER_ROW]
+  __shared__ unsigned long long bar[2];
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u;
+  unsigned long long c_placed = 0, c_gripped = 0, c_adj = 0;
+  const long long n_tiles = (a.n + HER_TILE - 1) / HER_TILE;
+  auto stage_ptr = [&](int stage, int which) { return buf + (stage * 2 + which) * (HER_TILE * HER_ROW); };
+
+  if (kBulk) {
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    long long t = blockIdx.x;
+    if (t < n_tiles && tid == 0) {
+      const long long r0 = a.row0 + t * HER_TILE;
+      mbar_expect_tx(&bar[0], 2 * HER_TILE_BYTES);
+      bulk_g2s(stage_ptr(0, 0), a.obs + r0 * HER_ROW, HER_TILE_BYTES, &bar[0]);
+      bulk_g2s(stage_ptr(0, 1), a.next_obs + r0 * HER_ROW, HER_TILE_BYTES, &bar[0]);
+    }
+    for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+      const int stage = it & 1;
+      const long long tn = t + gridDim.x;
+      if (tid == 0 && tn < n_tiles) {
+        bulk_wait_read_all();  // the store that last read stage^1 has drained its shared-memory reads
+        const long long rn = a.row0 + tn * HER_TILE;
+        mbar_expect_tx(&bar[stage ^ 1], 2 * HER_TILE_BYTES);
+        bulk_g2s(stage_ptr(stage ^ 1, 0), a.obs + rn * HER_ROW, HER_TILE_BYTES, &bar[stage ^ 1]);
+        bulk_g2s(stage_ptr(stage ^ 1, 1), a.next_obs + rn * HER_ROW, HER_TILE_BYTES, &bar[stage ^ 1]);
+      }
+      mbar_wait(&bar[stage], (unsigned)((it >> 1) & 1));
+      const long long row = a.row0 + t * HER_TILE + tid;
+      unsigned pl, gr, ad;
+      her_row(a, row, stage_ptr(stage, 0) + tid * HER_ROW, stage_ptr(stage, 1) + tid * HER_ROW, pl, gr, ad);
+      c_placed += pl; c_gripped += gr; c_adj += ad;
+      fence_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async) proxy
+      __syncthreads();
+      if (tid == 0) {
+        const long long r0 = a.row0 + t * HER_TILE;
+        bulk_s2g(a.out_obs + r0 * HER_ROW, stage_ptr(stage, 0), HER_TILE_BYTES);
+        bulk_s2g(a.out_next + r0 * HER_ROW, stage_ptr(stage, 1), HER_TILE_BYTES);
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait_all();
+  } else {
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const long long r0 = a.row0 + t * HER_TILE;
+      const long long rows = (a.row0 + a.n - r0 < HER_TILE) ? a.row0 + a.n - r0 : HER_TILE;
+      float* so = stage_ptr(0, 0);
+      float* sx = stage_ptr(0, 1);
+      for (int i = tid; i < rows * HER_ROW; i += HER_TILE) {
+        so[i] = a.obs[r0 * HER_ROW + i];
+        sx[i] = a.next_obs[r0 * HER_ROW + i];
+      }
+      __syncthreads();
+      if (tid < rows) {
+        unsigned pl, gr, ad;
+        her_row(a, r0 + tid, so + tid * HER_ROW, sx + tid * HER_ROW, pl, gr, ad);
+        c_placed += pl; c_gripped += gr; c_adj += ad;
+      }
+      __syncthreads();
+      for (int i = tid; i < rows * HER_ROW; i += HER_TILE) {
+        a.out_obs[r0 * HER_ROW + i] = so[i];
+        a.out_next[r0 * HER_ROW + i] = sx[i];
+      }
+      __syncthreads();
+    }
+  }
+  if (a.counters) {
+    c_placed = warp_sum(c_placed); c_gripped = warp_sum(c_gripped); c_adj = warp_sum(c_adj);
+    if (lane == 0) {
+      if (blockIdx.x == 0 && tid == 0) atomicAdd(a.counters + PNP_RW_CNT_N, (unsigned long long)a.n);
+      atomicAdd(a.counters + PNP_RW_CNT_PLACED, c_placed);
+      atomicAdd(a.counters + PNP_RW_CNT_GRIPPED, c_gripped);
+      atomicAdd(a.counters + PNP_RW_CNT_THRESHOLD_ADJACENT, c_adj);
+    }
+  }
+}
+
 // goal_distance (panda_env.py:311-315)
 __global__ void goal_distance_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n,
                                      double* __restrict__ d) {

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import KINEMATICS, PnpIkParams, PnpMoveParams, PnpRewardParams
+from ._lib import KINEMATICS, PnpIkParams, PnpMoveParams, PnpNormalizeParams, PnpRewardParams
 from .tree import KinematicTree, PnpTreeStruct
 
 _uploaded: Dict[int, bytes] = {}  # device index -> bytes of the PnpTree currently in constant memory
@@ -361,6 +361,52 @@ def get_obs(q_arm, qvel_arm, fingers, obj_pos, obj_quat, obj_vel, goal, dt: floa
             "pnp_get_obs",
         )
     return out
+
+
+def normalize_params(mean, var, epsilon: float = 1e-8, clip_obs: float = 10.0) -> PnpNormalizeParams:
+    """VecNormalize statistics for the 25-wide row: observation[19] | achieved_goal[3] | desired_goal[3]."""
+    mean = np.asarray(mean, dtype=np.float64).reshape(-1)
+    var = np.asarray(var, dtype=np.float64).reshape(-1)
+    if mean.shape != (25,) or var.shape != (25,):
+        raise ValueError("mean and var must have 25 entries (obs19 | ag3 | dg3)")
+    p = PnpNormalizeParams()
+    p.mean[:] = mean.tolist()
+    p.var[:] = var.tolist()
+    p.epsilon, p.clip_obs = float(epsilon), float(clip_obs)
+    return p
+
+
+def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewardParams,
+                norm: Optional[PnpNormalizeParams] = None, want_success: bool = True,
+                counters: Optional[torch.Tensor] = None, out_obs=None, out_next_obs=None, out_reward=None):
+    """HER relabel + reward + optional VecNormalize over N stored transitions (CUDA float32).
+
+    obs / next_obs: [N,25] rows (observation19 | achieved_goal3 | desired_goal3); future_idx int32[N]
+    (row whose next achieved_goal becomes the goal, < 0 keeps the stored one); ee_quat[N,4];
+    task_index int32[N].  Returns (out_obs[N,25], out_next_obs[N,25], reward[N], is_success[N] | None)."""
+    lib = _lib.load()
+    obs = _check_cuda("obs", obs, torch.float32, (25,))
+    next_obs = _check_cuda("next_obs", next_obs, torch.float32, (25,))
+    future_idx = _check_cuda("future_idx", future_idx, torch.int32, ())
+    ee_quat = _check_cuda("ee_quat", ee_quat, torch.float32, (4,))
+    task_index = _check_cuda("task_index", task_index, torch.int32, ())
+    n = obs.shape[0]
+    for name, t in (("next_obs", next_obs), ("future_idx", future_idx), ("ee_quat", ee_quat), ("task_index", task_index)):
+        if t.shape[0] != n:
+            raise ValueError(f"{name} disagrees with obs on N")
+    dev = obs.device
+    o = out_obs if out_obs is not None else torch.empty_like(obs)
+    x = out_next_obs if out_next_obs is not None else torch.empty_like(next_obs)
+    r = out_reward if out_reward is not None else torch.empty((n,), dtype=torch.float32, device=dev)
+    sc = torch.empty((n,), dtype=torch.float32, device=dev) if want_success else None
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.pnp_her_relabel_f32(_ptr(obs), _ptr(next_obs), _ptr(future_idx), _ptr(ee_quat), _ptr(task_index), n,
+                                    ctypes.byref(params), ctypes.byref(norm) if norm is not None else None, _ptr(o),
+                                    _ptr(x), _ptr(r), _ptr(sc), _ptr(counters), _stream()),
+            "pnp_her_relabel",
+        )
+    return o, x, r, sc
 
 
 def goal_distance(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
