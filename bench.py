@@ -389,6 +389,62 @@ def run_ours(args) -> int:
         side["cfg4"] = {"workload": "2^20 envs x 50 warm-started waypoint solves, 1 launch",
                         "ms_per_launch": min(ts), "warm_solves_per_s": float(cw[0]) / (min(ts) * 1e-3),
                         "mean_iterations": float(cw[3]) / max(1.0, float(cw[0]))}
+        # cfg1: single-query latency through the drop-in controller (host in, host out)
+        from mujoco_panda_pnp_b200 import KinematicData, KinematicModel
+        from mujoco_panda_pnp_b200.skills import JacobianIKController
+
+        kmodel = KinematicModel.from_xml_path(os.path.join(ROOT, "mujoco_panda_pnp_b200", "assets", "panda_shelf_kinematic.xml"))
+        ctl = JacobianIKController(kmodel, KinematicData(kmodel))
+        grasp = [np.array(t) for t in [(1.415, 0, 0.73), (1.415, 0, 1.03), (1.415, 0, 0.43)]]
+        for t_ in grasp:
+            ctl.solve(t_, NEUTRAL)
+        t0 = time.perf_counter()
+        reps = 50
+        its = []
+        for _ in range(reps):
+            for t_ in grasp:
+                its.append(ctl.solve(t_, NEUTRAL).iterations)
+        side["cfg1"] = {"workload": "single-query solve() to the 3 shelf grasp poses from neutral (test/ik_test.py path)",
+                        "us_per_solve_host_to_host": (time.perf_counter() - t0) / (3 * reps) * 1e6,
+                        "iterations": its[:3]}
+        # whole MoveIKSkill.reset planner, 2^18 envs in one launch
+        n_pl = 1 << 18
+        wp = synthetic.reachable_move_envs(n_pl, tree.lower, tree.upper, seed=1, device=dev)
+        wp["goal"] = engine.fk_jac(wp["q_goal"], want_quat=False, want_jac=False)[0]
+        cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+        engine.move_ik_plan(wp["q_start"], wp["goal"], params, counters=cnt)
+        torch.cuda.synchronize()
+        cp = cnt.cpu().numpy()
+        _, ts = cuda_time_steps(lambda: engine.move_ik_plan(wp["q_start"], wp["goal"], params), 2, torch)
+        side["move_planner"] = {"workload": "2^18 MoveIKSkill.reset plans, reachable goals FK(neutral +- 0.6 rad), 1 launch",
+                                "ms_per_launch": min(ts),
+                                "plans_per_s": n_pl / (min(ts) * 1e-3), "ik_solves_per_s": float(cp[0]) / (min(ts) * 1e-3),
+                                "mean_solves_per_plan": float(cp[0]) / n_pl}
+        del wp
+        # HER relabel + reward + VecNormalize over stored transitions (464 B/transition)
+        n_h = 1 << 23
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        h_next = torch.randn((n_h, 25), generator=g, device=dev)
+        h_obs = h_next + 0.01
+        h_fut = torch.randint(-1, n_h, (n_h,), generator=g, device=dev, dtype=torch.int32)
+        h_quat = torch.randn((n_h, 4), generator=g, device=dev)
+        h_task = torch.randint(0, 3, (n_h,), generator=g, device=dev, dtype=torch.int32)
+        h_o, h_x, h_r = torch.empty_like(h_obs), torch.empty_like(h_next), torch.empty(n_h, device=dev)
+        nrm = engine.normalize_params(np.zeros(25), np.ones(25))
+        f_her = lambda: engine.her_relabel(h_obs, h_next, h_fut, h_quat, h_task, rw_params, norm=nrm, want_success=False,  # noqa: E731
+                                           out_obs=h_o, out_next_obs=h_x, out_reward=h_r)
+        for _ in range(3):
+            f_her()
+        _, ts = cuda_time_steps(f_her, 10, torch)
+        ms = statistics.median(ts)
+        side["her_relabel"] = {"workload": "2^23 stored transitions: gather future goal, relabel obs/next_obs, reward, VecNormalize",
+                               "ms_per_launch": ms, "transitions_per_s": n_h / (ms * 1e-3),
+                               "roofline": {"bound": "hbm", "achieved": 464.0 * n_h / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                            "unit": "GB/s", "frac": 464.0 * n_h / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                            "algorithmic": "464 B/transition (200 read + 200 written + 64 reward stream, SURVEY 8d)",
+                                            "kernel": "her_relabel_kernel<true>"}}
+        del h_next, h_obs, h_o, h_x
     clocks = sampler.stop()
 
     # ---------------- CPU baselines (rank 0, N=1 only) ----------------------------------

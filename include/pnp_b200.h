@@ -13,6 +13,8 @@
  *   pnp_ik_solve_*         JacobianIKController.solve (ik_solver.py:35-101), batched
  *   pnp_ik_waypoints_*     the warm-started solve sequence of MoveIKSkill.reset
  *                          (skills/move.py:106-137), fixed number of waypoints per env
+ *   pnp_ik_pose_solve_*    FrankaEnv.solve_ik(target_pos, target_quat, q_init) (panda_env.py:399-409;
+ *                          dangling in the reference - an extension defined here)
  *   pnp_move_ik_plan_*     the whole MoveIKSkill.reset planner (skills/move.py:76-191)
  *   pnp_get_obs_*          FrankaEnv._get_obs (envs/panda_env.py:279-301) from kinematic state
  *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
@@ -158,6 +160,25 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
                          double step_size, const PnpIkParams* params, float* q_out, float* pos_out,
                          int32_t* n_accepted, int32_t* iters_total, unsigned long long* counters,
                          void* stream);
+
+/* ---- pose-mode IK: 6-row task, 6x6 solve (EXTENSION, fills FrankaEnv.solve_ik, panda_env.py:399-409) */
+/* target_pos[n,3], target_quat[n,4] wxyz (normalised on load).  e = [pos error; rot_weight * rotation
+ * vector of target (x) conj(site quat)] in the world frame, J = [jacp; rot_weight * jacr],
+ * dq = J^T (J J^T + damping I6)^-1 e, same clips and loop semantics as pnp_ik_solve_*; converged
+ * when |pos error| < pos_thresh and |rotation vector| < rot_thresh.  The reference has no such
+ * function (it imports a missing name), so parity is against this repo's own FP64 restatement.
+ * Outputs: q_out[n,7], final_pos[n,3], final_quat[n,4], pos_err[n], rot_err[n] (rad), iters, flags
+ * (all but q_out nullable), counters[4] (nullable). */
+int pnp_ik_pose_solve_f32(const float* target_pos, const float* target_quat, const float* q_init,
+                          int32_t q_init_stride, int64_t n, const PnpIkParams* params, double rot_thresh,
+                          double rot_weight, float* q_out, float* final_pos, float* final_quat, float* pos_err,
+                          float* rot_err, int32_t* iters, uint8_t* flags, unsigned long long* counters,
+                          void* stream);
+int pnp_ik_pose_solve_f64(const double* target_pos, const double* target_quat, const double* q_init,
+                          int32_t q_init_stride, int64_t n, const PnpIkParams* params, double rot_thresh,
+                          double rot_weight, double* q_out, double* final_pos, double* final_quat,
+                          double* pos_err, double* rot_err, int32_t* iters, uint8_t* flags,
+                          unsigned long long* counters, void* stream);
 
 /* ---- full MoveIKSkill.reset trajectory planner (skills/move.py:76-191) -------------------- */
 typedef struct PnpMoveParams {

@@ -453,6 +453,41 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
 
 namespace {
 template <typename T>
+int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_init_stride, int64_t n,
+                    const PnpIkParams* params, double rot_thresh, double rot_weight, T* q_out, T* final_pos,
+                    T* final_quat, T* pos_err, T* rot_err, int32_t* iters, uint8_t* flags,
+                    unsigned long long* counters, void* stream) {
+  int rc = check_ik_params(params);
+  if (rc) return rc;
+  if (!(rot_thresh > 0.0) || !(rot_weight > 0.0)) return fail(PNP_EINVAL, "rot_thresh and rot_weight must be > 0");
+  if (n < 0 || (n > 0 && (!tpos || !tquat || !q_init || !q_out)))
+    return fail(PNP_EINVAL, "ik_pose_solve: null pointer or negative n");
+  if (q_init_stride != 0 && q_init_stride != PNP_NJOINT) return fail(PNP_EINVAL, "q_init_stride must be 0 or 7");
+  DeviceState* s;
+  if ((rc = current_state(&s))) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  pnp::PoseIkArgs<T> a;
+  a.target_pos = tpos; a.target_quat = tquat; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = n;
+  a.k = make_ik_const<T>(params);
+  a.rot_thresh = (T)rot_thresh; a.rot_weight = (T)rot_weight;
+  a.q_out = q_out; a.final_pos = final_pos; a.final_quat = final_quat; a.pos_err = pos_err; a.rot_err = rot_err;
+  a.iters = iters; a.flags = flags; a.counters = counters;
+  const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spec)
+    pnp::ik_pose_solve_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
+  else
+    pnp::ik_pose_solve_kernel<T, pnp::GenericKin><<<grid, block, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+template <typename T>
 int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMoveParams* mp, const PnpIkParams* params,
                    T* traj, int32_t* traj_len, T* q_final, int32_t* n_solves, int32_t* status,
                    unsigned long long* counters, void* stream) {
@@ -492,6 +527,21 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
 }  // namespace
 
 extern "C" {
+
+int pnp_ik_pose_solve_f32(const float* target_pos, const float* target_quat, const float* q_init,
+                          int32_t q_init_stride, int64_t n, const PnpIkParams* params, double rot_thresh,
+                          double rot_weight, float* q_out, float* final_pos, float* final_quat, float* pos_err,
+                          float* rot_err, int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream) {
+  return pose_solve_impl<float>(target_pos, target_quat, q_init, q_init_stride, n, params, rot_thresh, rot_weight, q_out,
+                                final_pos, final_quat, pos_err, rot_err, iters, flags, counters, stream);
+}
+int pnp_ik_pose_solve_f64(const double* target_pos, const double* target_quat, const double* q_init,
+                          int32_t q_init_stride, int64_t n, const PnpIkParams* params, double rot_thresh,
+                          double rot_weight, double* q_out, double* final_pos, double* final_quat, double* pos_err,
+                          double* rot_err, int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream) {
+  return pose_solve_impl<double>(target_pos, target_quat, q_init, q_init_stride, n, params, rot_thresh, rot_weight, q_out,
+                                 final_pos, final_quat, pos_err, rot_err, iters, flags, counters, stream);
+}
 
 int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, const PnpMoveParams* mp,
                          const PnpIkParams* params, float* traj, int32_t* traj_len, float* q_final,

@@ -5,7 +5,7 @@
 
 namespace pnp {
 
-constexpr int IK_BLOCK = 128;
+constexpr int IK_BLOCK = 128;  // (forcing 8 blocks/SM = 64 regs was measured: no gain, generic path spills)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -380,6 +380,181 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
       for (int i = 0; i < 3; ++i) a.pos_out[e * 3 + i] = pos[i];
       if (a.n_accepted) a.n_accepted[e] = accepted;
       if (a.iters_total) a.iters_total[e] = iters_sum;
+    }
+  }
+  if (a.counters) {
+    c_n = warp_sum(c_n); c_conv = warp_sum(c_conv); c_iter = warp_sum(c_iter);
+    if (lane == 0) {
+      atomicAdd(a.counters + PNP_IK_CNT_N, c_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, c_iter);
+    }
+  }
+}
+
+// =============================================================================================
+// Pose-mode IK (an EXTENSION: the reference's FrankaEnv.solve_ik(target_pos,
+// target_quat, q_init) at envs/panda_env.py:399-409 imports a function that does not exist, so
+// there is no reference arithmetic to match).  Same loop as the position solver with a 6-row task:
+//   e = [target_pos - p ;  w * rotvec(target_quat (x) conj(site_quat))]      (world frame)
+//   J = [jacp ; w * jacr]  (6x7, mj_jacSite),  dq = J^T (J J^T + damping I_6)^-1 e
+//   converged  <=>  |e_pos| < pos_thresh  and  |rotvec| < rot_thresh          (tested before update)
+// The 6x6 SPD system is solved by an LDL^T factorisation held in registers.  One lane per query.
+// =============================================================================================
+template <typename T>
+struct PoseIkArgs {
+  const T* target_pos;
+  const T* target_quat;
+  const T* q_init;
+  int q_init_stride;
+  long long n;
+  IkConst<T> k;
+  T rot_thresh, rot_weight;
+  T* q_out;
+  T* final_pos;
+  T* final_quat;
+  T* pos_err;
+  T* rot_err;
+  int32_t* iters;
+  uint8_t* flags;
+  unsigned long long* counters;
+};
+
+// mju_quat2Vel(res, quat, 1): rotation vector of a unit quaternion, angle folded into (-pi, pi]
+template <typename T>
+__device__ __forceinline__ void quat2vel(const T* q, T* v) {
+  const T sin_a_2 = sqrt_t(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  T speed = T(2) * atan2_t(sin_a_2, q[0]);
+  if (speed > T(3.14159265358979323846)) speed -= T(6.28318530717958647692);
+  const T sc = sin_a_2 > T(0) ? speed / sin_a_2 : T(0);
+  v[0] = q[1] * sc; v[1] = q[2] * sc; v[2] = q[3] * sc;
+}
+
+// solve the SPD system A y = b, A given by its lower triangle L[i][j] (j <= i), in place (LDL^T)
+template <typename T, int N>
+__device__ __forceinline__ void ldlt_solve(T (&A)[N][N], T (&b)[N]) {
+  T dg[N], dinv[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    T d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k] * dg[k];
+    dg[j] = d;
+    dinv[j] = T(1) / d;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      T v = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k] * dg[k];
+      A[i][j] = v * dinv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int k = 0; k < i; ++k) b[i] -= A[i][k] * b[k];
+#pragma unroll
+  for (int i = 0; i < N; ++i) b[i] *= dinv[i];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i)
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) b[i] -= A[k][i] * b[k];
+}
+
+template <typename T, typename Kin>
+__global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArgs<T> a) {
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
+  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < a.n;
+       base += (long long)gridDim.x * blockDim.x) {
+    const long long e = base + lane;
+    const bool valid = e < a.n;
+    T q[NJ], tp[3], tq[4];
+    const T* qi = a.q_init + (valid ? (long long)a.q_init_stride * e : 0);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tp[i] = valid ? a.target_pos[e * 3 + i] : T(0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tq[i] = valid ? a.target_quat[e * 4 + i] : (i == 0 ? T(1) : T(0));
+    {
+      const T nq = sqrt_t(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tq[i] = tq[i] / nq;
+    }
+    int it = 0;
+    bool done = !valid, conv = false;
+    T p[3] = {T(0), T(0), T(0)}, qc[4] = {T(1), T(0), T(0), T(0)}, perr = T(0), rerr = T(0);
+    while (__any_sync(FULL, !done)) {
+      T s[NJ], c[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) sincos_t(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
+      T pp[3], J[42], R[9], qcur[4];
+      Kin::template fk_full<T>(s, c, pp, J, R);
+      mat2quat<T>(R, qcur);
+      // err_quat = target (x) conj(current); rotation vector in the world frame
+      const T eq[4] = {tq[0] * qcur[0] + tq[1] * qcur[1] + tq[2] * qcur[2] + tq[3] * qcur[3],
+                       -tq[0] * qcur[1] + tq[1] * qcur[0] - tq[2] * qcur[3] + tq[3] * qcur[2],
+                       -tq[0] * qcur[2] + tq[1] * qcur[3] + tq[2] * qcur[0] - tq[3] * qcur[1],
+                       -tq[0] * qcur[3] - tq[1] * qcur[2] + tq[2] * qcur[1] + tq[3] * qcur[0]};
+      T rv[3];
+      quat2vel<T>(eq, rv);
+      T err[6] = {tp[0] - pp[0], tp[1] - pp[1], tp[2] - pp[2], rv[0] * a.rot_weight, rv[1] * a.rot_weight,
+                  rv[2] * a.rot_weight};
+      const T pe = sqrt_t((err[0] * err[0] + err[1] * err[1]) + err[2] * err[2]);
+      const T re = sqrt_t((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+      if (!done) {
+        const bool last = it >= a.k.max_iters;
+        conv = !last && (pe < a.k.pos_thresh) && (re < a.rot_thresh);
+        if (conv || last) {
+          p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) qc[i] = qcur[i];
+          perr = pe; rerr = re;
+          it = conv ? it + 1 : it;
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { J[21 + j] *= a.rot_weight; J[28 + j] *= a.rot_weight; J[35 + j] *= a.rot_weight; }
+        T A[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c2 = 0; c2 <= r; ++c2) {
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * J[c2 * 7 + j];
+            A[r][c2] = acc + (r == c2 ? a.k.damping : T(0));
+          }
+        ldlt_solve<T, 6>(A, err);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          T dq = T(0);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dq = dq + J[r * 7 + j] * err[r];
+          dq = clamp_t(dq, -a.k.step_limit, a.k.step_limit);
+          q[j] = clamp_t(q[j] + dq, Kin::template lower<T>(j), Kin::template upper<T>(j));
+        }
+        ++it;
+      }
+    }
+    if (valid) {
+      const bool success = conv && (perr < a.k.pos_thresh * T(2)) && (rerr < a.rot_thresh * T(2));
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) a.q_out[e * NJ + i] = q[i];
+      if (a.final_pos) { a.final_pos[e * 3] = p[0]; a.final_pos[e * 3 + 1] = p[1]; a.final_pos[e * 3 + 2] = p[2]; }
+      if (a.final_quat) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a.final_quat[e * 4 + i] = qc[i];
+      }
+      if (a.pos_err) a.pos_err[e] = perr;
+      if (a.rot_err) a.rot_err[e] = rerr;
+      if (a.iters) a.iters[e] = it;
+      if (a.flags) a.flags[e] = (uint8_t)((conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u));
+      c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
     }
   }
   if (a.counters) {

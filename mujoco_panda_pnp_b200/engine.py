@@ -254,6 +254,46 @@ def ik_waypoints(q_start: torch.Tensor, goal: torch.Tensor, n_steps: int, params
     return dict(q=q, pos=pos, n_accepted=acc, iters_total=its)
 
 
+def ik_pose_solve(target_pos: torch.Tensor, target_quat: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams,
+                  rot_thresh: float = 1e-2, rot_weight: float = 1.0, counters: Optional[torch.Tensor] = None) -> dict:
+    """Pose-mode IK (extension): target_pos[N,3], target_quat[N,4] wxyz, q_init[N,7] or [7]."""
+    lib = _lib.load()
+    dt = target_pos.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("target_pos must be float32 or float64")
+    target_pos = _check_cuda("target_pos", target_pos, dt, (3,))
+    target_quat = _check_cuda("target_quat", target_quat, dt, (4,))
+    n = target_pos.shape[0]
+    if target_quat.shape[0] != n:
+        raise ValueError("target_pos and target_quat disagree on N")
+    if q_init.dim() == 1:
+        if q_init.shape != (7,):
+            raise ValueError("broadcast q_init must have shape (7,)")
+        q_init, stride = q_init.to(device=target_pos.device, dtype=dt).contiguous(), 0
+    else:
+        q_init, stride = _check_cuda("q_init", q_init, dt, (7,)), 7
+        if q_init.shape[0] != n:
+            raise ValueError("q_init disagrees with target_pos on N")
+    dev = target_pos.device
+    q = torch.empty((n, 7), dtype=dt, device=dev)
+    fpos = torch.empty((n, 3), dtype=dt, device=dev)
+    fquat = torch.empty((n, 4), dtype=dt, device=dev)
+    perr = torch.empty((n,), dtype=dt, device=dev)
+    rerr = torch.empty((n,), dtype=dt, device=dev)
+    iters = torch.empty((n,), dtype=torch.int32, device=dev)
+    flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+    fn = lib.pnp_ik_pose_solve_f32 if dt == torch.float32 else lib.pnp_ik_pose_solve_f64
+    with torch.cuda.device(dev):
+        _lib.check(
+            fn(_ptr(target_pos), _ptr(target_quat), _ptr(q_init), stride, n, ctypes.byref(params), float(rot_thresh),
+               float(rot_weight), _ptr(q), _ptr(fpos), _ptr(fquat), _ptr(perr), _ptr(rerr), _ptr(iters), _ptr(flags),
+               _ptr(counters), _stream()),
+            "pnp_ik_pose_solve",
+        )
+    return dict(q=q, final_pos=fpos, final_quat=fquat, pos_error=perr, rot_error=rerr, iterations=iters,
+                converged=(flags & 1) != 0, success=(flags & 2) != 0)
+
+
 def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParams, pos_thresh: float = 0.01,
                  max_traj_points: int = 200, step_size: float = 0.01, max_outer: int = 0, traj_cap: int = 256,
                  counters: Optional[torch.Tensor] = None):

@@ -111,6 +111,22 @@ class JacobianIKController:
             qt = _to_tensor(q).to(device=self.device, dtype=self._dtype()).reshape(-1, 7)
             return engine.fk_jac(qt, kinematics=self.kinematics)
 
+    def solve_pose(self, target_pos, target_quat, q_init, max_iters: int = 100, pos_thresh: float = 1e-3,
+                   rot_thresh: float = 1e-2, damping: float = 1e-2, step_limit: float = 0.1,
+                   rot_weight: float = 1.0) -> dict:
+        """Pose-mode IK (EXTENSION, no reference counterpart: see pnp_ik_pose_solve_* in
+        include/pnp_b200.h).  target_pos (3,)|(N,3), target_quat wxyz (4,)|(N,4), q_init (7,)|(N,7).
+        Returns a dict of device tensors (batched) with q, final_pos, final_quat, pos_error,
+        rot_error, iterations, converged, success."""
+        dt = self._dtype()
+        with torch.cuda.device(self.device):
+            engine.set_tree(self.tree)
+            tp = _to_tensor(target_pos).to(device=self.device, dtype=dt).reshape(-1, 3)
+            tq = _to_tensor(target_quat).to(device=self.device, dtype=dt).reshape(-1, 4)
+            qi = _to_tensor(q_init).to(device=self.device, dtype=dt)
+            return engine.ik_pose_solve(tp, tq, qi, self._params(max_iters, pos_thresh, damping, step_limit),
+                                        rot_thresh=rot_thresh, rot_weight=rot_weight)
+
     def _write_back(self, q: np.ndarray, final_pos: np.ndarray) -> None:
         d = self.data
         if d is None:
@@ -129,3 +145,15 @@ class JacobianIKController:
 
 
 IKSolver = JacobianIKController  # north_star calls the class IKSolver
+
+
+def solve_ik(model, data, site_name, target_pos, target_quat, q_init):
+    """The function FrankaEnv.solve_ik tries to import (envs/panda_env.py:399-409) and the reference
+    never defined.  Pose-mode DLS IK on the GPU; returns an IKResult for the single query."""
+    ctl = JacobianIKController(model, data, site_name)
+    r = ctl.solve_pose(np.asarray(target_pos, float), np.asarray(target_quat, float), np.asarray(q_init, float))
+    q = r["q"][0].double().cpu().numpy()
+    final_pos = r["final_pos"][0].double().cpu().numpy()
+    ctl._write_back(q, final_pos)
+    return IKResult(success=bool(r["success"][0]), q=q, final_pos=final_pos, pos_error=float(r["pos_error"][0]),
+                    iterations=int(r["iterations"][0]), converged=bool(r["converged"][0]))

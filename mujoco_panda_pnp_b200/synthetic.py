@@ -132,3 +132,18 @@ def waypoint_envs(n: int, seed: int = 0, device="cpu", dtype=torch.float32) -> D
     hi = torch.tensor([b[1] for b in SHELF_BOX], dtype=f64, device=device)
     goal = lo + (hi - lo) * torch.rand((n, 3), generator=g, device=device, dtype=f64)
     return dict(q_start=q0.to(dtype).contiguous(), goal=goal.to(dtype).contiguous())
+
+
+def reachable_move_envs(n: int, lower, upper, seed: int = 0, device="cpu", dtype=torch.float32, spread: float = 0.6):
+    """Planner workload with goals that are reachable by construction: start = neutral +- 0.05 rad,
+    goal = FK(q*) with q* = neutral +- ``spread`` rad clipped to the limits (the caller evaluates FK).
+    The reference's MoveIKSkill loop never terminates for unreachable goals, so the headline planner
+    numbers use this generator; the shelf box of ``waypoint_envs`` contains a few unreachable goals."""
+    g = _gen(seed, device)
+    f64 = torch.float64
+    neutral = torch.tensor(NEUTRAL_Q, dtype=f64, device=device)
+    q0 = neutral + (torch.rand((n, 7), generator=g, device=device, dtype=f64) * 0.1 - 0.05)
+    qs = neutral + (torch.rand((n, 7), generator=g, device=device, dtype=f64) * 2 - 1) * spread
+    lo = torch.as_tensor(lower, dtype=f64, device=device)
+    hi = torch.as_tensor(upper, dtype=f64, device=device)
+    return dict(q_start=q0.to(dtype).contiguous(), q_goal=torch.minimum(torch.maximum(qs, lo), hi).to(dtype).contiguous())
