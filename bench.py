@@ -119,6 +119,18 @@ class ClockSampler:
         }
 
 
+def ncu_traffic(kernel: str, units: int):
+    """DRAM bytes per launch for `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic_r1.json: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
+    this launch's unit count); None when no capture is on file."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)[kernel]["dram_bytes_per_unit"]) * units
+    except Exception:
+        return None
+
+
 def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -442,9 +454,35 @@ def run_ours(args) -> int:
                                "ms_per_launch": ms, "transitions_per_s": n_h / (ms * 1e-3),
                                "roofline": {"bound": "hbm", "achieved": 464.0 * n_h / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                             "unit": "GB/s", "frac": 464.0 * n_h / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                            "traffic": ncu_traffic("her_relabel_kernel", n_h),
                                             "algorithmic": "464 B/transition (200 read + 200 written + 64 reward stream, SURVEY 8d)",
                                             "kernel": "her_relabel_kernel<true>"}}
         del h_next, h_obs, h_o, h_x
+        # R4: batched _get_obs from kinematic state (128 B in + 100 B out per env)
+        n_o = 1 << 22
+        go = torch.Generator(device=dev)
+        go.manual_seed(3)
+        rnd = lambda *sh: torch.randn(sh, generator=go, device=dev)  # noqa: E731
+        o_args = [rnd(n_o, 7), rnd(n_o, 7), rnd(n_o, 2).abs() * 0.02, rnd(n_o, 3), rnd(n_o, 4), rnd(n_o, 6), rnd(n_o, 3)]
+        f_obs = lambda: engine.get_obs(*o_args)  # noqa: E731
+        for _ in range(3):
+            f_obs()
+        _, ts = cuda_time_steps(f_obs, 10, torch)
+        ms = statistics.median(ts)
+        side["get_obs"] = {"workload": "2^22 envs, FrankaEnv._get_obs from kinematic state -> [obs19|ag3|dg3] rows",
+                           "ms_per_launch": ms, "envs_per_s": n_o / (ms * 1e-3), "GBps_algorithmic": 228.0 * n_o / (ms * 1e-3) / 1e9}
+        # pose-mode (6x6) IK extension, reachable poses near neutral
+        n_p = 1 << 20
+        qp = synthetic.reachable_move_envs(n_p, tree.lower, tree.upper, seed=5, device=dev, spread=0.5)["q_goal"]
+        ppos, pquat, _ = engine.fk_jac(qp, want_jac=False)
+        cntp = torch.zeros(4, dtype=torch.int64, device=dev)
+        engine.ik_pose_solve(ppos, pquat, neutral, params, counters=cntp)
+        torch.cuda.synchronize()
+        cpp = cntp.cpu().numpy()
+        _, ts = cuda_time_steps(lambda: engine.ik_pose_solve(ppos, pquat, neutral, params), 3, torch)
+        side["pose_ik"] = {"workload": "2^20 pose targets FK(neutral +- 0.5 rad), cold from neutral, 6-row DLS",
+                           "ms_per_launch": min(ts), "solves_per_s": n_p / (min(ts) * 1e-3),
+                           "converged": float(cpp[1]) / n_p, "mean_iterations": float(cpp[3]) / n_p}
     clocks = sampler.stop()
 
     # ---------------- CPU baselines (rank 0, N=1 only) ----------------------------------
@@ -474,7 +512,8 @@ def run_ours(args) -> int:
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ik_tflops / fp32_peak, "traffic": None,
+                "frac": ik_tflops / fp32_peak, "traffic": ncu_traffic("ik_solve_kernel", n_ik),
+                "traffic_note": "DRAM bytes/launch from the ncu capture (48 B/query; algorithmic 60 B, part of the output is still in L2 at kernel end)",
                 "kernel": "ik_solve_kernel<float,SpecKin,packed>" if specialized else "ik_solve_kernel<float,GenericKin,packed>",
                 "kernel_ms": ik_kernel_ms,
                 "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json)",
@@ -488,7 +527,8 @@ def run_ours(args) -> int:
                 "e2e": {"value": rw_e2e, "unit": "rows/s", "h2d_bytes_per_step": n_rw * 60, "d2h_bytes_per_step": n_rw * 4,
                         "api": "pnp_reward_host_f32"},
                 "roofline": {"bound": "hbm", "achieved": rw_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": rw_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": "reward_kernel<float,true>",
+                             "frac": rw_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("reward_kernel", n_rw),
+                             "kernel": "reward_kernel<float,true>",
                              "kernel_ms": rw_kernel_ms, "peak_source": peaks["source"],
                              "algorithmic": "64 B/row (60 in + 4 out)"},
                 "cpu_baseline": cpu_rw,

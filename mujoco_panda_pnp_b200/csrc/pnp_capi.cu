@@ -169,12 +169,12 @@ int get_obs_impl(const T* q_arm, const T* qvel_arm, const T* fingers, const T* o
   pnp::ObsArgs<T> a;
   a.q_arm = q_arm; a.qvel_arm = qvel_arm; a.fingers = fingers; a.obj_pos = obj_pos; a.obj_quat = obj_quat;
   a.obj_vel = obj_vel; a.goal = goal; a.goal_stride = goal_stride; a.n = n; a.dt = (T)dt; a.out = out;
-  const int grid = grid_for(n, 128, s->sm_count, 16);
+  const int grid = grid_for(n, pnp::OBS_TILE, s->sm_count, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (spec)
-    pnp::get_obs_kernel<T, pnp::SpecKin><<<grid, 128, 0, st>>>(a);
+    pnp::get_obs_kernel<T, pnp::SpecKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
   else
-    pnp::get_obs_kernel<T, pnp::GenericKin><<<grid, 128, 0, st>>>(a);
+    pnp::get_obs_kernel<T, pnp::GenericKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;

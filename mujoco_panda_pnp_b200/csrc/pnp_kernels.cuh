@@ -66,58 +66,71 @@ struct ObsArgs {
   T* out;  // [n][25]
 };
 
+// One lane per env, 128 envs per block tile.  The 25-wide output rows (100 B for FP32) are
+// assembled in shared memory (row stride 25 words: conflict-free) and written out by the whole
+// block as consecutive words, so every store instruction covers 128 contiguous bytes instead of
+// 32 rows 100 B apart.
+constexpr int OBS_TILE = 128;
+
 template <typename T, typename Kin>
-__global__ void __launch_bounds__(128) get_obs_kernel(const ObsArgs<T> a) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n;
-       i += (long long)gridDim.x * blockDim.x) {
-    T s[NJ], c[NJ], qv[NJ];
+__global__ void __launch_bounds__(OBS_TILE) get_obs_kernel(const ObsArgs<T> a) {
+  __shared__ T s_out[OBS_TILE * 25];
+  const long long n_tiles = (a.n + OBS_TILE - 1) / OBS_TILE;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long i = t * OBS_TILE + threadIdx.x;
+    if (i < a.n) {
+      T s[NJ], c[NJ], qv[NJ];
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      sincos_t(a.q_arm[i * NJ + k] - Kin::template qref<T>(k), &s[k], &c[k]);
-      qv[k] = a.qvel_arm[i * NJ + k];
+      for (int k = 0; k < NJ; ++k) {
+        sincos_t(a.q_arm[i * NJ + k] - Kin::template qref<T>(k), &s[k], &c[k]);
+        qv[k] = a.qvel_arm[i * NJ + k];
+      }
+      T p[3], J[21];
+#pragma unroll
+      for (int k = 0; k < 21; ++k) J[k] = T(0);
+      Kin::template fk_jacp<T>(s, c, p, J);
+      T* o = s_out + threadIdx.x * 25;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * qv[j];
+        o[3 + r] = acc * a.dt;
+      }
+      o[6] = a.fingers[i * 2] + a.fingers[i * 2 + 1];
+      // free-joint body pose: mj_kinematics normalises the quaternion, xmat = quat2mat
+      T w = a.obj_quat[i * 4], x = a.obj_quat[i * 4 + 1], y = a.obj_quat[i * 4 + 2], z = a.obj_quat[i * 4 + 3];
+      const T nrm = sqrt_t(w * w + x * x + y * y + z * z);
+      if (nrm < T(1e-15)) { w = T(1); x = y = z = T(0); } else { w = w / nrm; x = x / nrm; y = y / nrm; z = z / nrm; }
+      const T q00 = w * w, q01 = w * x, q02 = w * y, q03 = w * z, q11 = x * x, q12 = x * y, q13 = x * z;
+      const T q22 = y * y, q23 = y * z, q33 = z * z;
+      const T m00 = q00 + q11 - q22 - q33, m01 = T(2) * (q12 - q03), m02 = T(2) * (q13 + q02);
+      const T m10 = T(2) * (q12 + q03), m11 = q00 - q11 + q22 - q33, m12 = T(2) * (q23 - q01);
+      const T m20 = T(2) * (q13 - q02), m21 = T(2) * (q23 + q01), m22 = q00 - q11 - q22 + q33;
+      const T ox = a.obj_pos[i * 3], oy = a.obj_pos[i * 3 + 1], oz = a.obj_pos[i * 3 + 2];
+      o[7] = ox; o[8] = oy; o[9] = oz;
+      // rotations.mat2euler
+      const T cy = sqrt_t(m22 * m22 + m12 * m12);
+      const bool cond = cy > T(4.0 * 2.220446049250313e-16);
+      o[12] = cond ? -atan2_t(m01, m00) : -atan2_t(-m10, m11);
+      o[11] = -atan2_t(-m02, cy);
+      o[10] = cond ? -atan2_t(m12, m22) : T(0);
+      const T vx = a.obj_vel[i * 6], vy = a.obj_vel[i * 6 + 1], vz = a.obj_vel[i * 6 + 2];
+      const T wx = a.obj_vel[i * 6 + 3], wy = a.obj_vel[i * 6 + 4], wz = a.obj_vel[i * 6 + 5];
+      o[13] = vx * a.dt; o[14] = vy * a.dt; o[15] = vz * a.dt;
+      o[16] = (m00 * wx + m01 * wy + m02 * wz) * a.dt;
+      o[17] = (m10 * wx + m11 * wy + m12 * wz) * a.dt;
+      o[18] = (m20 * wx + m21 * wy + m22 * wz) * a.dt;
+      o[19] = ox; o[20] = oy; o[21] = oz;
+      const T* g = a.goal + (long long)a.goal_stride * i;
+      o[22] = g[0]; o[23] = g[1]; o[24] = g[2];
     }
-    T p[3], J[21];
-#pragma unroll
-    for (int k = 0; k < 21; ++k) J[k] = T(0);
-    Kin::template fk_jacp<T>(s, c, p, J);
-    T o[25];
-    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      T acc = T(0);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * qv[j];
-      o[3 + r] = acc * a.dt;
-    }
-    o[6] = a.fingers[i * 2] + a.fingers[i * 2 + 1];
-    // free-joint body pose: mj_kinematics normalises the quaternion, xmat = quat2mat
-    T w = a.obj_quat[i * 4], x = a.obj_quat[i * 4 + 1], y = a.obj_quat[i * 4 + 2], z = a.obj_quat[i * 4 + 3];
-    const T nrm = sqrt_t(w * w + x * x + y * y + z * z);
-    if (nrm < T(1e-15)) { w = T(1); x = y = z = T(0); } else { w = w / nrm; x = x / nrm; y = y / nrm; z = z / nrm; }
-    const T q00 = w * w, q01 = w * x, q02 = w * y, q03 = w * z, q11 = x * x, q12 = x * y, q13 = x * z;
-    const T q22 = y * y, q23 = y * z, q33 = z * z;
-    const T m00 = q00 + q11 - q22 - q33, m01 = T(2) * (q12 - q03), m02 = T(2) * (q13 + q02);
-    const T m10 = T(2) * (q12 + q03), m11 = q00 - q11 + q22 - q33, m12 = T(2) * (q23 - q01);
-    const T m20 = T(2) * (q13 - q02), m21 = T(2) * (q23 + q01), m22 = q00 - q11 - q22 + q33;
-    o[7] = a.obj_pos[i * 3]; o[8] = a.obj_pos[i * 3 + 1]; o[9] = a.obj_pos[i * 3 + 2];
-    // rotations.mat2euler
-    const T cy = sqrt_t(m22 * m22 + m12 * m12);
-    const bool cond = cy > T(4.0 * 2.220446049250313e-16);
-    o[12] = cond ? -atan2_t(m01, m00) : -atan2_t(-m10, m11);
-    o[11] = -atan2_t(-m02, cy);
-    o[10] = cond ? -atan2_t(m12, m22) : T(0);
-    const T vx = a.obj_vel[i * 6], vy = a.obj_vel[i * 6 + 1], vz = a.obj_vel[i * 6 + 2];
-    const T wx = a.obj_vel[i * 6 + 3], wy = a.obj_vel[i * 6 + 4], wz = a.obj_vel[i * 6 + 5];
-    o[13] = vx * a.dt; o[14] = vy * a.dt; o[15] = vz * a.dt;
-    o[16] = (m00 * wx + m01 * wy + m02 * wz) * a.dt;
-    o[17] = (m10 * wx + m11 * wy + m12 * wz) * a.dt;
-    o[18] = (m20 * wx + m21 * wy + m22 * wz) * a.dt;
-    o[19] = o[7]; o[20] = o[8]; o[21] = o[9];
-    const T* g = a.goal + (long long)a.goal_stride * i;
-    o[22] = g[0]; o[23] = g[1]; o[24] = g[2];
-    T* dst = a.out + i * 25;
-#pragma unroll
-    for (int k = 0; k < 25; ++k) dst[k] = o[k];
+    __syncthreads();
+    const long long rows = (a.n - t * OBS_TILE < OBS_TILE) ? a.n - t * OBS_TILE : OBS_TILE;
+    T* dst = a.out + t * OBS_TILE * 25;
+    for (int k = threadIdx.x; k < rows * 25; k += OBS_TILE) dst[k] = s_out[k];
+    __syncthreads();
   }
 }
 

@@ -80,6 +80,18 @@ class JacobianIKController:
         q_init = np.asarray(q_init, dtype=np.float64)
         if target_pos.shape != (3,) or q_init.shape != (7,):
             raise ValueError("solve expects target_pos (3,) and q_init (7,)")
+        if self.precision == "fp32":
+            # one C call: H2D of 10 floats, one kernel, D2H of the two packed records
+            with torch.cuda.device(self.device):
+                engine.set_tree(self.tree)
+                h = engine.ik_solve_host(target_pos[None].astype(np.float32), q_init.astype(np.float32),
+                                         self._params(max_iters, pos_thresh, damping, step_limit))
+            word = int(h["aux4"][0, 3:4].view(np.int32)[0])
+            q = h["q"][0].astype(np.float64)
+            final_pos = h["final_pos"][0].astype(np.float64)
+            self._write_back(q, final_pos)
+            return IKResult(success=bool(word & (2 << 24)), q=q, final_pos=final_pos, pos_error=float(h["pos_error"][0]),
+                            iterations=word & 0xFFFFFF, converged=bool(word & (1 << 24)))
         r = self.solve_batch(target_pos[None], q_init[None], max_iters, pos_thresh, damping, step_limit)
         q = r.q[0].double().cpu().numpy()
         final_pos = r.final_pos[0].double().cpu().numpy()

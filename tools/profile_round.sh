@@ -17,4 +17,6 @@ ncu --set full --clock-control none --import-source on -k regex:ik_solve_kernel 
 echo "ik full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:reward_kernel -s 3 -c 1 -f -o $OUT/reward_${TAG} $SMALL > $OUT/ncu_reward_${TAG}.log 2>&1
 echo "reward full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:her_relabel_kernel -s 3 -c 1 -f -o $OUT/her_${TAG} $SMALL > $OUT/ncu_her_${TAG}.log 2>&1
+echo "her full rc=$?"
 ls -la $OUT
