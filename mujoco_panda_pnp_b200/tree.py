@@ -199,14 +199,3 @@ class KinematicTree:
             site_id=self.site_id,
             body_chain=list(self.body_chain),
         )
-
-    # --- tiny host-side FK used only to sanity-check the packing (not the oracle) ------
-    def fk_host(self, q: np.ndarray) -> np.ndarray:
-        p, r = np.zeros(3), np.eye(3)
-        for i in range(N_ARM):
-            p = p + r @ self.link_pos[i]
-            r = r @ self.link_rot[i]
-            a = float(q[i]) - self.qref[i]
-            c, s = np.cos(a), np.sin(a)
-            r = r @ np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
-        return p + r @ self.ee_pos

@@ -32,45 +32,50 @@ class IKResult:  # ik_solver.py:16-24
 
 
 class JacobianIKController:
-    def __init__(self, model, data, site_name: str = "ee_center_site"):  # ik_solver.py:27-33
-        self.model = model
-        self.data = data
-        self.site_id = model.site(site_name).id
-        self.joint_ids = np.arange(7)
-        self.lower = model.jnt_range[:7, 0].copy()
-        self.upper = model.jnt_range[:7, 1].copy()
+    """Restated controller.  Attribute names follow the reference (ik_solver.py:27-33)."""
+
+    def __init__(self, model, data, site_name: str = "ee_center_site"):
+        self.model, self.data = model, data
+        self.site_id = model.site(site_name).id  # :30
+        self.joint_ids = np.arange(7)  # :31
+        rng = model.jnt_range[:7]
+        self.lower, self.upper = rng[:, 0].copy(), rng[:, 1].copy()  # :32-33
+
+    # -- pieces of the loop body, in the reference's arithmetic order ------------------------
+    def _write_q(self, q):
+        self.data.qpos[:7] = q  # :51 / :82
+        mujoco.mj_forward(self.model, self.data)  # :52 / :83
+
+    def _site_pos(self):
+        return self.data.site_xpos[self.site_id].copy()  # :59 / :88
+
+    def _dls_update(self, q, residual, damping, step_limit):
+        nv = self.model.nv
+        jac_p, jac_r = np.zeros((3, nv)), np.zeros((3, nv))  # :70-71 (rotational part unused)
+        mujoco.mj_jacSite(self.model, self.data, jac_p, jac_r, self.site_id)  # :72
+        jac = jac_p[:3, :]  # :74
+        gram = jac @ jac.T + damping * np.eye(3)  # :79 (damping un-squared)
+        dq_all = jac.T @ np.linalg.solve(gram, residual[:3])  # :75, :78-79
+        dq = np.clip(dq_all[:7], -step_limit, step_limit)  # :80
+        return np.clip(q + dq, self.lower, self.upper)  # :81
 
     def solve(self, target_pos, q_init, max_iters=100, pos_thresh=1e-3, damping=1e-2, step_limit=0.1):
-        m, d, sid = self.model, self.data, self.site_id
         q = np.array(q_init, dtype=np.float64).copy()  # :50
-        d.qpos[:7] = q  # :51
-        mujoco.mj_forward(m, d)  # :52
-        converged, iterations = False, 0  # :54-55
-        for i in range(max_iters):  # :57
-            mujoco.mj_kinematics(m, d)  # :58
-            curr_pos = d.site_xpos[sid].copy()  # :59
-            pos_err = target_pos - curr_pos  # :60
-            pos_error_norm = np.linalg.norm(pos_err)  # :61
-            if pos_error_norm < pos_thresh:  # :64
-                converged = True
-                iterations = i + 1
-                break
-            J_pos = np.zeros((3, m.nv))  # :70
-            J_rot = np.zeros((3, m.nv))  # :71
-            mujoco.mj_jacSite(m, d, J_pos, J_rot, sid)  # :72
-            J = J_pos[:3, :]  # :74
-            err = pos_err[:3]  # :75
-            JT = J.T  # :78
-            delta_q_full = JT @ np.linalg.solve(J @ JT + damping * np.eye(3), err)  # :79
-            delta_q = np.clip(delta_q_full[:7], -step_limit, step_limit)  # :80
-            q = np.clip(q + delta_q, self.lower, self.upper)  # :81
-            d.qpos[:7] = q  # :82
-            mujoco.mj_forward(m, d)  # :83
-            iterations = i + 1  # :85
-        final_pos = d.site_xpos[sid].copy()  # :88
-        final_error = np.linalg.norm(final_pos - target_pos)  # :89
-        success = bool(converged and final_error < pos_thresh * 2)  # :92
-        return IKResult(success, q.copy(), final_pos.copy(), float(final_error), int(iterations), bool(converged))
+        self._write_q(q)  # :51-52
+        hit, n_iter = False, 0  # :54-55
+        for k in range(max_iters):  # :57
+            mujoco.mj_kinematics(self.model, self.data)  # :58
+            residual = target_pos - self._site_pos()  # :59-60
+            if np.linalg.norm(residual) < pos_thresh:  # :61, :64 (tested BEFORE the update)
+                hit, n_iter = True, k + 1  # :65-66
+                break  # :67
+            q = self._dls_update(q, residual, damping, step_limit)  # :70-81
+            self._write_q(q)  # :82-83
+            n_iter = k + 1  # :85
+        end_pos = self._site_pos()  # :88
+        end_err = np.linalg.norm(end_pos - target_pos)  # :89
+        ok = bool(hit and end_err < pos_thresh * 2)  # :92
+        return IKResult(ok, q.copy(), end_pos.copy(), float(end_err), int(n_iter), bool(hit))  # :94-101
 
 
 def fk_site(model, data, q, site_name="ee_center_site"):

@@ -14,6 +14,18 @@ REFERENCE_XML = "/root/reference/panda_mujoco_gym/assets/shelf_pnp.xml"
 NEUTRAL = np.array([0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79])
 
 
+def tree_fk(tree, q):
+    """EE-site position from a canonical KinematicTree (test helper: the product has no CPU FK)."""
+    p, r = np.zeros(3), np.eye(3)
+    for i in range(7):
+        p = p + r @ tree.link_pos[i]
+        r = r @ tree.link_rot[i]
+        a = float(q[i]) - tree.qref[i]
+        c, s = np.cos(a), np.sin(a)
+        r = r @ np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    return p + r @ tree.ee_pos
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ASSET, NEUTRAL, REFERENCE_XML
+from conftest import ASSET, NEUTRAL, REFERENCE_XML, tree_fk
 from mujoco_panda_pnp_b200 import KinematicData, KinematicModel, KinematicTree
 from mujoco_panda_pnp_b200.mjcf import JNT_FREE, JNT_HINGE, JNT_SLIDE
 from oracle import ik_oracle, mj_oracle
@@ -14,8 +14,8 @@ HOME_WPT = np.array([1.23843967, 0.0, 0.49740014])  # real MuJoCo, scripts/execu
 
 def test_fk_neutral_matches_real_mujoco_value():
     tree = KinematicTree.from_mjcf()
-    assert np.abs(tree.fk_host(NEUTRAL) - HOME_WPT).max() < 1e-8
-    assert np.allclose(tree.fk_host(np.zeros(7)), [0.688, 0.0, 1.121], atol=1e-12)
+    assert np.abs(tree_fk(tree, NEUTRAL) - HOME_WPT).max() < 1e-8
+    assert np.allclose(tree_fk(tree, np.zeros(7)), [0.688, 0.0, 1.121], atol=1e-12)
 
 
 def test_model_layout_matches_reference_scene(kin_model):
@@ -126,7 +126,7 @@ def test_general_tree_folding_matches_mujoco_semantics(tmp_path):
     for _ in range(20):
         q = rng.uniform(-2.5, 2.5, 7)
         want = ik_oracle.fk_site(model, data, q)[0]
-        np.testing.assert_allclose(tree.fk_host(q), want, atol=1e-13)
+        np.testing.assert_allclose(tree_fk(tree, q), want, atol=1e-13)
 
 
 def test_kinematic_data_mimics_mjdata(kin_model):
