@@ -503,8 +503,16 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   bool spec;
   if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
   if (n == 0) return PNP_OK;
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "move_ik_plan: n must be < 2^31 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ticket;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
+  }
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::MoveArgs<T> a;
-  a.q_start = q_start; a.target = target; a.n = n;
+  a.q_start = q_start; a.target = target; a.n = (unsigned)n; a.ticket = ticket;
   a.pos_thresh = (T)mp->pos_thresh; a.step_size = (T)mp->step_size;
   a.max_traj_points = mp->max_traj_points;
   a.max_outer = mp->max_outer > 0 ? mp->max_outer : 4 * mp->max_traj_points + 64;
@@ -515,7 +523,10 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = small ? 32 : pnp::IK_BLOCK;
   const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 4);
-  cudaStream_t st = (cudaStream_t)stream;
+  // envs reserved per ticket atomic: ~1/8 of a warp's share within [32, 128] (keeps the tail short)
+  long long chunk = n / ((long long)grid * (block / 32) * 8);
+  chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk);
+  a.chunk = (unsigned)(chunk & ~31ll);
   if (spec)
     pnp::move_ik_plan_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
   else

@@ -601,7 +601,7 @@ template <typename T>
 struct MoveArgs {
   const T* q_start;
   const T* target;
-  long long n;
+  unsigned n;       // < 2^31 (checked on the host)
   T pos_thresh, step_size;
   int max_traj_points, max_outer, traj_cap;
   IkConst<T> k;
@@ -611,8 +611,14 @@ struct MoveArgs {
   int32_t* n_solves;
   int32_t* status;
   unsigned long long* counters;
+  unsigned* ticket; // zeroed before launch
+  unsigned chunk;   // envs a warp reserves per ticket atomic
 };
 
+// Persistent warps with lane refill (like ik_solve_kernel): trajectories differ in length (40-200
+// rounds), so a lane whose env is finished writes it back and takes the next env instead of idling
+// until the longest trajectory of its warp ends.  A fresh env enters in state INIT and gets its
+// start position FK(q_start) (move.py:91) from the shared DLS pass of that round - no divergent FK.
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
@@ -620,134 +626,165 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
   if (Trig<T>::kUsesTable) load_trig_table(s_tab);
   __syncthreads();
   const Trig<T> trig{s_tab};
-  enum { NORMAL = 0, FB1 = 1, FB2 = 2, DONE = 3 };
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  enum { NORMAL = 0, FB1 = 1, FB2 = 2, DONE = 3, INIT = 4, IDLE = 5 };
   unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < a.n;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long e = base + lane;
-    const bool valid = e < a.n;
-    T q[NJ], goal[3], pos[3];
+  unsigned pool_next = 0, pool_end = 0;
+  bool exhausted = false;
+  unsigned e = 0;
+  T q[NJ], goal[3] = {T(0), T(0), T(0)}, pos[3] = {T(0), T(0), T(0)};
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) q[i] = valid ? a.q_start[e * NJ + i] : T(0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) goal[i] = valid ? a.target[e * 3 + i] : T(0);
-    fk_position<T, Kin>(q, pos);                                                      // :91
-    T* traj = a.traj + (valid ? e : 0) * (long long)a.traj_cap * 3;
-    int len = 0, solves = 0, st = 0, state = valid ? NORMAL : DONE;
-    int point_count = 0, cf = 0, outer = 0;
-    T astep = T(0);
-    auto append = [&](const T* pt) {
-      if (len < a.traj_cap) { traj[len * 3] = pt[0]; traj[len * 3 + 1] = pt[1]; traj[len * 3 + 2] = pt[2]; }
-      else st |= 4;
-      ++len;
-    };
-    if (valid) append(pos);                                                           // :98
-    while (true) {
-      // ---- (i) choose this round's IK target ---------------------------------------------
-      const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];    // :110
-      const T dist = sqrt_t((dx * dx + dy * dy) + dz * dz);                           // :111 (== :106 norm)
-      T tgt[3] = {pos[0], pos[1], pos[2]};
-      if (state == NORMAL) {
-        if (!(dist > a.pos_thresh && point_count < a.max_traj_points)) {              // :106-107
-          state = DONE;
-        } else if (outer >= a.max_outer) {
-          st |= 2;
-          state = DONE;
-        } else {
-          ++outer;
-          T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                    // :114-117
-          if (cf > 0) stp = stp * T(0.5);                                             // :118-119
-          astep = stp;
-          if (dist > stp) {                                                           // :122-125
-            tgt[0] = pos[0] + dx * stp / dist; tgt[1] = pos[1] + dy * stp / dist; tgt[2] = pos[2] + dz * stp / dist;
-          } else {
-            tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
-          }
-        }
-        if (state == DONE && dist > a.pos_thresh) append(goal);                       // :189-191
-      } else if (state == FB1) {
-        const T smaller = astep * T(0.1);                                             // :149-151
-        tgt[0] = pos[0] + dx * smaller / dist; tgt[1] = pos[1] + dy * smaller / dist; tgt[2] = pos[2] + dz * smaller / dist;
-      } else if (state == FB2) {
-        const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                              // :163-167
-        tgt[0] = pos[0] + (dx / an) * astep; tgt[1] = pos[1] + (T(0) / an) * astep; tgt[2] = pos[2] + (dz / an) * astep;
-      }
-      if (!__any_sync(FULL, state != DONE)) break;
+  for (int i = 0; i < NJ; ++i) q[i] = T(0);
+  T* traj = a.traj;
+  int len = 0, solves = 0, st = 0, state = IDLE;
+  int point_count = 0, cf = 0, outer = 0;
+  T astep = T(0);
+  auto append = [&](const T* pt) {
+    if (len < a.traj_cap) { traj[len * 3] = pt[0]; traj[len * 3 + 1] = pt[1]; traj[len * 3 + 2] = pt[2]; }
+    else st |= 4;
+    ++len;
+  };
 
-      // ---- (ii) shared DLS solve from q (ik_solver.py:50-101) --------------------------------
-      T qs[NJ], p[3] = {T(0), T(0), T(0)}, err = T(0);
+  while (true) {
+    // ---- write back finished envs, refill idle lanes -------------------------------------------
+    if (state == DONE) {
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) qs[i] = q[i];
-      int it = 0;
-      bool conv = false, done = (state == DONE);
-      while (__any_sync(FULL, !done)) {
-        T n2, qn[NJ], pp[3];
-        ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
-        if (!done) {
-          const bool last = it >= a.k.max_iters;
-          conv = !last && below_thresh(n2, a.k);
-          if (conv || last) {
-            err = finish_sqrt(n2);
-            p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
-            it = conv ? it + 1 : it;
-            done = true;
-          } else {
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
-            ++it;
-          }
-        }
-      }
-
-      // ---- (iii) post-process by state -------------------------------------------------------
-      if (state != DONE) {
-        ++solves;
-        c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
-        const bool success = conv && (err < a.k.pos_thresh * T(2));                   // ik_solver.py:92
-        const bool accept = state == NORMAL ? (success && err < a.step_size * T(2)) : success;  // :131/:154/:170
-        if (accept) {
-          append(p);
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) q[i] = qs[i];
-          pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
-          cf = 0;
-          if (state == NORMAL) ++point_count;                                         // :186 (fallbacks `continue`)
-          state = NORMAL;
-        } else {
-          bool try_fb2 = false;
-          if (state == NORMAL) {
-            ++cf;                                                                     // :142
-            if (cf >= 3) {                                                            // :144
-              if (dist > astep * T(0.1)) state = FB1; else try_fb2 = true;            // :150
-            } else {
-              ++cf;                                                                   // :183
-            }
-          } else if (state == FB1) {
-            try_fb2 = true;
-          } else {                                                                    // FB2 failed
-            st |= 1;                                                                  // :178-180
-            state = DONE;
-            if (dist > a.pos_thresh) append(goal);                                    // :189-191
-          }
-          if (try_fb2) {
-            const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                          // :165
-            if (an > T(0.001)) {
-              state = FB2;
-            } else {
-              st |= 1;
-              state = DONE;
-              if (dist > a.pos_thresh) append(goal);
-            }
-          }
-        }
-      }
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) a.q_final[e * NJ + i] = q[i];
+      for (int i = 0; i < NJ; ++i) a.q_final[(size_t)e * NJ + i] = q[i];
       a.traj_len[e] = len;
       if (a.n_solves) a.n_solves[e] = solves;
       if (a.status) a.status[e] = st;
+      state = IDLE;
+    }
+    const unsigned need = __ballot_sync(FULL, state == IDLE && !exhausted);
+    if (need) {
+      const unsigned count = (unsigned)__popc(need);
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
+      }
+      if (state == IDLE && !exhausted) {
+        const unsigned rank = (unsigned)__popc(need & lanemask_lt);
+        const unsigned idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
+        if (idx < a.n) {
+          e = idx;
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) q[i] = a.q_start[(size_t)e * NJ + i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) goal[i] = a.target[(size_t)e * 3 + i];
+          traj = a.traj + (size_t)e * a.traj_cap * 3;
+          len = 0; solves = 0; st = 0; point_count = 0; cf = 0; outer = 0; astep = T(0);
+          state = INIT;
+        } else {
+          exhausted = true;
+        }
+      }
+      if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
+      else pool_next += count;
+    }
+    if (!__any_sync(FULL, state != IDLE)) break;
+
+    // ---- (i) choose this round's IK target -----------------------------------------------------
+    const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];      // :110
+    const T dist = sqrt_t((dx * dx + dy * dy) + dz * dz);                             // :111 (== :106 norm)
+    T tgt[3] = {pos[0], pos[1], pos[2]};
+    if (state == NORMAL) {
+      if (!(dist > a.pos_thresh && point_count < a.max_traj_points)) {                // :106-107
+        state = DONE;
+      } else if (outer >= a.max_outer) {
+        st |= 2;
+        state = DONE;
+      } else {
+        ++outer;
+        T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                      // :114-117
+        if (cf > 0) stp = stp * T(0.5);                                               // :118-119
+        astep = stp;
+        if (dist > stp) {                                                             // :122-125
+          tgt[0] = pos[0] + dx * stp / dist; tgt[1] = pos[1] + dy * stp / dist; tgt[2] = pos[2] + dz * stp / dist;
+        } else {
+          tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
+        }
+      }
+      if (state == DONE && dist > a.pos_thresh) append(goal);                         // :189-191
+    } else if (state == FB1) {
+      const T smaller = astep * T(0.1);                                               // :149-151
+      tgt[0] = pos[0] + dx * smaller / dist; tgt[1] = pos[1] + dy * smaller / dist; tgt[2] = pos[2] + dz * smaller / dist;
+    } else if (state == FB2) {
+      const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                                // :163-167
+      tgt[0] = pos[0] + (dx / an) * astep; tgt[1] = pos[1] + (T(0) / an) * astep; tgt[2] = pos[2] + (dz / an) * astep;
+    }
+
+    // ---- (ii) shared DLS solve from q (ik_solver.py:50-101); INIT lanes only take FK(q) ----------
+    T qs[NJ], p[3] = {T(0), T(0), T(0)}, err = T(0);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) qs[i] = q[i];
+    int it = 0;
+    bool conv = false, done = (state == DONE || state == IDLE);
+    while (__any_sync(FULL, !done)) {
+      T n2, qn[NJ], pp[3];
+      ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
+      if (!done) {
+        const bool last = (it >= a.k.max_iters) || (state == INIT);
+        conv = !last && below_thresh(n2, a.k);
+        if (conv || last) {
+          err = finish_sqrt(n2);
+          p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
+          it = conv ? it + 1 : it;
+          done = true;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
+          ++it;
+        }
+      }
+    }
+
+    // ---- (iii) post-process by state -------------------------------------------------------------
+    if (state == INIT) {
+      pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];                                    // :91 start_pos = FK(q_start)
+      append(pos);                                                                    // :98
+      state = NORMAL;
+    } else if (state != DONE && state != IDLE) {
+      ++solves;
+      c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
+      const bool success = conv && (err < a.k.pos_thresh * T(2));                     // ik_solver.py:92
+      const bool accept = state == NORMAL ? (success && err < a.step_size * T(2)) : success;  // :131/:154/:170
+      if (accept) {
+        append(p);
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) q[i] = qs[i];
+        pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
+        cf = 0;
+        if (state == NORMAL) ++point_count;                                           // :186 (fallbacks `continue`)
+        state = NORMAL;
+      } else {
+        bool try_fb2 = false;
+        if (state == NORMAL) {
+          ++cf;                                                                       // :142
+          if (cf >= 3) {                                                              // :144
+            if (dist > astep * T(0.1)) state = FB1; else try_fb2 = true;              // :150
+          } else {
+            ++cf;                                                                     // :183
+          }
+        } else if (state == FB1) {
+          try_fb2 = true;
+        } else {                                                                      // FB2 failed
+          st |= 1;                                                                    // :178-180
+          state = DONE;
+          if (dist > a.pos_thresh) append(goal);                                      // :189-191
+        }
+        if (try_fb2) {
+          const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                            // :165
+          if (an > T(0.001)) {
+            state = FB2;
+          } else {
+            st |= 1;
+            state = DONE;
+            if (dist > a.pos_thresh) append(goal);
+          }
+        }
+      }
     }
   }
   if (a.counters) {
