@@ -131,6 +131,33 @@ def ncu_traffic(kernel: str, units: int):
         return None
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers of the e2e path are allocated (first touch) on the NUMA node behind the same PCIe root.
+    Best effort: returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = gpu_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                phys = int(ids[gpu_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus = allowed & local
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -246,7 +273,7 @@ def run_reference(args) -> int:
         "note": "reference arm = oracle port (C, FP64, all host threads): mujoco is not installable in this image, "
                 "see DESIGN.md; it omits mj_forward's collision/constraint work and is faster than the real reference",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -275,10 +302,17 @@ def run_ours(args) -> int:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     rank, local_rank, world = D.init_process_group("nccl")
+    if not os.path.exists(_lib.LIB_PATH):  # normally prebuilt by __graft_entry__.build(); never fall back to CPU
+        if rank == 0:
+            from mujoco_panda_pnp_b200.csrc import build as cuda_build
+
+            cuda_build.build()
+        D.barrier()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     lib = _lib.load()
     tree = KinematicTree.from_mjcf()
     specialized = engine.set_tree(tree)
@@ -505,6 +539,7 @@ def run_ours(args) -> int:
                 "kinematics": "specialized" if specialized else "generic",
                 "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
                 "parallelism": f"batch-index shards x{world}, NCCL all_reduce of 4 counters",
+                "numa_bound_cpus": numa,
             },
             "e2e": {"value": ik_e2e, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": ik_d2h,
                     "steps": Ke, "api": "pnp_ik_solve_packed_host_f32 (pinned host buffers, 3-stream chunk pipeline)"},
@@ -536,7 +571,7 @@ def run_ours(args) -> int:
             },
             **side,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -544,7 +579,24 @@ def run_ours(args) -> int:
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """Write the one JSON line to the real stdout (see main(): fd 1 is pointed at stderr meanwhile)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main() -> int:
+    global _JSON_FD
+    # Libraries write banners to stdout from C (NCCL prints "NCCL version ..." on init).  The
+    # contract is ONE JSON line on stdout, so keep a private handle on the real stdout and point
+    # fd 1 / sys.stdout at stderr for everything else.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
