@@ -19,7 +19,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libpnp_b200.so")
 SOURCES = ["pnp_capi.cu"]
-DEPS = ["pnp_capi.cu", "pnp_kernels.cuh", "pnp_common.cuh", "pnp_host_api.inc",
+DEPS = ["pnp_capi.cu", "pnp_kernels.cuh", "pnp_common.cuh", "pnp_vec.cuh", "pnp_host_api.inc",
         os.path.join("generated", "spec_kinematics.cuh"), os.path.join(ROOT, "include", "pnp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

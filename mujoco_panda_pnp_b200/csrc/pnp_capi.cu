@@ -5,9 +5,11 @@
 #include <cstdarg>
 #include <new>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 #include "pnp_kernels.cuh"
 
@@ -23,7 +25,7 @@ struct DeviceState {
   int sm_count = 0;
   unsigned* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
   unsigned ticket_seq = 0;
-  int occ_ik[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int occ_ik[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 constexpr int kMaxDevices = 16;
 constexpr int kTicketSlots = 64;
@@ -98,6 +100,8 @@ int pick_kin(const DeviceState* s, int kinematics, bool* use_spec) {
     case PNP_KIN_AUTO: *use_spec = s->specialized; return PNP_OK;
     case PNP_KIN_GENERIC: *use_spec = false; return PNP_OK;
     case PNP_KIN_SPECIALIZED:
+    case PNP_KIN_SPEC_LANE:
+    case PNP_KIN_SPEC_PAIR:
       if (!s->specialized) return fail(PNP_EINVAL, "uploaded tree differs from the build-time specialised tree");
       *use_spec = true;
       return PNP_OK;
@@ -205,6 +209,49 @@ int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t 
   return PNP_OK;
 }
 
+// Value-type kernels (pnp_vec.cuh): V = float, one query per lane; V = F2, two queries per lane.
+template <typename V, bool kPacked>
+int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStream_t st) {
+  constexpr int S = pnp::Slots<V>::kN;
+  const int slot = 8 + (S - 1) * 2 + (kPacked ? 1 : 0);
+  if (s->occ_ik[slot] == 0) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kPacked>,
+                                                                  pnp::IK_BLOCK, 0);
+    s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
+  }
+  const int block = small ? 32 : pnp::IK_BLOCK;
+  const long long lanes_needed = ((long long)a.n + S - 1) / S;
+  const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, s->occ_ik[slot]);
+  pnp::IkArgs<float> args = a;
+  const long long warps = (long long)grid * (block / 32);
+  long long chunk = (long long)a.n / (warps * 16);
+  chunk = chunk < 32 * S ? 32 * S : (chunk > 256 ? 256 : chunk);
+  args.chunk = (unsigned)(chunk & ~31ll);
+  {
+    // lanes with a finished slot that trigger a store + refill (PNP_IK_FLUSH_MIN overrides, for tuning)
+    static const int env_flush = [] { const char* e = getenv("PNP_IK_FLUSH_MIN"); return e ? atoi(e) : 0; }();
+    const bool oversubscribed = (long long)a.n >= (long long)s->sm_count * 8192;
+    args.flush_min = env_flush > 0 ? (unsigned)env_flush : (S == 2 ? (small ? 1u : 8u) : (oversubscribed ? 4u : 1u));
+  }
+  pnp::ik_solve_v_kernel<V, kPacked><<<grid, block, 0, st>>>(args);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+// FP32 on the specialised tree always runs the value-type kernels (same arithmetic in both, so a
+// batch gives bit-identical results whichever is picked).  AUTO / SPECIALIZED: two queries per lane
+// once the batch oversubscribes the machine (>= 8192 queries per SM); below that the batch is
+// latency bound and one query per lane finishes sooner.
+template <bool kPacked>
+int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
+  const bool big = (long long)a.n >= (long long)s->sm_count * 8192;
+  if (kinematics == PNP_KIN_SPEC_PAIR || (kinematics != PNP_KIN_SPEC_LANE && big))
+    return launch_ik_v<pnp::F2, kPacked>(s, a, (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2, st);
+  return launch_ik_v<float, kPacked>(s, a, small, st);
+}
+
 template <typename T, bool kPacked>
 int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int64_t n, const PnpIkParams* params,
                   T* q_out, T* final_pos, T* pos_err, int32_t* iters, uint8_t* flags, unsigned long long* counters,
@@ -236,8 +283,13 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
   a.counters = counters; a.ticket = ticket;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  return spec ? launch_ik<T, pnp::SpecKin, kPacked>(s, a, small, st)
-              : launch_ik<T, pnp::GenericKin, kPacked>(s, a, small, st);
+  if (spec) {
+    if constexpr (std::is_same<T, float>::value)
+      return launch_ik_spec_f32<kPacked>(s, a, params->kinematics, small, st);
+    else
+      return launch_ik<T, pnp::SpecKin, kPacked>(s, a, small, st);
+  }
+  return launch_ik<T, pnp::GenericKin, kPacked>(s, a, small, st);
 }
 
 // Smallest double s >= 0 with sqrt(s) >= t (sqrt is correctly rounded, hence monotone): the

@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "../../include/pnp_b200.h"
+#include "pnp_vec.cuh"
 #include "generated/spec_kinematics.cuh"
 
 namespace pnp {
@@ -318,6 +319,124 @@ __device__ __forceinline__ void ik_eval_and_step(const T (&q)[NJ], const T (&tgt
   for (int i = 0; i < NJ; ++i) {
     const T d = clamp_t(dq[i], -k.step_limit, k.step_limit);                              // :80
     qn[i] = clamp_t(q[i] + d, Kin::template lower<T>(i), Kin::template upper<T>(i));      // :81
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same DLS evaluation in explicit-FMA form for the value types of pnp_vec.cuh: V = float (one
+// query per lane) or V = F2 (two queries per lane on FFMA2/FMUL2/FADD2).  Every operation is the
+// same correctly-rounded FP32 operation in both instantiations, so the packed kernel reproduces
+// the scalar FP32 kernel bit for bit (tests/test_gpu_ik.py::test_pair_kernel_is_bit_identical).
+// Specialised tree only (the generated "_v" kinematics).
+// ---------------------------------------------------------------------------------------------
+using pnp_spec::F2;
+using pnp_spec::pnp_add;
+using pnp_spec::pnp_fma;
+using pnp_spec::pnp_mul;
+using pnp_spec::pnp_neg;
+
+__device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
+__device__ __forceinline__ F2 v_sub(F2 a, F2 b) { return pnp_spec::pnp_sub(a, b); }
+// one MUFU.RCP (the pivots of J J^T + damping I lie in [damping, ~10]: no range fix-up needed, which
+// is what __fdividef(1, x) spends four more instructions on)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float v_rcp(float x) { return rcp_approx(x); }
+__device__ __forceinline__ F2 v_rcp(F2 x) { return F2(rcp_approx(x.v.x), rcp_approx(x.v.y)); }
+__device__ __forceinline__ float v_clamp_sym(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
+__device__ __forceinline__ F2 v_clamp_sym(F2 x, F2 lim) {
+  return F2(fminf(fmaxf(x.v.x, -lim.v.x), lim.v.x), fminf(fmaxf(x.v.y, -lim.v.y), lim.v.y));
+}
+__device__ __forceinline__ float v_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ F2 v_clamp(F2 x, float lo, float hi) {
+  return F2(fminf(fmaxf(x.v.x, lo), hi), fminf(fmaxf(x.v.y, lo), hi));
+}
+
+// Table trig for V (same arithmetic as Trig<float>; the table is split into a sin and a cos array so
+// that the two slots of an F2 load straight into the halves of a register pair).
+struct TrigV {
+  const float* sin_tab;  // shared memory, kTrigTabN entries each
+  const float* cos_tab;
+  __device__ __forceinline__ void operator()(float x, float* s, float* c) const {
+    const float t = fmaf(x, 162.974655f, 12582912.0f);
+    const int ji = __float_as_int(t) & (kTrigTabN - 1);
+    const float k = t + (-12582912.0f);
+    float r = fmaf(k, -0.0061359233222901821f, x);
+    r = fmaf(k, 1.7074761049507003e-10f, r);
+    const float es = sin_tab[ji], ec = cos_tab[ji];
+    const float h = (r * 0.5f) * r;
+    *s = fmaf(ec, r, fmaf(-es, h, es));
+    *c = fmaf(-es, r, fmaf(-ec, h, ec));
+  }
+  __device__ __forceinline__ void operator()(F2 x, F2* s, F2* c) const {
+    const F2 t = pnp_fma(x, F2(162.974655f), F2(12582912.0f));
+    const int ja = __float_as_int(t.v.x) & (kTrigTabN - 1), jb = __float_as_int(t.v.y) & (kTrigTabN - 1);
+    const F2 k = pnp_add(t, F2(-12582912.0f));
+    F2 r = pnp_fma(k, F2(-0.0061359233222901821f), x);
+    r = pnp_fma(k, F2(1.7074761049507003e-10f), r);
+    const F2 es(sin_tab[ja], sin_tab[jb]), ec(cos_tab[ja], cos_tab[jb]);
+    const F2 h = pnp_mul(pnp_mul(r, F2(0.5f)), r);
+    *s = pnp_fma(ec, r, pnp_fma(pnp_neg(es), h, es));
+    *c = pnp_fma(pnp_neg(es), r, pnp_fma(pnp_neg(ec), h, ec));
+  }
+};
+
+__device__ __forceinline__ void load_trig_table_split(float* s_sin, float* s_cos) {
+  for (int i = threadIdx.x; i < kTrigTabN; i += blockDim.x) {
+    const float2 e = g_trig_tab[i];
+    s_sin[i] = e.x;
+    s_cos[i] = e.y;
+  }
+}
+
+// Split in two so that a kernel can decide between the halves (from n2) whether a slot takes the step:
+//   ik_eval_v : p = FK(q), J = jacp, e = target - p, n2 = |e|^2          (ik_solver.py:58-61, 70-72)
+//   ik_step_v : qn = clip(q + clip(J^T (J J^T + damping I)^-1 e, +-slim), lower, upper)   (:78-81)
+// slim is per slot: step_limit for a running query, 0 to freeze a finished one (qn == q).
+template <typename V>
+__device__ __forceinline__ void ik_eval_v(const V (&q)[NJ], const V (&tgt)[3], const TrigV& trig, V (&p)[3],
+                                          V (&e)[3], V& n2, V (&J)[21]) {
+  V s[NJ], c[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const float qr = pnp_spec::spec_qref<float>(i);
+    trig(qr != 0.0f ? pnp_add(q[i], V(-qr)) : q[i], &s[i], &c[i]);
+  }
+  pnp_spec::spec_fk_jacp_v<V>(s, c, p, J);
+  e[0] = v_sub(tgt[0], p[0]); e[1] = v_sub(tgt[1], p[1]); e[2] = v_sub(tgt[2], p[2]);
+  n2 = pnp_fma(e[2], e[2], pnp_fma(e[1], e[1], pnp_mul(e[0], e[0])));
+}
+
+template <typename V>
+__device__ __forceinline__ void ik_step_v(const V (&q)[NJ], const V (&J)[21], const V (&e)[3], float damping,
+                                          const V& slim, V (&qn)[NJ]) {
+  V A[6];
+  pnp_spec::spec_jjt_v<V>(J, A);
+  const V lam(damping);
+  const V a00 = pnp_add(A[0], lam), a11 = pnp_add(A[3], lam), a22 = pnp_add(A[5], lam);
+  const V i0 = v_rcp(a00);
+  const V l10 = pnp_mul(A[1], i0), l20 = pnp_mul(A[2], i0);
+  const V d1 = pnp_fma(pnp_neg(l10), A[1], a11);
+  const V u12 = pnp_fma(pnp_neg(l10), A[2], A[4]);
+  const V i1 = v_rcp(d1);
+  const V l21 = pnp_mul(u12, i1);
+  const V d2 = pnp_fma(pnp_neg(l21), u12, pnp_fma(pnp_neg(l20), A[2], a22));
+  const V i2 = v_rcp(d2);
+  const V z1 = pnp_fma(pnp_neg(l10), e[0], e[1]);
+  const V z2 = pnp_fma(pnp_neg(l21), z1, pnp_fma(pnp_neg(l20), e[0], e[2]));
+  V y[3];
+  y[2] = pnp_mul(z2, i2);
+  y[1] = pnp_fma(pnp_neg(l21), y[2], pnp_mul(z1, i1));
+  y[0] = pnp_fma(pnp_neg(l20), y[2], pnp_fma(pnp_neg(l10), y[1], pnp_mul(e[0], i0)));
+  V dq[NJ];
+  pnp_spec::spec_jty_v<V>(J, y, dq);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const V d = v_clamp_sym(dq[i], slim);                                                                // :80
+    qn[i] = v_clamp(pnp_add(q[i], d), pnp_spec::spec_lower<float>(i), pnp_spec::spec_upper<float>(i));   // :81
   }
 }
 

@@ -7,6 +7,9 @@ namespace pnp {
 
 constexpr int IK_BLOCK = 128;  // (forcing 8 blocks/SM = 64 regs was measured: no gain, generic path spills)
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef IK_PAIR_MIN_BLOCKS
+#define IK_PAIR_MIN_BLOCKS 4
+#endif
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
@@ -166,6 +169,7 @@ struct IkArgs {
   unsigned long long* counters;
   unsigned* ticket;   // zeroed before launch
   unsigned chunk;     // queries a warp reserves per ticket atomic (>= 32)
+  unsigned flush_min; // ik_solve_v_kernel: lanes with a finished slot that trigger a store + refill
 };
 
 // convergence test (ik_solver.py:61-64).  FP64 follows the reference literally (sqrt, then
@@ -281,6 +285,203 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) q[i] = qn[i];
     ++it;
+  }
+
+  if (a.counters) {
+    const unsigned long long w_n = warp_sum((unsigned long long)c_n), w_conv = warp_sum((unsigned long long)c_conv),
+                             w_iter = warp_sum(c_iter);
+    if (lane == 0) {
+      atomicAdd(a.counters + PNP_IK_CNT_N, w_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, w_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, w_conv);  // success == converged
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, w_iter);
+    }
+  }
+}
+
+// =============================================================================================
+// The same solver over the value types of pnp_vec.cuh (specialised tree, FP32 only):
+//   V = float : one query per lane (used for the bit-identity test and small batches)
+//   V = F2    : TWO queries per lane.  All FK / Jacobian / J J^T / LDL^T / J^T y arithmetic of the two
+//               queries runs on packed FFMA2 / FMUL2 / FADD2 (one issue slot, two FP32 results per
+//               lane), which frees issue slots for the per-query clamps, compares, table look-ups
+//               and the finish / refill control flow.  Each of the 64 slots of a warp refills
+//               independently from the warp's reserved index pool.
+// Control flow per query, output layouts and counters are those of ik_solve_kernel above.
+// =============================================================================================
+template <typename V>
+struct Slots;
+template <>
+struct Slots<float> {
+  static constexpr int kN = 1;
+  static __device__ __forceinline__ float get(float v, int) { return v; }
+  static __device__ __forceinline__ void set(float& v, int, float x) { v = x; }
+};
+template <>
+struct Slots<F2> {
+  static constexpr int kN = 2;
+  static __device__ __forceinline__ float get(const F2& v, int k) { return k == 0 ? v.v.x : v.v.y; }
+  static __device__ __forceinline__ void set(F2& v, int k, float x) { if (k == 0) v.v.x = x; else v.v.y = x; }
+};
+
+// Deferred flush: a finished slot is FROZEN (its step limit becomes 0, so qn == q and the next passes
+// recompute the same p / n2) instead of being stored and refilled at once; the divergent store +
+// refill code runs only when at least `flush_min` lanes hold a finished slot, when nothing is
+// running any more, or when a query finished on its very first pass (its q_init may lie outside the
+// joint limits, where the limit clip would not leave it untouched).  With 64 slots per warp and a
+// mean of 16 passes per query some slot finishes on 98 % of the passes; flushing every pass made the
+// finish/refill code 45 % of all issued instructions.
+template <typename V, bool kPacked>
+__global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
+  constexpr int S = Slots<V>::kN;
+  const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) float s_q0[8];
+  __shared__ __align__(16) float s_sin[kTrigTabN];
+  __shared__ __align__(16) float s_cos[kTrigTabN];
+  load_trig_table_split(s_sin, s_cos);
+  if (a.q_init_stride == 0 && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
+  __syncthreads();
+  const TrigV trig{s_sin, s_cos};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
+  const int flush_min = (int)a.flush_min;
+
+  V q[NJ], tgt[3], slim(0.0f);
+  int it[S];
+  unsigned idx[S];
+  bool run[S], fin[S], cv[S];
+  bool exhausted = false;
+  unsigned c_n = 0, c_conv = 0;
+  unsigned long long c_iter = 0;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) q[i] = V(0.0f);
+  tgt[0] = tgt[1] = tgt[2] = V(0.0f);
+#pragma unroll
+  for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; run[k] = false; fin[k] = false; cv[k] = false; }
+  unsigned pool_next = 0, pool_end = 0;  // warp-local pool of reserved query indices
+  bool flush = true;  // first pass: nothing to store, every slot to fill
+
+  while (true) {
+    if (flush) {  // warp-uniform
+      // ---- refill idle slots (slot-major ranks: all idle slot-0 lanes first, then slot 1) -----------
+      unsigned need[S], count = 0;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        need[k] = __ballot_sync(FULL, !run[k] && !exhausted);
+        count += (unsigned)__popc(need[k]);
+      }
+      if (count) {
+        const unsigned avail = pool_end - pool_next;
+        unsigned fresh = 0;
+        if (count > avail) {  // warp-uniform
+          if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+          fresh = __shfl_sync(FULL, fresh, 0);
+        }
+        unsigned before = 0;
+        bool ran_out = false;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          if (!run[k] && !exhausted) {
+            const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
+            const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
+            if (id < a.n) {
+              idx[k] = id;
+              const float* tp = a.targets + (size_t)id * 3u;
+              Slots<V>::set(tgt[0], k, tp[0]);
+              Slots<V>::set(tgt[1], k, tp[1]);
+              Slots<V>::set(tgt[2], k, tp[2]);
+              if (a.q_init_stride == 0) {
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, s_q0[i]);
+              } else {
+                const float* qi = a.q_init + (size_t)id * NJ;
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, qi[i]);
+              }
+              it[k] = 0;
+              run[k] = true;
+              Slots<V>::set(slim, k, a.k.step_limit);
+            } else {
+              ran_out = true;
+            }
+          }
+          before += (unsigned)__popc(need[k]);
+        }
+        exhausted = exhausted || ran_out;
+        if (count > avail) {
+          pool_next = fresh + (count - avail);
+          pool_end = fresh + a.chunk;
+        } else {
+          pool_next += count;
+        }
+      }
+      bool any_run = false;
+#pragma unroll
+      for (int k = 0; k < S; ++k) any_run = any_run || run[k];
+      if (!__any_sync(FULL, any_run)) break;  // everything stored, nothing left to take
+    }
+
+    // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
+    V p[3], n2, e[3], J[21], qn[NJ];
+    ik_eval_v<V>(q, tgt, trig, p, e, n2, J);
+    bool imm = false, any_fin = false, any_run = false;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const bool last = it[k] >= a.k.max_iters;                       // loop ran out (ik_solver.py:57)
+      const bool cnv = !last && Slots<V>::get(n2, k) < thresh2;       // :61-64
+      const bool newly = run[k] && (cnv || last);
+      imm = imm || (newly && it[k] == 0);
+      cv[k] = newly ? cnv : cv[k];
+      fin[k] = fin[k] || newly;
+      run[k] = run[k] && !newly;
+      it[k] += (run[k] || (newly && cnv)) ? 1 : 0;                    // iterations = i+1 (:66 / :85), then frozen
+      if (newly) Slots<V>::set(slim, k, 0.0f);
+      any_fin = any_fin || fin[k];
+      any_run = any_run || run[k];
+    }
+    ik_step_v<V>(q, J, e, a.k.damping, slim, qn);
+    const int n_fin = __popc(__ballot_sync(FULL, any_fin));
+    flush = n_fin >= flush_min || __any_sync(FULL, imm) || !__any_sync(FULL, any_run);
+    if (flush) {  // warp-uniform
+      // ---- store finished slots: q (not qn) is the value the convergence test saw; a frozen slot
+      //      recomputes the same p / n2 every pass, so this pass's values are the query's final ones
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        if (fin[k]) {
+          const float err = finish_sqrt(Slots<V>::get(n2, k));
+          const bool conv = cv[k];
+          const int iterations = it[k];
+          const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
+          const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+          const unsigned id = idx[k];
+          if (kPacked) {
+            float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
+            oq[0] = make_float4(Slots<V>::get(q[0], k), Slots<V>::get(q[1], k), Slots<V>::get(q[2], k), Slots<V>::get(q[3], k));
+            oq[1] = make_float4(Slots<V>::get(q[4], k), Slots<V>::get(q[5], k), Slots<V>::get(q[6], k), err);
+            reinterpret_cast<float4*>(a.final_pos)[id] =
+                make_float4(Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k),
+                            __int_as_float((int)((unsigned)iterations | (fl << 24))));
+          } else {
+            float* qo = a.q_out + (size_t)id * NJ;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) qo[i] = Slots<V>::get(q[i], k);
+            if (a.final_pos) {
+              float* fp = a.final_pos + (size_t)id * 3u;
+              fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
+            }
+            if (a.pos_err) a.pos_err[id] = err;
+            if (a.iters) a.iters[id] = iterations;
+            if (a.flags) a.flags[id] = (uint8_t)fl;
+          }
+          c_n += 1u;
+          c_conv += conv ? 1u : 0u;
+          c_iter += (unsigned)iterations;
+          fin[k] = false;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) q[i] = qn[i];
   }
 
   if (a.counters) {

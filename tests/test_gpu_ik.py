@@ -221,6 +221,43 @@ def test_large_batch_properties(tree, oracle_chain):
     print(f"iteration-count flips FP32 vs FP64 oracle: {flips}/{m}")
 
 
+def test_pair_kernel_is_bit_identical_to_lane_kernel(tree, oracle_chain):
+    """The two-queries-per-lane kernel (packed FFMA2/FMUL2/FADD2, deferred flush) executes the same
+    correctly rounded FP32 operations per query as the one-query-per-lane kernel: every output must be
+    bit-identical, whatever the batch size, q_init mode, output layout or which slot a query lands in."""
+    neutral = torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda")
+    for n in (1, 2, 63, 64, 65, 4097, 300_001, (1 << 21) + 5):
+        q = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=100 + n % 97, device="cuda")
+        targets = engine.fk_jac(q, want_quat=False, want_jac=False)[0]
+        q0 = (neutral + 0.2 * torch.randn((n, 7), device="cuda")).contiguous()
+        # a few unreachable targets (run out of iterations) and queries that converge on the first pass
+        # from a q_init OUTSIDE the joint limits (must be returned untouched, ik_solver.py:61-67)
+        targets[::97] = torch.tensor([2.5, 0.0, 0.5], device="cuda")
+        q_out = q0.clone()
+        q_out[::53, 0] = 3.2  # upper limit of joint 1 is 2.8973
+        t_out = targets.clone()
+        t_out[::53] = engine.fk_jac(q_out[::53].contiguous(), want_quat=False, want_jac=False)[0]
+        for qi, tg in ((neutral, targets), (q0, targets), (q_out, t_out)):
+            for packed in (True, False):
+                cl = torch.zeros(4, dtype=torch.int64, device="cuda")
+                cp = torch.zeros(4, dtype=torch.int64, device="cuda")
+                a = engine.ik_solve(tg, qi, engine.ik_params(max_iters=60, kinematics="spec_lane"), packed=packed, counters=cl)
+                b = engine.ik_solve(tg, qi, engine.ik_params(max_iters=60, kinematics="spec_pair"), packed=packed, counters=cp)
+                for f in ("q", "final_pos", "pos_error", "iterations", "converged", "success"):
+                    assert torch.equal(getattr(a, f), getattr(b, f)), (n, f, packed)
+                assert torch.equal(cl, cp) and int(cl[0]) == n
+        first = engine.ik_solve(t_out, q_out, engine.ik_params(kinematics="spec_pair"))
+        sel = torch.arange(0, n, 53, device="cuda")
+        assert bool((first.iterations[sel] == 1).all()) and torch.equal(first.q[sel], q_out[sel])
+    # and the pair kernel against the FP64 oracle on its own
+    n = 8192
+    qstar = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=5, dtype=torch.float64).numpy()
+    th = c_oracle.fk_jac(oracle_chain, qstar, nthreads=8)[0].astype(np.float32).astype(np.float64)
+    ref = c_oracle.ik_solve(oracle_chain, th, NEUTRAL, nthreads=8)
+    res = engine.ik_solve(torch.tensor(th, dtype=torch.float32, device="cuda"), neutral, engine.ik_params(kinematics="spec_pair"))
+    _compare_with_oracle(res, ref, th, oracle_chain, 1e-3, flip_budget=16)
+
+
 def test_packed_and_separate_outputs_agree(tree):
     """pnp_ik_solve_packed_f32 (the default) and pnp_ik_solve_f32 write the same results."""
     n = 100_003

@@ -104,8 +104,8 @@ class Compiler:
                 return Signed(n, -1)
         name = f"t{self.n_tmp}"
         self.n_tmp += 1
-        expr, op, deps = expr_fn()
-        self.lines.append(dict(name=name, expr=expr, op=op, deps=deps))
+        expr, op, deps, vexpr = expr_fn()
+        self.lines.append(dict(name=name, expr=expr, op=op, deps=deps, vexpr=vexpr))
         n = Node("var", name=name, fp=fp)
         self.nodes.append(n)
         return Signed(n)
@@ -120,6 +120,12 @@ class Compiler:
             v = s.cval
             return self._lit(v) if leading or v >= 0 else f"({self._lit(v)})"
         return s.node.name if s.sign > 0 else (f"-{s.node.name}" if leading else f"(-{s.node.name})")
+
+    def vref(self, s):
+        """Operand text for the function-call ("_v") rendering: signs become pnp_neg()."""
+        if s.is_const:
+            return self._lit(s.cval)
+        return s.node.name if s.sign > 0 else f"pnp_neg({s.node.name})"
 
     # --- arithmetic -------------------------------------------------------------------
     def mul(self, a, b):
@@ -140,7 +146,12 @@ class Compiler:
             ta = self._lit(a.cval) if a.is_const else a.node.name
             tb = self._lit(b.cval) if b.is_const else b.node.name
             # a constant carries its own sign in the literal
-            return f"{'-' if sign < 0 else ''}{ta} * {tb}", "mul", self._deps(a, b)
+            if a.is_const or b.is_const:
+                k, v = (a, b) if a.is_const else (b, a)
+                vx = f"pnp_mul({v.node.name}, {self._lit(k.cval * v.sign)})"
+            else:
+                vx = f"pnp_mul({'pnp_neg(' + a.node.name + ')' if sign < 0 else a.node.name}, {b.node.name})"
+            return f"{'-' if sign < 0 else ''}{ta} * {tb}", "mul", self._deps(a, b), vx
 
         return self._canon(fp, emit)
 
@@ -154,7 +165,8 @@ class Compiler:
         fp = a.fp + b.fp
 
         def emit():
-            return f"{self.ref(a)} + {self.ref(b, leading=False)}", "add", self._deps(a, b)
+            return (f"{self.ref(a)} + {self.ref(b, leading=False)}", "add", self._deps(a, b),
+                    f"pnp_add({self.vref(a)}, {self.vref(b)})")
 
         return self._canon(fp, emit)
 
@@ -176,9 +188,12 @@ class Compiler:
                 k, v = (a, b) if a.is_const else (b, a)
                 coef = k.cval * v.sign
                 prod = f"{self._lit(coef)} * {v.node.name}"
+                vx = f"pnp_fma({v.node.name}, {self._lit(coef)}, {self.vref(c)})"
             else:
-                prod = f"{'-' if a.sign * b.sign < 0 else ''}{a.node.name} * {b.node.name}"
-            return f"{prod} + {self.ref(c, leading=False)}", "fma", self._deps(a, b, c)
+                neg = a.sign * b.sign < 0
+                prod = f"{'-' if neg else ''}{a.node.name} * {b.node.name}"
+                vx = f"pnp_fma({'pnp_neg(' + a.node.name + ')' if neg else a.node.name}, {b.node.name}, {self.vref(c)})"
+            return f"{prod} + {self.ref(c, leading=False)}", "fma", self._deps(a, b, c), vx
 
         return self._canon(fp, emit)
 
@@ -190,7 +205,8 @@ class Compiler:
         return acc
 
     def store(self, target, s):
-        self.lines.append(dict(name=None, expr=f"  {target} = {self.ref(s)};", op="store", deps=self._deps(s)))
+        self.lines.append(dict(name=None, expr=f"  {target} = {self.ref(s)};", op="store", deps=self._deps(s),
+                               vexpr=f"  {target} = {self.vref(s)};"))
 
     @staticmethod
     def _deps(*ops):
@@ -205,14 +221,16 @@ class Compiler:
                 live.update(ln["deps"])
         keep.reverse()
         stats = dict(mul=0, add=0, fma=0)
-        out = []
+        out, vout = [], []
         for ln in keep:
             if ln["op"] == "store":
                 out.append(ln["expr"])
+                vout.append(ln["vexpr"])
             else:
                 stats[ln["op"]] += 1
                 out.append(f"  const T {ln['name']} = {ln['expr']};")
-        return out, stats
+                vout.append(f"  const T {ln['name']} = {ln['vexpr']};")
+        return out, stats, vout
 
 
 def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: bool):
@@ -290,8 +308,14 @@ def gen_function(tree, rng, name, want_jacp, want_full):
     if want_full:
         sig += ", T* __restrict__ R"
     out_lines.append(f"template <typename T>\n__device__ __forceinline__ void {name}({sig}) {{")
-    body, stats = cp.finish()
+    body, stats, vbody = cp.finish()
     out_lines.extend(body)
+    out_lines.append("}")
+    # the same straight-line program in function-call form (pnp_fma / pnp_mul / pnp_add / pnp_neg,
+    # overloaded for float, double and the packed f32x2 pair type): explicit FMAs, no reliance on
+    # contraction, so it also instantiates for types the compiler cannot contract (FFMA2).
+    out_lines.append(f"template <typename T>\n__device__ __forceinline__ void {name}_v({sig}) {{")
+    out_lines.extend(vbody)
     out_lines.append("}")
     return "\n".join(out_lines), stats, jp_zero, jr_zero
 
@@ -333,12 +357,34 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         flops_jjt += 2 * len(terms) - 1 if terms else 0
         jjt.append(f"  A[{k}] = {' + '.join(terms) if terms else 'T(0)'};")
     jjt.append("}")
+    jjt.append("template <typename T>\n__device__ __forceinline__ void spec_jjt_v(const T* __restrict__ J, T* __restrict__ A) {")
+    for k, (r, s_) in enumerate(pairs):
+        cols = [j for j in range(7) if not (jp_zero[r, j] or jp_zero[s_, j])]
+        if not cols:
+            jjt.append(f"  A[{k}] = T(0.0);")
+            continue
+        acc = f"pnp_mul(J[{r * 7 + cols[0]}], J[{s_ * 7 + cols[0]}])"
+        for j in cols[1:]:
+            acc = f"pnp_fma(J[{r * 7 + j}], J[{s_ * 7 + j}], {acc})"
+        jjt.append(f"  A[{k}] = {acc};")
+    jjt.append("}")
     jty = ["template <typename T>\n__device__ __forceinline__ void spec_jty(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {"]
     flops_jty = 0
     for j in range(7):
         terms = [f"J[{r * 7 + j}] * y[{r}]" for r in range(3) if not jp_zero[r, j]]
         flops_jty += 2 * len(terms) - 1 if terms else 0
         jty.append(f"  dq[{j}] = {' + '.join(terms) if terms else 'T(0)'};")
+    jty.append("}")
+    jty.append("template <typename T>\n__device__ __forceinline__ void spec_jty_v(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {")
+    for j in range(7):
+        rows = [r for r in range(3) if not jp_zero[r, j]]
+        if not rows:
+            jty.append(f"  dq[{j}] = T(0.0);")
+            continue
+        acc = f"pnp_mul(J[{rows[0] * 7 + j}], y[{rows[0]}])"
+        for r in rows[1:]:
+            acc = f"pnp_fma(J[{r * 7 + j}], y[{r}], {acc})"
+        jty.append(f"  dq[{j}] = {acc};")
     jty.append("}")
 
     def flop(st):
