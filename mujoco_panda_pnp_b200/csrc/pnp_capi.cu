@@ -216,7 +216,7 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   const int slot = 8 + (S - 1) * 2 + (kPacked ? 1 : 0);
   if (s->occ_ik[slot] == 0) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kPacked>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kPacked, true>,
                                                                   pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
@@ -234,7 +234,10 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     const bool oversubscribed = (long long)a.n >= (long long)s->sm_count * 8192;
     args.flush_min = env_flush > 0 ? (unsigned)env_flush : (S == 2 ? (small ? 1u : 8u) : (oversubscribed ? 4u : 1u));
   }
-  pnp::ik_solve_v_kernel<V, kPacked><<<grid, block, 0, st>>>(args);
+  if (a.q_init_stride == 0)
+    pnp::ik_solve_v_kernel<V, kPacked, true><<<grid, block, 0, st>>>(args);
+  else
+    pnp::ik_solve_v_kernel<V, kPacked, false><<<grid, block, 0, st>>>(args);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;
@@ -242,11 +245,11 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
 
 // FP32 on the specialised tree always runs the value-type kernels (same arithmetic in both, so a
 // batch gives bit-identical results whichever is picked).  AUTO / SPECIALIZED: two queries per lane
-// once the batch oversubscribes the machine (>= 8192 queries per SM); below that the batch is
+// once the batch oversubscribes the machine (>= 4096 queries per SM); below that the batch is
 // latency bound and one query per lane finishes sooner.
 template <bool kPacked>
 int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
-  const bool big = (long long)a.n >= (long long)s->sm_count * 8192;
+  const bool big = (long long)a.n >= (long long)s->sm_count * 4096;
   if (kinematics == PNP_KIN_SPEC_PAIR || (kinematics != PNP_KIN_SPEC_LANE && big))
     return launch_ik_v<pnp::F2, kPacked>(s, a, (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2, st);
   return launch_ik_v<float, kPacked>(s, a, small, st);

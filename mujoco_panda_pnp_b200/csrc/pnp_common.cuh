@@ -411,8 +411,8 @@ __device__ __forceinline__ void ik_eval_v(const V (&q)[NJ], const V (&tgt)[3], c
 }
 
 template <typename V>
-__device__ __forceinline__ void ik_step_v(const V (&q)[NJ], const V (&J)[21], const V (&e)[3], float damping,
-                                          const V& slim, V (&qn)[NJ]) {
+__device__ __forceinline__ void ik_step_v(V (&q)[NJ], const V (&J)[21], const V (&e)[3], float damping,
+                                          const V& slim) {  // q is updated in place
   V A[6];
   pnp_spec::spec_jjt_v<V>(J, A);
   const V lam(damping);
@@ -435,8 +435,11 @@ __device__ __forceinline__ void ik_step_v(const V (&q)[NJ], const V (&J)[21], co
   pnp_spec::spec_jty_v<V>(J, y, dq);
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    const V d = v_clamp_sym(dq[i], slim);                                                                // :80
-    qn[i] = v_clamp(pnp_add(q[i], d), pnp_spec::spec_lower<float>(i), pnp_spec::spec_upper<float>(i));   // :81
+    // a joint whose Jacobian column is structurally zero (joint 7: the EE site lies on its axis) has
+    // dq == 0 exactly: only the limit clip of :81 remains
+    const bool moves = !pnp_spec::spec_jp_col_zero(i);
+    const V qd = moves ? pnp_add(q[i], v_clamp_sym(dq[i], slim)) : q[i];                                 // :80
+    q[i] = v_clamp(qd, pnp_spec::spec_lower<float>(i), pnp_spec::spec_upper<float>(i));                  // :81
   }
 }
 

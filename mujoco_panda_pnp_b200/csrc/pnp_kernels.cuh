@@ -328,10 +328,15 @@ struct Slots<F2> {
 // recompute the same p / n2) instead of being stored and refilled at once; the divergent store +
 // refill code runs only when at least `flush_min` lanes hold a finished slot, when nothing is
 // running any more, or when a query finished on its very first pass (its q_init may lie outside the
-// joint limits, where the limit clip would not leave it untouched).  With 64 slots per warp and a
+// joint limits, where the limit clip would not leave it untouched - see the store block).  With 64 slots per warp and a
 // mean of 16 passes per query some slot finishes on 98 % of the passes; flushing every pass made the
 // finish/refill code 45 % of all issued instructions.
-template <typename V, bool kPacked>
+//
+// kBcast: one q_init for the whole batch (staged in shared memory) vs one per query.  A template
+// parameter rather than a run-time branch because ptxas puts the (predicated-off) q_init loads on
+// the scoreboard of the target loads, and the first trig FFMA2 of the pass then waited a full
+// global-load latency for targets it does not need until mid-pass.
+template <typename V, bool kPacked, bool kBcast>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
@@ -339,17 +344,17 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   __shared__ __align__(16) float s_sin[kTrigTabN];
   __shared__ __align__(16) float s_cos[kTrigTabN];
   load_trig_table_split(s_sin, s_cos);
-  if (a.q_init_stride == 0 && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
+  if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   __syncthreads();
   const TrigV trig{s_sin, s_cos};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
+  enum { IDLE = 0, RUN = 1, FIN_CONV = 2, FIN_NOCONV = 3 };
 
   V q[NJ], tgt[3], slim(0.0f);
-  int it[S];
+  int it[S], st[S];
   unsigned idx[S];
-  bool run[S], fin[S], cv[S];
   bool exhausted = false;
   unsigned c_n = 0, c_conv = 0;
   unsigned long long c_iter = 0;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   for (int i = 0; i < NJ; ++i) q[i] = V(0.0f);
   tgt[0] = tgt[1] = tgt[2] = V(0.0f);
 #pragma unroll
-  for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; run[k] = false; fin[k] = false; cv[k] = false; }
+  for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; st[k] = IDLE; }
   unsigned pool_next = 0, pool_end = 0;  // warp-local pool of reserved query indices
   bool flush = true;  // first pass: nothing to store, every slot to fill
 
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       unsigned need[S], count = 0;
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        need[k] = __ballot_sync(FULL, !run[k] && !exhausted);
+        need[k] = __ballot_sync(FULL, st[k] == IDLE && !exhausted);
         count += (unsigned)__popc(need[k]);
       }
       if (count) {
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         bool ran_out = false;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-          if (!run[k] && !exhausted) {
+          if (st[k] == IDLE && !exhausted) {
             const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
             const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
             if (id < a.n) {
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
               Slots<V>::set(tgt[0], k, tp[0]);
               Slots<V>::set(tgt[1], k, tp[1]);
               Slots<V>::set(tgt[2], k, tp[2]);
-              if (a.q_init_stride == 0) {
+              if (kBcast) {
 #pragma unroll
                 for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, s_q0[i]);
               } else {
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
                 for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, qi[i]);
               }
               it[k] = 0;
-              run[k] = true;
+              st[k] = RUN;
               Slots<V>::set(slim, k, a.k.step_limit);
             } else {
               ran_out = true;
@@ -417,54 +422,65 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       }
       bool any_run = false;
 #pragma unroll
-      for (int k = 0; k < S; ++k) any_run = any_run || run[k];
+      for (int k = 0; k < S; ++k) any_run = any_run || st[k] == RUN;
       if (!__any_sync(FULL, any_run)) break;  // everything stored, nothing left to take
     }
 
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
-    V p[3], n2, e[3], J[21], qn[NJ];
+    V p[3], n2, e[3], J[21];
     ik_eval_v<V>(q, tgt, trig, p, e, n2, J);
-    bool imm = false, any_fin = false, any_run = false;
+    bool any_fin = false, any_run = false, imm = false;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const bool last = it[k] >= a.k.max_iters;                       // loop ran out (ik_solver.py:57)
-      const bool cnv = !last && Slots<V>::get(n2, k) < thresh2;       // :61-64
-      const bool newly = run[k] && (cnv || last);
-      imm = imm || (newly && it[k] == 0);
-      cv[k] = newly ? cnv : cv[k];
-      fin[k] = fin[k] || newly;
-      run[k] = run[k] && !newly;
-      it[k] += (run[k] || (newly && cnv)) ? 1 : 0;                    // iterations = i+1 (:66 / :85), then frozen
-      if (newly) Slots<V>::set(slim, k, 0.0f);
-      any_fin = any_fin || fin[k];
-      any_run = any_run || run[k];
+      const bool last = it[k] >= a.k.max_iters;                            // loop ran out (ik_solver.py:57)
+      const bool newly = st[k] == RUN && (last || Slots<V>::get(n2, k) < thresh2);   // :61-64
+      const bool stays = st[k] == RUN && !newly;
+      imm = imm || (newly && it[k] == 0);                                  // finished on its first pass
+      it[k] += (stays || (newly && !last)) ? 1 : 0;                        // iterations = i+1 (:66 / :85), then frozen
+      if (newly) {
+        st[k] = last ? FIN_NOCONV : FIN_CONV;
+        Slots<V>::set(slim, k, 0.0f);                                      // freeze: the step below leaves q as it is
+      }
+      any_fin = any_fin || st[k] >= FIN_CONV;
+      any_run = any_run || stays;
     }
-    ik_step_v<V>(q, J, e, a.k.damping, slim, qn);
+    ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    flush = n_fin >= flush_min || __any_sync(FULL, imm) || !__any_sync(FULL, any_run);
+    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
     if (flush) {  // warp-uniform
-      // ---- store finished slots: q (not qn) is the value the convergence test saw; a frozen slot
-      //      recomputes the same p / n2 every pass, so this pass's values are the query's final ones
+      // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,
+      //      so this pass's values are the query's final ones.  One exception: a query that finished on
+      //      its FIRST pass returns q_init untouched (ik_solver.py:61-67 tests before any update) even
+      //      when q_init violates the joint limits, where the limit clip of the frozen step has just
+      //      moved it: those are flushed in the same pass (imm) and re-read their q_init.
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        if (fin[k]) {
+        if (st[k] >= FIN_CONV) {
           const float err = finish_sqrt(Slots<V>::get(n2, k));
-          const bool conv = cv[k];
+          const bool conv = st[k] == FIN_CONV;
           const int iterations = it[k];
           const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
           const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
           const unsigned id = idx[k];
+          float qf[NJ];
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
+          if (iterations == (conv ? 1 : 0)) {  // finished on the first pass (non-converged: max_iters == 0)
+            const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
+          }
           if (kPacked) {
             float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
-            oq[0] = make_float4(Slots<V>::get(q[0], k), Slots<V>::get(q[1], k), Slots<V>::get(q[2], k), Slots<V>::get(q[3], k));
-            oq[1] = make_float4(Slots<V>::get(q[4], k), Slots<V>::get(q[5], k), Slots<V>::get(q[6], k), err);
+            oq[0] = make_float4(qf[0], qf[1], qf[2], qf[3]);
+            oq[1] = make_float4(qf[4], qf[5], qf[6], err);
             reinterpret_cast<float4*>(a.final_pos)[id] =
                 make_float4(Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k),
                             __int_as_float((int)((unsigned)iterations | (fl << 24))));
           } else {
             float* qo = a.q_out + (size_t)id * NJ;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) qo[i] = Slots<V>::get(q[i], k);
+            for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
             if (a.final_pos) {
               float* fp = a.final_pos + (size_t)id * 3u;
               fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
@@ -476,12 +492,10 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           c_n += 1u;
           c_conv += conv ? 1u : 0u;
           c_iter += (unsigned)iterations;
-          fin[k] = false;
+          st[k] = IDLE;
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) q[i] = qn[i];
   }
 
   if (a.counters) {

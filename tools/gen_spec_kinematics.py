@@ -249,8 +249,14 @@ def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: boo
         axes.append([R[r][2] for r in range(3)])
         need_xy = want_rot or i < 6 or np.any(np.abs(tree.ee_pos[:2]) > 0)
         if need_xy:
-            newx = [cp.fma(c[i], R[r][0], cp.mul(s[i], R[r][1])) for r in range(3)]
-            newy = [cp.fma(c[i], R[r][1], cp.mul(Signed(s[i].node, -s[i].sign), R[r][0])) for r in range(3)]
+            # emission order groups the three rows of each product so that consecutive instructions
+            # share s_i (then c_i) in the same operand slot: on the packed f32x2 path the register file
+            # delivers two 64-bit operands per instruction slot (a third costs an extra cycle unless it
+            # sits in the operand-reuse cache, tools/microbench/fp32x2_operands.cu)
+            mx = [cp.mul(s[i], R[r][1]) for r in range(3)]
+            my = [cp.mul(Signed(s[i].node, -s[i].sign), R[r][0]) for r in range(3)]
+            newx = [cp.fma(c[i], R[r][0], mx[r]) for r in range(3)]
+            newy = [cp.fma(c[i], R[r][1], my[r]) for r in range(3)]
             R = [[newx[r], newy[r], R[r][2]] for r in range(3)]
     ee = [cp.const(v) for v in tree.ee_pos]
     p_ee = [cp.dot(R[r], ee, init=p[r]) for r in range(3)]
@@ -358,15 +364,18 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         jjt.append(f"  A[{k}] = {' + '.join(terms) if terms else 'T(0)'};")
     jjt.append("}")
     jjt.append("template <typename T>\n__device__ __forceinline__ void spec_jjt_v(const T* __restrict__ J, T* __restrict__ A) {")
-    for k, (r, s_) in enumerate(pairs):
-        cols = [j for j in range(7) if not (jp_zero[r, j] or jp_zero[s_, j])]
-        if not cols:
-            jjt.append(f"  A[{k}] = T(0.0);")
-            continue
-        acc = f"pnp_mul(J[{r * 7 + cols[0]}], J[{s_ * 7 + cols[0]}])"
-        for j in cols[1:]:
-            acc = f"pnp_fma(J[{r * 7 + j}], J[{s_ * 7 + j}], {acc})"
-        jjt.append(f"  A[{k}] = {acc};")
+    # column-major accumulation: the products of one Jacobian column are emitted back to back and share
+    # J[r][j] in the first operand slot (operand-reuse cache, see build_chain)
+    started = [False] * 6
+    for j in range(7):
+        for k, (r, s_) in enumerate(pairs):
+            if jp_zero[r, j] or jp_zero[s_, j]:
+                continue
+            a_, b_ = f"J[{r * 7 + j}]", f"J[{s_ * 7 + j}]"
+            jjt.append(f"  {'T ' if not started[k] else ''}a{k} = " + (f"pnp_fma({a_}, {b_}, a{k});" if started[k] else f"pnp_mul({a_}, {b_});"))
+            started[k] = True
+    for k in range(6):
+        jjt.append(f"  A[{k}] = {'a%d' % k if started[k] else 'T(0.0)'};")
     jjt.append("}")
     jty = ["template <typename T>\n__device__ __forceinline__ void spec_jty(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {"]
     flops_jty = 0
@@ -376,20 +385,22 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         jty.append(f"  dq[{j}] = {' + '.join(terms) if terms else 'T(0)'};")
     jty.append("}")
     jty.append("template <typename T>\n__device__ __forceinline__ void spec_jty_v(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {")
+    # row-major accumulation: y[r] stays in the second operand slot across the seven joints
+    started = [False] * 7
+    for r in range(3):
+        for j in range(7):
+            if jp_zero[r, j]:
+                continue
+            jty.append(f"  {'T ' if not started[j] else ''}d{j} = " + (f"pnp_fma(J[{r * 7 + j}], y[{r}], d{j});" if started[j] else f"pnp_mul(J[{r * 7 + j}], y[{r}]);"))
+            started[j] = True
     for j in range(7):
-        rows = [r for r in range(3) if not jp_zero[r, j]]
-        if not rows:
-            jty.append(f"  dq[{j}] = T(0.0);")
-            continue
-        acc = f"pnp_mul(J[{rows[0] * 7 + j}], y[{rows[0]}])"
-        for r in rows[1:]:
-            acc = f"pnp_fma(J[{r * 7 + j}], y[{r}], {acc})"
-        jty.append(f"  dq[{j}] = {acc};")
+        jty.append(f"  dq[{j}] = {'d%d' % j if started[j] else 'T(0.0)'};")
     jty.append("}")
 
     def flop(st):
         return st["mul"] + st["add"] + 2 * st["fma"]
 
+    col_zero = " || ".join(f"j == {j}" for j in range(7) if jp_zero[:, j].all()) or "false"
     mask_rows = ", ".join("{" + ", ".join("true" if z else "false" for z in row) + "}" for row in jp_zero)
     hdr = f"""// GENERATED by tools/gen_spec_kinematics.py - do not edit.
 // Source tree: {src_desc}
@@ -416,6 +427,8 @@ static constexpr char kTreeSha256[] = "{tree_fingerprint(tree)}";
 {cfun('spec_qref', tree.qref)}
 // structurally-zero entries of the 3x7 position Jacobian
 static constexpr bool kJpZero[3][7] = {{{mask_rows}}};
+// joints whose whole position-Jacobian column is structurally zero (they cannot move the EE site)
+__host__ __device__ __forceinline__ constexpr bool spec_jp_col_zero(int j) {{ return {col_zero}; }}
 
 {f_pos}
 
