@@ -485,16 +485,33 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   bool spec;
   if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
   if (n == 0) return PNP_OK;
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_waypoints: n must be < 2^31 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ticket;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
+  }
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::WaypointArgs<float> a;
-  a.q_start = q_start; a.goal = goal; a.n = n; a.n_steps = n_steps;
+  a.q_start = q_start; a.goal = goal; a.n = (unsigned)n; a.n_steps = n_steps; a.ticket = ticket;
   a.step_size = (float)step_size; a.reach_thresh = 0.01f;
   a.k = make_ik_const<float>(params);
   a.q_out = q_out; a.pos_out = pos_out; a.n_accepted = n_accepted; a.iters_total = iters_total;
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = small ? 32 : pnp::IK_BLOCK;
-  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 4);
-  cudaStream_t st = (cudaStream_t)stream;
+  int occ = 4;
+  if (!small) {
+    cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::SpecKin>, pnp::IK_BLOCK, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::GenericKin>, pnp::IK_BLOCK, 0);
+    if (e != cudaSuccess || occ < 1) occ = 4;
+  }
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
+  // envs reserved per ticket atomic: ~1/8 of a warp's share within [32, 128] (keeps the tail short)
+  long long chunk = n / ((long long)grid * (block / 32) * 8);
+  chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk);
+  a.chunk = (unsigned)(chunk & ~31ll);
   if (spec)
     pnp::ik_waypoints_kernel<float, pnp::SpecKin><<<grid, block, 0, st>>>(a);
   else

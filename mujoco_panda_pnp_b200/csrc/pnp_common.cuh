@@ -93,7 +93,14 @@ __device__ __forceinline__ void load_trig_table(float2* s_tab) {
   for (int i = threadIdx.x; i < kTrigTabN / 2; i += blockDim.x) dst[i] = src[i];
 }
 
-__device__ __forceinline__ float rcp_t(float x) { return __fdividef(1.0f, x); }
+// one MUFU.RCP (callers pass pivots of J J^T + damping I in [damping, ~10] or distances > 1e-3: no
+// range fix-up needed, which is what __fdividef(1, x) spends four more instructions on)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_t(float x) { return rcp_approx(x); }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
@@ -337,13 +344,6 @@ using pnp_spec::pnp_neg;
 
 __device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
 __device__ __forceinline__ F2 v_sub(F2 a, F2 b) { return pnp_spec::pnp_sub(a, b); }
-// one MUFU.RCP (the pivots of J J^T + damping I lie in [damping, ~10]: no range fix-up needed, which
-// is what __fdividef(1, x) spends four more instructions on)
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ float v_rcp(float x) { return rcp_approx(x); }
 __device__ __forceinline__ F2 v_rcp(F2 x) { return F2(rcp_approx(x.v.x), rcp_approx(x.v.y)); }
 __device__ __forceinline__ float v_clamp_sym(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }

@@ -518,7 +518,7 @@ template <typename T>
 struct WaypointArgs {
   const T* q_start;
   const T* goal;
-  long long n;
+  unsigned n;       // < 2^31 (checked on the host)
   int n_steps;
   T step_size;
   T reach_thresh;  // MoveIKSkill.pos_thresh = 0.01 (move.py:66,106)
@@ -528,8 +528,18 @@ struct WaypointArgs {
   int32_t* n_accepted;
   int32_t* iters_total;
   unsigned long long* counters;
+  unsigned* ticket; // zeroed before launch
+  unsigned chunk;   // envs a warp reserves per ticket atomic
 };
 
+// The two loop levels (waypoints x DLS passes) are FLATTENED and the lanes are PERSISTENT: every pass
+// of the warp loop is one DLS evaluation for all lanes; a lane whose inner solve finished does its
+// accept / advance-to-next-waypoint bookkeeping on the spot and starts the next solve in the following
+// pass; a lane whose env is finished writes it back and takes the next env (chunked ticket, as in
+// ik_solve_kernel).  A fresh env enters in state INIT and gets its start position FK(q_start) from the
+// shared DLS pass of that round.  (The first version ran the inner solve as a warp-synchronous loop per
+// waypoint inside a grid-stride loop over envs: warm-started solves take 2 passes on average but 3 for
+// some lane of nearly every warp, and envs need 10-50 waypoints, so lanes idled for 1/3 of the passes.)
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
@@ -537,77 +547,113 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
   if (Trig<T>::kUsesTable) load_trig_table(s_tab);
   __syncthreads();
   const Trig<T> trig{s_tab};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  enum { IDLE = 0, INIT = 1, RUN = 2 };
   unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < a.n;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long e = base + lane;
-    const bool valid = e < a.n;
-    T q[NJ], goal[3], pos[3];
+  unsigned pool_next = 0, pool_end = 0;
+  bool exhausted = false;
+  unsigned e = 0;
+  int state = IDLE;
+  T q[NJ], qs[NJ], goal[3] = {T(0), T(0), T(0)}, pos[3] = {T(0), T(0), T(0)}, tgt[3] = {T(0), T(0), T(0)};
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) q[i] = valid ? a.q_start[e * NJ + i] : T(0);
+  for (int i = 0; i < NJ; ++i) q[i] = qs[i] = T(0);
+  int step = 0, it = 0, accepted = 0, iters_sum = 0, fails = 0;
+
+  // set up the solve of waypoint `step`; false when the env has nothing left to do
+  auto next_waypoint = [&]() -> bool {
+    if (step >= a.n_steps) return false;
+    const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];   // :110
+    const T d2 = (dx * dx + dy * dy) + dz * dz;
+    const T dist = finish_sqrt(d2);                                                // :111 (FP32: d2 * rsqrt(d2))
+    if (!(dist > a.reach_thresh)) return false;                                    // :106 (pos no longer changes)
+    T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                       // :114-117
+    if (fails > 0) stp = stp * T(0.5);                                             // :118-119
+    if (dist > stp) {                                                              // :122-125
+      const T f = stp * rcp_t(dist);
+      tgt[0] = pos[0] + dx * f; tgt[1] = pos[1] + dy * f; tgt[2] = pos[2] + dz * f;
+    } else {
+      tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
+    }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) goal[i] = valid ? a.goal[e * 3 + i] : T(0);
-    fk_position<T, Kin>(q, pos);                                   // move.py:91 start_pos
-    int accepted = 0, iters_sum = 0, fails = 0;
-    for (int step = 0; step < a.n_steps; ++step) {
-      const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];   // :110
-      const T dist = sqrt_t((dx * dx + dy * dy) + dz * dz);                          // :111
-      const bool moving = valid && (dist > a.reach_thresh);                          // :106
-      T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                       // :114-117
-      if (fails > 0) stp = stp * T(0.5);                                             // :118-119
-      T tgt[3];
-      if (dist > stp) {                                                              // :122-125
-        const T f = stp / dist;
-        tgt[0] = pos[0] + dx * f; tgt[1] = pos[1] + dy * f; tgt[2] = pos[2] + dz * f;
-      } else {
-        tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
+    for (int i = 0; i < NJ; ++i) qs[i] = q[i];                                     // solve(next_pos, q_current) (:128)
+    it = 0;
+    return true;
+  };
+
+  while (true) {
+    // ---- refill idle lanes ------------------------------------------------------------------
+    const unsigned need = __ballot_sync(FULL, state == IDLE && !exhausted);
+    if (need) {
+      const unsigned count = (unsigned)__popc(need);
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
       }
-      // solve(next_pos, q_current) with the controller defaults (:128)
-      T qs[NJ], p[3], err = T(0);
+      if (state == IDLE && !exhausted) {
+        const unsigned rank = (unsigned)__popc(need & lanemask_lt);
+        const unsigned idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
+        if (idx < a.n) {
+          e = idx;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) qs[i] = q[i];
-      int it = 0;
-      bool conv = false, done = !moving;
-      while (__any_sync(FULL, !done)) {
-        T n2, qn[NJ], pp[3];
-        ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
-        if (!done) {
-          const bool last = it >= a.k.max_iters;
-          conv = !last && below_thresh(n2, a.k);
-          if (conv || last) {
-            err = finish_sqrt(n2);
-            p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
-            it = conv ? it + 1 : it;
-            done = true;
-          } else {
+          for (int i = 0; i < NJ; ++i) q[i] = qs[i] = a.q_start[(size_t)e * NJ + i];
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
-            ++it;
-          }
+          for (int i = 0; i < 3; ++i) goal[i] = a.goal[(size_t)e * 3 + i];
+          step = 0; accepted = 0; iters_sum = 0; fails = 0;
+          state = INIT;
+        } else {
+          exhausted = true;
         }
       }
-      if (moving) {
+      if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
+      else pool_next += count;
+    }
+    if (!__any_sync(FULL, state != IDLE)) break;
+
+    // ---- one DLS pass for all lanes -------------------------------------------------------------
+    T n2, qn[NJ], pp[3];
+    ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
+    bool advance = false;
+    if (state == INIT) {
+      pos[0] = pp[0]; pos[1] = pp[1]; pos[2] = pp[2];               // move.py:91 start_pos = FK(q_start)
+      state = RUN;
+      advance = true;
+    } else if (state == RUN) {
+      const bool last = it >= a.k.max_iters;
+      const bool conv = !last && below_thresh(n2, a.k);
+      if (conv || last) {
+        const T err = finish_sqrt(n2);
+        const int iters = conv ? it + 1 : it;
         const bool success = conv && (err < a.k.pos_thresh * T(2));
-        iters_sum += it;
-        c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
-        if (success && (err < a.step_size * T(2))) {                                 // :131-138
+        iters_sum += iters;
+        c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)iters;
+        if (success && (err < a.step_size * T(2))) {                               // :131-138
 #pragma unroll
           for (int i = 0; i < NJ; ++i) q[i] = qs[i];
-          pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
+          pos[0] = pp[0]; pos[1] = pp[1]; pos[2] = pp[2];
           fails = 0;
           ++accepted;
         } else {
-          ++fails;                                                                   // :142
+          ++fails;                                                                 // :142
         }
+        ++step;
+        advance = true;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
+        ++it;
       }
     }
-    if (valid) {
+    const bool done = advance && !next_waypoint();
+    if (done) {
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) a.q_out[e * NJ + i] = q[i];
+      for (int i = 0; i < NJ; ++i) a.q_out[(size_t)e * NJ + i] = q[i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) a.pos_out[e * 3 + i] = pos[i];
+      for (int i = 0; i < 3; ++i) a.pos_out[(size_t)e * 3 + i] = pos[i];
       if (a.n_accepted) a.n_accepted[e] = accepted;
       if (a.iters_total) a.iters_total[e] = iters_sum;
+      state = IDLE;
     }
   }
   if (a.counters) {
