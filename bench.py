@@ -547,9 +547,10 @@ def run_ours(args) -> int:
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ik_tflops / fp32_peak, "traffic": ncu_traffic("ik_solve_kernel", n_ik),
+                "frac": ik_tflops / fp32_peak, "traffic": ncu_traffic("ik_solve_v_kernel" if specialized else "ik_solve_kernel", n_ik),
                 "traffic_note": "DRAM bytes/launch from the ncu capture (48 B/query; algorithmic 60 B, part of the output is still in L2 at kernel end)",
-                "kernel": "ik_solve_kernel<float,SpecKin,packed>" if specialized else "ik_solve_kernel<float,GenericKin,packed>",
+                "kernel": ("ik_solve_v_kernel<F2,packed,bcast> (two queries per lane on FFMA2/FMUL2/FADD2)" if specialized
+                           else "ik_solve_kernel<float,GenericKin,packed>"),
                 "kernel_ms": ik_kernel_ms,
                 "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json)",
                 "algorithmic": f"{IK_FLOP_PER_ITER:.0f} FLOP x iterations + {IK_FLOP_PER_SOLVE:.0f} per solve (SURVEY 8d)",

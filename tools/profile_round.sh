@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"
 SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --log2-n-ik 22 --log2-n-reward 24"
 $SMALL > $OUT/plain_small_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ik_solve_kernel -s 3 -c 1 -f -o $OUT/ik_${TAG} $SMALL > $OUT/ncu_ik_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ik_solve_v_kernel -s 3 -c 1 -f -o $OUT/ik_${TAG} $SMALL > $OUT/ncu_ik_${TAG}.log 2>&1
 echo "ik full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:reward_kernel -s 3 -c 1 -f -o $OUT/reward_${TAG} $SMALL > $OUT/ncu_reward_${TAG}.log 2>&1
 echo "reward full rc=$?"
