@@ -1,5 +1,6 @@
 // C ABI of libpnp_b200.so (declared in include/pnp_b200.h).  Host-side glue only: argument
 // checks, constant-memory upload, launch geometry, the host-buffer pipeline.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -26,6 +27,7 @@ struct DeviceState {
   unsigned* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
   unsigned ticket_seq = 0;
   int occ_ik[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool obs_smem_set = false;
 };
 constexpr int kMaxDevices = 16;
 constexpr int kTicketSlots = 64;
@@ -173,14 +175,42 @@ int get_obs_impl(const T* q_arm, const T* qvel_arm, const T* fingers, const T* o
   pnp::ObsArgs<T> a;
   a.q_arm = q_arm; a.qvel_arm = qvel_arm; a.fingers = fingers; a.obj_pos = obj_pos; a.obj_quat = obj_quat;
   a.obj_vel = obj_vel; a.goal = goal; a.goal_stride = goal_stride; a.n = n; a.dt = (T)dt; a.out = out;
-  const int grid = grid_for(n, pnp::OBS_TILE, s->sm_count, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (spec)
-    pnp::get_obs_kernel<T, pnp::SpecKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
-  else
-    pnp::get_obs_kernel<T, pnp::GenericKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  // FP32, 16-byte aligned arrays: full 128-env tiles go through the bulk-async-copy kernel, the ragged
+  // tail (and everything else) through the per-lane kernel
+  int64_t done = 0;
+  if constexpr (std::is_same<T, float>::value) {
+    const bool aligned = aligned16(q_arm) && aligned16(qvel_arm) && aligned16(fingers) && aligned16(obj_pos) &&
+                         aligned16(obj_quat) && aligned16(obj_vel) && aligned16(out) && (goal_stride == 0 || aligned16(goal));
+    static const bool bulk_enabled = [] { const char* e = getenv("PNP_OBS_BULK"); return !e || atoi(e) != 0; }();
+    if (aligned && bulk_enabled && n >= pnp::OBS_TILE) {
+      if (!s->obs_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(pnp::get_obs_bulk_kernel<pnp::SpecKin>, cudaFuncAttributeMaxDynamicSharedMemorySize, pnp::OBS_BULK_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(pnp::get_obs_bulk_kernel<pnp::GenericKin>, cudaFuncAttributeMaxDynamicSharedMemorySize, pnp::OBS_BULK_SMEM));
+        s->obs_smem_set = true;
+      }
+      const int64_t tiles = n / pnp::OBS_TILE;
+      const int grid = (int)std::min<int64_t>(tiles, (int64_t)s->sm_count * 7);  // 7 x 32 KB of shared memory per SM
+      if (spec)
+        pnp::get_obs_bulk_kernel<pnp::SpecKin><<<grid, pnp::OBS_TILE, pnp::OBS_BULK_SMEM, st>>>(a);
+      else
+        pnp::get_obs_bulk_kernel<pnp::GenericKin><<<grid, pnp::OBS_TILE, pnp::OBS_BULK_SMEM, st>>>(a);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+      done = tiles * pnp::OBS_TILE;
+    }
+  }
+  if (done < n) {
+    a.q_arm += done * 7; a.qvel_arm += done * 7; a.fingers += done * 2; a.obj_pos += done * 3; a.obj_quat += done * 4;
+    a.obj_vel += done * 6; a.goal += done * goal_stride; a.out += done * 25; a.n = n - done;
+    const int grid = grid_for(a.n, pnp::OBS_TILE, s->sm_count, 8);
+    if (spec)
+      pnp::get_obs_kernel<T, pnp::SpecKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
+    else
+      pnp::get_obs_kernel<T, pnp::GenericKin><<<grid, pnp::OBS_TILE, 0, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   return PNP_OK;
 }
 

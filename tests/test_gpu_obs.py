@@ -53,3 +53,30 @@ def test_env_level_get_obs_dict(cuda_lib):
         env._get_obs({"q_arm": g["q_arm"]})
     assert engine.get_obs(*[torch.empty((0, t.shape[1]), device="cuda") for t in
                             [torch.tensor(g[k]) for k in KEYS]]).shape == (0, 25)
+
+
+@pytest.mark.parametrize("kin", ["specialized", "generic"])
+def test_bulk_copy_kernel_equals_per_lane_kernel(cuda_lib, kin):
+    """FP32 full tiles of aligned arrays run get_obs_bulk_kernel (all data movement on cp.async.bulk);
+    unaligned views and tails run get_obs_kernel.  Same row arithmetic: the rows must agree (bitwise up
+    to the compiler's FMA contraction, checked at 2 ulp of the value range) for every size/goal mode."""
+    engine.set_tree(KinematicTree.from_mjcf())
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(11)
+    for n in (127, 128, 129, 1000, 128 * 700 + 77):
+        rnd = lambda *sh: torch.randn(sh, generator=gen, device="cuda")  # noqa: E731
+        # allocate one row more and slice from row 1: 28/8/12/24-byte row strides are then not 16-byte
+        # aligned, which forces the per-lane kernel; the contiguous clones are aligned (bulk kernel)
+        big = [rnd(n + 1, 7), rnd(n + 1, 7), rnd(n + 1, 2).abs() * 0.02, rnd(n + 1, 3), rnd(n + 1, 4), rnd(n + 1, 6), rnd(n + 1, 3)]
+        views = [t[1:] for t in big]
+        assert views[0].data_ptr() % 16 != 0
+        aligned = [v.clone() for v in views]
+        assert all(t.data_ptr() % 16 == 0 for t in aligned)
+        for goal_mode in ("per_env", "broadcast"):
+            g_v = views[6] if goal_mode == "per_env" else torch.tensor([1.0, -0.1, 0.3], device="cuda")
+            g_a = aligned[6] if goal_mode == "per_env" else g_v
+            a = engine.get_obs(*aligned[:6], g_a, kinematics=kin)
+            b = engine.get_obs(*views[:6], g_v, kinematics=kin)
+            assert a.shape == (n, 25)
+            assert float((a - b).abs().max()) <= 1e-6, (n, goal_mode)
+            assert torch.equal(a[:, [6, 7, 8, 9, 19, 20, 21, 22, 23, 24]], b[:, [6, 7, 8, 9, 19, 20, 21, 22, 23, 24]])
