@@ -19,8 +19,8 @@
  *   pnp_get_obs_*          FrankaEnv._get_obs (envs/panda_env.py:279-301) from kinematic state
  *   pnp_reward_*           FrankaEnv.compute_reward / _is_success / goal_distance
  *                          (envs/panda_env.py:205-245, 303-306, 311-315), row-wise
- *   pnp_her_relabel_f32    HER goal relabel + reward + VecNormalize over stored transitions
- *                          (scripts/train.py:4,68,74-93; SB3 HerReplayBuffer semantics)
+ *   pnp_her_relabel_f32,   HER goal relabel + reward + VecNormalize over stored transitions
+ *   pnp_her_relabel_table_f32   (scripts/train.py:4,68,74-93; SB3 HerReplayBuffer semantics)
  *   pnp_*_host             the same operators taking HOST buffers (what a Python/ctypes
  *                          caller of the reference API holds): chunked H2D -> kernel -> D2H
  *                          pipeline on library-owned streams
@@ -243,6 +243,17 @@ int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* 
                         const int32_t* task_index, int64_t n, const PnpRewardParams* params,
                         const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
                         float* is_success, unsigned long long* counters, void* stream);
+
+/* Same operator with the future goals gathered from a separate table future_ag[n,3] (row j = the
+ * achieved goal of next_obs[j]; what SB3's DictReplayBuffer keeps as next_observations["achieved_goal"])
+ * instead of out of the 100-byte next_obs rows: the random 12-byte gather then hits a table that fits
+ * the L2 instead of costing a 64-128 B DRAM burst per transition.  future_ag == NULL is
+ * pnp_her_relabel_f32.  Identical results when the table matches next_obs[:, 19:22]. */
+int pnp_her_relabel_table_f32(const float* obs, const float* next_obs, const int32_t* future_idx,
+                              const float* future_ag, const float* ee_quat, const int32_t* task_index, int64_t n,
+                              const PnpRewardParams* params, const PnpNormalizeParams* norm, float* out_obs,
+                              float* out_next_obs, float* reward, float* is_success, unsigned long long* counters,
+                              void* stream);
 
 /* goal_distance (panda_env.py:311-315): a[n,3], b[n,3] -> d[n] (FP64 math) */
 int pnp_goal_distance_f64(const double* a, const double* b, int64_t n, double* d, void* stream);

@@ -97,6 +97,8 @@ SIGNATURES = {
     "pnp_get_obs_f64": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_double, _P, c_int32, _P]),
     "pnp_her_relabel_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), POINTER(PnpNormalizeParams),
                                     _P, _P, _P, _P, _P, _P]),
+    "pnp_her_relabel_table_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams),
+                                          POINTER(PnpNormalizeParams), _P, _P, _P, _P, _P, _P]),
     "pnp_goal_distance_f64": (c_int, [_P, _P, c_int64, _P, _P]),
     "pnp_host_ctx_create": (c_int, [POINTER(c_void_p), c_int64]),
     "pnp_host_ctx_destroy": (c_int, [c_void_p]),

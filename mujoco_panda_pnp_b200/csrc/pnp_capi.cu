@@ -696,6 +696,14 @@ int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* 
                         const int32_t* task_index, int64_t n, const PnpRewardParams* params,
                         const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
                         float* is_success, unsigned long long* counters, void* stream) {
+  return pnp_her_relabel_table_f32(obs, next_obs, future_idx, nullptr, ee_quat, task_index, n, params, norm, out_obs,
+                                   out_next_obs, reward, is_success, counters, stream);
+}
+
+int pnp_her_relabel_table_f32(const float* obs, const float* next_obs, const int32_t* future_idx, const float* future_ag,
+                              const float* ee_quat, const int32_t* task_index, int64_t n, const PnpRewardParams* params,
+                              const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
+                              float* is_success, unsigned long long* counters, void* stream) {
   if (!params) return fail(PNP_EINVAL, "params is NULL");
   if (params->n_tasks <= 0) return fail(PNP_EINVAL, "n_tasks must be > 0");
   if (n < 0 || (n > 0 && (!obs || !next_obs || !future_idx || !ee_quat || !task_index || !out_obs || !out_next_obs || !reward)))
@@ -708,7 +716,8 @@ int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* 
   if (rc) return rc;
   if (n == 0) return PNP_OK;
   pnp::HerArgs a;
-  a.obs = obs; a.next_obs = next_obs; a.future_idx = future_idx; a.ee_quat = ee_quat; a.task = task_index;
+  a.obs = obs; a.next_obs = next_obs; a.future_idx = future_idx; a.future_ag = future_ag; a.ee_quat = ee_quat;
+  a.task = task_index;
   a.n_total = n; a.k = make_reward_const(params);
   a.out_obs = out_obs; a.out_next = out_next_obs; a.reward = reward; a.success = is_success; a.counters = counters;
   a.normalize = norm ? 1 : 0;

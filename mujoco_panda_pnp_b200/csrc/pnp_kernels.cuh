@@ -1289,6 +1289,9 @@ struct HerArgs {
   const float* obs;
   const float* next_obs;
   const int32_t* future_idx;
+  const float* future_ag;  // optional [n_total][3] table of next achieved goals (what a replay buffer keeps
+                           // anyway): the random gather then reads 12 B from a table that fits the L2
+                           // instead of 12 B out of a 100-byte row (a 64-128 B DRAM burst each)
   const float* ee_quat;
   const int32_t* task;
   long long n;          // rows handled by this launch
@@ -1350,7 +1353,8 @@ __device__ __forceinline__ void her_row(const HerArgs& a, long long row, float* 
   const int fi = a.future_idx[row];
   float g[3] = {x[22], x[23], x[24]};
   if (fi >= 0) {
-    const float* src = a.next_obs + (long long)fi * HER_ROW + 19;   // future achieved_goal (original rows)
+    const float* src = a.future_ag ? a.future_ag + (long long)fi * 3
+                                   : a.next_obs + (long long)fi * HER_ROW + 19;   // future achieved_goal (original rows)
     g[0] = src[0]; g[1] = src[1]; g[2] = src[2];
   }
   const float ag[3] = {x[19], x[20], x[21]};

@@ -418,12 +418,15 @@ def normalize_params(mean, var, epsilon: float = 1e-8, clip_obs: float = 10.0) -
 
 def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewardParams,
                 norm: Optional[PnpNormalizeParams] = None, want_success: bool = True,
-                counters: Optional[torch.Tensor] = None, out_obs=None, out_next_obs=None, out_reward=None):
+                counters: Optional[torch.Tensor] = None, out_obs=None, out_next_obs=None, out_reward=None,
+                future_ag: Optional[torch.Tensor] = None):
     """HER relabel + reward + optional VecNormalize over N stored transitions (CUDA float32).
 
     obs / next_obs: [N,25] rows (observation19 | achieved_goal3 | desired_goal3); future_idx int32[N]
     (row whose next achieved_goal becomes the goal, < 0 keeps the stored one); ee_quat[N,4];
-    task_index int32[N].  Returns (out_obs[N,25], out_next_obs[N,25], reward[N], is_success[N] | None)."""
+    task_index int32[N].  ``future_ag`` [N,3] (optional): the next achieved goals as a separate table
+    (SB3's ``next_observations["achieved_goal"]``); the goal gather then reads this L2-sized table instead
+    of the 100-byte rows.  Returns (out_obs[N,25], out_next_obs[N,25], reward[N], is_success[N] | None)."""
     lib = _lib.load()
     obs = _check_cuda("obs", obs, torch.float32, (25,))
     next_obs = _check_cuda("next_obs", next_obs, torch.float32, (25,))
@@ -431,8 +434,11 @@ def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewar
     ee_quat = _check_cuda("ee_quat", ee_quat, torch.float32, (4,))
     task_index = _check_cuda("task_index", task_index, torch.int32, ())
     n = obs.shape[0]
-    for name, t in (("next_obs", next_obs), ("future_idx", future_idx), ("ee_quat", ee_quat), ("task_index", task_index)):
-        if t.shape[0] != n:
+    if future_ag is not None:
+        future_ag = _check_cuda("future_ag", future_ag, torch.float32, (3,))
+    for name, t in (("next_obs", next_obs), ("future_idx", future_idx), ("ee_quat", ee_quat), ("task_index", task_index),
+                    ("future_ag", future_ag)):
+        if t is not None and t.shape[0] != n:
             raise ValueError(f"{name} disagrees with obs on N")
     dev = obs.device
     o = out_obs if out_obs is not None else torch.empty_like(obs)
@@ -441,9 +447,10 @@ def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewar
     sc = torch.empty((n,), dtype=torch.float32, device=dev) if want_success else None
     with torch.cuda.device(dev):
         _lib.check(
-            lib.pnp_her_relabel_f32(_ptr(obs), _ptr(next_obs), _ptr(future_idx), _ptr(ee_quat), _ptr(task_index), n,
-                                    ctypes.byref(params), ctypes.byref(norm) if norm is not None else None, _ptr(o),
-                                    _ptr(x), _ptr(r), _ptr(sc), _ptr(counters), _stream()),
+            lib.pnp_her_relabel_table_f32(_ptr(obs), _ptr(next_obs), _ptr(future_idx), _ptr(future_ag), _ptr(ee_quat),
+                                          _ptr(task_index), n, ctypes.byref(params),
+                                          ctypes.byref(norm) if norm is not None else None, _ptr(o), _ptr(x), _ptr(r),
+                                          _ptr(sc), _ptr(counters), _stream()),
             "pnp_her_relabel",
         )
     return o, x, r, sc

@@ -110,3 +110,19 @@ def test_relabel_4m_transitions_properties(cuda_lib):
                            nxt[:, 6].contiguous(), task, engine.reward_params("dense"))
     assert torch.equal(r.view(torch.int32), r2.view(torch.int32)) and torch.equal(s, s2)
     assert int(s.sum()) > n // 32  # the "own row" relabels are placed
+
+
+@pytest.mark.parametrize("n", [5, 129, 4096 + 77, 1 << 20])
+def test_relabel_from_goal_table_is_identical(cuda_lib, n):
+    """pnp_her_relabel_table_f32: future goals gathered from a separate [N,3] table (what a replay buffer
+    keeps as next_observations["achieved_goal"]) instead of out of the 100-byte rows - identical outputs."""
+    obs, nxt, fut, quat, task = _transitions(n, seed=3 + n % 11)
+    mean, var = _norm_stats()
+    table = nxt[:, 19:22].contiguous()
+    for norm in (None, engine.normalize_params(mean, var)):
+        a = engine.her_relabel(obs, nxt, fut, quat, task, engine.reward_params("dense"), norm=norm)
+        b = engine.her_relabel(obs, nxt, fut, quat, task, engine.reward_params("dense"), norm=norm, future_ag=table)
+        for u, v in zip(a, b):
+            assert torch.equal(u.view(torch.int32), v.view(torch.int32))
+    with pytest.raises(ValueError):
+        engine.her_relabel(obs, nxt, fut, quat, task, engine.reward_params("dense"), future_ag=table[:-1])
