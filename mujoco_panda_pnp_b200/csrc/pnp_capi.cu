@@ -624,7 +624,13 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = small ? 32 : pnp::IK_BLOCK;
-  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 4);
+  int occ = 4;
+  if (!small) {
+    cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::move_ik_plan_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::move_ik_plan_kernel<T, pnp::GenericKin>, pnp::IK_BLOCK, 0);
+    if (e != cudaSuccess || occ < 1) occ = 4;
+  }
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
   // envs reserved per ticket atomic: ~1/8 of a warp's share within [32, 128] (keeps the tail short)
   long long chunk = n / ((long long)grid * (block / 32) * 8);
   chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk);

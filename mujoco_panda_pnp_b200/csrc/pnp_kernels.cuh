@@ -845,11 +845,11 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArg
 // =============================================================================================
 // MoveIKSkill.reset trajectory planner (skills/move.py:76-191) as a per-lane state machine.
 //
-// One lane per env.  Every round of the warp loop each lane (i) picks the IK target its state
-// asks for - NORMAL: the adaptive waypoint (:110-125); FB1: fallback strategy 1, a 10x smaller
-// step (:149-151); FB2: strategy 2, the same step with y frozen (:163-167) - (ii) all lanes run
-// the shared, divergence-free DLS solve (:128/:152/:168) and (iii) each lane post-processes by
-// state: accept rule success && err < 2*step_size (:131), failure counter incl. the reference's
+// One lane per env.  Every trip of the warp loop is ONE shared, divergence-free DLS pass
+// (:128/:152/:168) for all lanes.  A lane whose solve finished in that pass post-processes it by
+// state and then picks the IK target its new state asks for - NORMAL: the adaptive waypoint
+// (:110-125); FB1: fallback strategy 1, a 10x smaller step (:149-151); FB2: strategy 2, the same
+// step with y frozen (:163-167).  Post-processing: accept rule success && err < 2*step_size (:131), failure counter incl. the reference's
 // double increment (:142,:183), fallback chaining, `break` when both fallbacks fail (:178-180),
 // point_count only advanced on an accepted NORMAL step (:186), final target append (:189-191).
 // The reference loop has no bound and spins forever on unreachable targets (fallback 1 keeps
@@ -876,10 +876,26 @@ struct MoveArgs {
   unsigned chunk;   // envs a warp reserves per ticket atomic
 };
 
+// The planner's scalar bookkeeping in the two precisions: FP64 follows the reference's operations
+// literally (sqrt, a*b/c, (a/c)*b); FP32 - held to the 1e-4 m tolerance, not to bit parity - uses one
+// MUFU each (x*rsqrt(x), a*b*rcp(c)): the bookkeeping runs on every pass of the flattened loop, and
+// IEEE division / sqrt sequences were a fifth of its instructions.
+__device__ __forceinline__ double norm_fast(double d2) { return sqrt(d2); }
+__device__ __forceinline__ float norm_fast(float d2) { return finish_sqrt(d2); }
+__device__ __forceinline__ double muldiv(double a, double b, double c) { return a * b / c; }
+__device__ __forceinline__ float muldiv(float a, float b, float c) { return a * b * rcp_approx(c); }
+__device__ __forceinline__ double divmul(double a, double c, double b) { return (a / c) * b; }
+__device__ __forceinline__ float divmul(float a, float c, float b) { return a * rcp_approx(c) * b; }
+
 // Persistent warps with lane refill (like ik_solve_kernel): trajectories differ in length (40-200
 // rounds), so a lane whose env is finished writes it back and takes the next env instead of idling
 // until the longest trajectory of its warp ends.  A fresh env enters in state INIT and gets its
 // start position FK(q_start) (move.py:91) from the shared DLS pass of that round - no divergent FK.
+// The planner's loop and the solver's loop are FLATTENED: one DLS pass per trip of the warp loop; a
+// lane whose solve finished post-processes it (accept rule, fallback transitions) and picks the target
+// of its next solve in the same trip.  Lanes therefore never wait for the slowest solve of their warp
+// (a failing fallback solve runs 100 passes, a warm accepted one 2), and a batch that mixes reachable
+// and unreachable goals no longer runs at the pace of its capped envs.
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
@@ -893,11 +909,11 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
   unsigned pool_next = 0, pool_end = 0;
   bool exhausted = false;
   unsigned e = 0;
-  T q[NJ], goal[3] = {T(0), T(0), T(0)}, pos[3] = {T(0), T(0), T(0)};
+  T q[NJ], qs[NJ], goal[3] = {T(0), T(0), T(0)}, pos[3] = {T(0), T(0), T(0)}, tgt[3] = {T(0), T(0), T(0)};
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) q[i] = T(0);
+  for (int i = 0; i < NJ; ++i) q[i] = qs[i] = T(0);
   T* traj = a.traj;
-  int len = 0, solves = 0, st = 0, state = IDLE;
+  int len = 0, solves = 0, st = 0, state = IDLE, it = 0;
   int point_count = 0, cf = 0, outer = 0;
   T astep = T(0);
   auto append = [&](const T* pt) {
@@ -931,7 +947,7 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
         if (idx < a.n) {
           e = idx;
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) q[i] = a.q_start[(size_t)e * NJ + i];
+          for (int i = 0; i < NJ; ++i) q[i] = qs[i] = a.q_start[(size_t)e * NJ + i];
 #pragma unroll
           for (int i = 0; i < 3; ++i) goal[i] = a.target[(size_t)e * 3 + i];
           traj = a.traj + (size_t)e * a.traj_cap * 3;
@@ -946,106 +962,104 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
     }
     if (!__any_sync(FULL, state != IDLE)) break;
 
-    // ---- (i) choose this round's IK target -----------------------------------------------------
-    const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];      // :110
-    const T dist = sqrt_t((dx * dx + dy * dy) + dz * dz);                             // :111 (== :106 norm)
-    T tgt[3] = {pos[0], pos[1], pos[2]};
-    if (state == NORMAL) {
-      if (!(dist > a.pos_thresh && point_count < a.max_traj_points)) {                // :106-107
-        state = DONE;
-      } else if (outer >= a.max_outer) {
-        st |= 2;
-        state = DONE;
-      } else {
-        ++outer;
-        T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                      // :114-117
-        if (cf > 0) stp = stp * T(0.5);                                               // :118-119
-        astep = stp;
-        if (dist > stp) {                                                             // :122-125
-          tgt[0] = pos[0] + dx * stp / dist; tgt[1] = pos[1] + dy * stp / dist; tgt[2] = pos[2] + dz * stp / dist;
-        } else {
-          tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
-        }
-      }
-      if (state == DONE && dist > a.pos_thresh) append(goal);                         // :189-191
-    } else if (state == FB1) {
-      const T smaller = astep * T(0.1);                                               // :149-151
-      tgt[0] = pos[0] + dx * smaller / dist; tgt[1] = pos[1] + dy * smaller / dist; tgt[2] = pos[2] + dz * smaller / dist;
-    } else if (state == FB2) {
-      const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                                // :163-167
-      tgt[0] = pos[0] + (dx / an) * astep; tgt[1] = pos[1] + (T(0) / an) * astep; tgt[2] = pos[2] + (dz / an) * astep;
-    }
+    // ---- one DLS pass for all lanes (ik_solver.py:58-83); INIT lanes only take FK(q_start) from it ----
+    T n2, qn[NJ], pp[3];
+    ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
 
-    // ---- (ii) shared DLS solve from q (ik_solver.py:50-101); INIT lanes only take FK(q) ----------
-    T qs[NJ], p[3] = {T(0), T(0), T(0)}, err = T(0);
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) qs[i] = q[i];
-    int it = 0;
-    bool conv = false, done = (state == DONE || state == IDLE);
-    while (__any_sync(FULL, !done)) {
-      T n2, qn[NJ], pp[3];
-      ik_eval_and_step<T, Kin>(qs, tgt, a.k, trig, pp, n2, qn);
-      if (!done) {
-        const bool last = (it >= a.k.max_iters) || (state == INIT);
-        conv = !last && below_thresh(n2, a.k);
-        if (conv || last) {
-          err = finish_sqrt(n2);
-          p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
-          it = conv ? it + 1 : it;
-          done = true;
-        } else {
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
-          ++it;
-        }
-      }
-    }
-
-    // ---- (iii) post-process by state -------------------------------------------------------------
+    bool choose = false;  // this lane starts a new solve: pick its IK target below
     if (state == INIT) {
-      pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];                                    // :91 start_pos = FK(q_start)
+      pos[0] = pp[0]; pos[1] = pp[1]; pos[2] = pp[2];                                 // :91 start_pos = FK(q_start)
       append(pos);                                                                    // :98
       state = NORMAL;
-    } else if (state != DONE && state != IDLE) {
-      ++solves;
-      c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
-      const bool success = conv && (err < a.k.pos_thresh * T(2));                     // ik_solver.py:92
-      const bool accept = state == NORMAL ? (success && err < a.step_size * T(2)) : success;  // :131/:154/:170
-      if (accept) {
-        append(p);
+      choose = true;
+    } else if (state == NORMAL || state == FB1 || state == FB2) {
+      const bool last = it >= a.k.max_iters;
+      const bool conv = !last && below_thresh(n2, a.k);
+      if (conv || last) {
+        // ---- the solve of this lane finished: post-process by state ------------------------------
+        const T err = finish_sqrt(n2);
+        const int iters = conv ? it + 1 : it;
+        const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];  // :110 (pos of this solve)
+        const T dist = norm_fast((dx * dx + dy * dy) + dz * dz);                      // :111
+        ++solves;
+        c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)iters;
+        const bool success = conv && (err < a.k.pos_thresh * T(2));                   // ik_solver.py:92
+        const bool accept = state == NORMAL ? (success && err < a.step_size * T(2)) : success;  // :131/:154/:170
+        if (accept) {
+          append(pp);
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) q[i] = qs[i];
-        pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
-        cf = 0;
-        if (state == NORMAL) ++point_count;                                           // :186 (fallbacks `continue`)
-        state = NORMAL;
-      } else {
-        bool try_fb2 = false;
-        if (state == NORMAL) {
-          ++cf;                                                                       // :142
-          if (cf >= 3) {                                                              // :144
-            if (dist > astep * T(0.1)) state = FB1; else try_fb2 = true;              // :150
-          } else {
-            ++cf;                                                                     // :183
-          }
-        } else if (state == FB1) {
-          try_fb2 = true;
-        } else {                                                                      // FB2 failed
-          st |= 1;                                                                    // :178-180
-          state = DONE;
-          if (dist > a.pos_thresh) append(goal);                                      // :189-191
-        }
-        if (try_fb2) {
-          const T an = sqrt_t((dx * dx + T(0)) + dz * dz);                            // :165
-          if (an > T(0.001)) {
-            state = FB2;
-          } else {
-            st |= 1;
+          for (int i = 0; i < NJ; ++i) q[i] = qs[i];
+          pos[0] = pp[0]; pos[1] = pp[1]; pos[2] = pp[2];
+          cf = 0;
+          if (state == NORMAL) ++point_count;                                         // :186 (fallbacks `continue`)
+          state = NORMAL;
+        } else {
+          bool try_fb2 = false;
+          if (state == NORMAL) {
+            ++cf;                                                                     // :142
+            if (cf >= 3) {                                                            // :144
+              if (dist > astep * T(0.1)) state = FB1; else try_fb2 = true;            // :150
+            } else {
+              ++cf;                                                                   // :183
+            }
+          } else if (state == FB1) {
+            try_fb2 = true;
+          } else {                                                                    // FB2 failed
+            st |= 1;                                                                  // :178-180
             state = DONE;
-            if (dist > a.pos_thresh) append(goal);
+            if (dist > a.pos_thresh) append(goal);                                    // :189-191
+          }
+          if (try_fb2) {
+            const T an = norm_fast((dx * dx + T(0)) + dz * dz);                       // :165
+            if (an > T(0.001)) {
+              state = FB2;
+            } else {
+              st |= 1;
+              state = DONE;
+              if (dist > a.pos_thresh) append(goal);
+            }
           }
         }
+        choose = state != DONE;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) qs[i] = qn[i];
+        ++it;
       }
+    }
+
+    // ---- choose the IK target of the solve that starts in the next pass ---------------------------
+    if (choose) {
+      const T dx = goal[0] - pos[0], dy = goal[1] - pos[1], dz = goal[2] - pos[2];    // :110
+      const T dist = norm_fast((dx * dx + dy * dy) + dz * dz);                        // :111 (== :106 norm)
+      if (state == NORMAL) {
+        if (!(dist > a.pos_thresh && point_count < a.max_traj_points)) {              // :106-107
+          state = DONE;
+        } else if (outer >= a.max_outer) {
+          st |= 2;
+          state = DONE;
+        } else {
+          ++outer;
+          T stp = fmin(fmin(a.step_size, dist * T(0.1)), T(0.02));                    // :114-117
+          if (cf > 0) stp = stp * T(0.5);                                             // :118-119
+          astep = stp;
+          if (dist > stp) {                                                           // :122-125
+            tgt[0] = pos[0] + muldiv(dx, stp, dist); tgt[1] = pos[1] + muldiv(dy, stp, dist); tgt[2] = pos[2] + muldiv(dz, stp, dist);
+          } else {
+            tgt[0] = goal[0]; tgt[1] = goal[1]; tgt[2] = goal[2];
+          }
+        }
+        if (state == DONE && dist > a.pos_thresh) append(goal);                       // :189-191
+      } else if (state == FB1) {
+        const T smaller = astep * T(0.1);                                             // :149-151
+        tgt[0] = pos[0] + muldiv(dx, smaller, dist); tgt[1] = pos[1] + muldiv(dy, smaller, dist); tgt[2] = pos[2] + muldiv(dz, smaller, dist);
+      } else {  // FB2
+        const T an = norm_fast((dx * dx + T(0)) + dz * dz);                           // :163-167
+        tgt[0] = pos[0] + divmul(dx, an, astep); tgt[1] = pos[1] + divmul(T(0), an, astep); tgt[2] = pos[2] + divmul(dz, an, astep);
+      }
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) qs[i] = q[i];                                      // every solve starts from q_current
+      it = 0;
     }
   }
   if (a.counters) {
