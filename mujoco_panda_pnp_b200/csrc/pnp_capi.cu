@@ -531,21 +531,30 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = small ? 32 : pnp::IK_BLOCK;
+  // specialised tree: the value-type kernels (same arithmetic in both): two envs per lane once the
+  // batch oversubscribes the machine, one per lane below that; other trees: the scalar-template kernel
+  const bool pair = spec && params->kinematics != PNP_KIN_SPEC_LANE &&
+                    (params->kinematics == PNP_KIN_SPEC_PAIR || n >= (long long)s->sm_count * 4096);
+  const int S = pair ? 2 : 1;
   int occ = 4;
   if (!small) {
-    cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::SpecKin>, pnp::IK_BLOCK, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::GenericKin>, pnp::IK_BLOCK, 0);
+    cudaError_t e = !spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::GenericKin>, pnp::IK_BLOCK, 0)
+                    : pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<pnp::F2>, pnp::IK_BLOCK, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<float>, pnp::IK_BLOCK, 0);
     if (e != cudaSuccess || occ < 1) occ = 4;
   }
-  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
-  // envs reserved per ticket atomic: ~1/8 of a warp's share within [32, 128] (keeps the tail short)
+  const long long lanes_needed = (n + S - 1) / S;
+  const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occ);
+  // envs reserved per ticket atomic: ~1/8 of a warp's share within [32 S, 128] (keeps the tail short)
   long long chunk = n / ((long long)grid * (block / 32) * 8);
-  chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk);
+  chunk = chunk < 32 * S ? 32 * S : (chunk > 128 ? 128 : chunk);
   a.chunk = (unsigned)(chunk & ~31ll);
-  if (spec)
-    pnp::ik_waypoints_kernel<float, pnp::SpecKin><<<grid, block, 0, st>>>(a);
-  else
+  if (!spec)
     pnp::ik_waypoints_kernel<float, pnp::GenericKin><<<grid, block, 0, st>>>(a);
+  else if (pair)
+    pnp::ik_waypoints_v_kernel<pnp::F2><<<grid, block, 0, st>>>(a);
+  else
+    pnp::ik_waypoints_v_kernel<float><<<grid, block, 0, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;

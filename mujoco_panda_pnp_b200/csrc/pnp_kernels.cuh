@@ -667,6 +667,191 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same waypoint state machine over the value types of pnp_vec.cuh (specialised tree, FP32):
+// V = F2 runs TWO envs per lane with all DLS arithmetic on packed FFMA2/FMUL2/FADD2 (the scalar kernel
+// above is issue bound at ~500 instructions per pass, 55 % of them FP32 math); V = float is the
+// one-env-per-lane instantiation of the same code, bit-identical to the pair kernel.
+// A slot whose solve finishes in a pass is frozen for that pass (step limit 0), does its accept /
+// advance bookkeeping after the shared step, and starts its next solve in the following pass.  The
+// accepted joint vector of each slot lives in shared memory (written on accept, read on a rejected
+// solve and at write-back), which keeps the kernel at 4 blocks per SM.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_waypoints_v_kernel(const WaypointArgs<float> a) {
+  constexpr int S = Slots<V>::kN;
+  const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) float s_sin[kTrigTabN];
+  __shared__ __align__(16) float s_cos[kTrigTabN];
+  __shared__ float s_qa[S * NJ * IK_BLOCK];  // accepted q of every slot: [(k * NJ + i) * IK_BLOCK + thread]
+  load_trig_table_split(s_sin, s_cos);
+  __syncthreads();
+  const TrigV trig{s_sin, s_cos};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
+  float* const qa = s_qa + threadIdx.x;
+  enum { IDLE = 0, INIT = 1, RUN = 2 };
+
+  V qs[NJ], tgt[3], pos[3], goal[3], slim(0.0f);
+  int state[S], step[S], it[S], accepted[S], iters_sum[S], fails[S];
+  unsigned env[S];
+  bool exhausted = false;
+  unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
+  unsigned pool_next = 0, pool_end = 0;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) qs[i] = V(0.0f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tgt[i] = pos[i] = goal[i] = V(0.0f);
+#pragma unroll
+  for (int k = 0; k < S; ++k) { state[k] = IDLE; step[k] = it[k] = accepted[k] = iters_sum[k] = fails[k] = 0; env[k] = 0; }
+
+  while (true) {
+    // ---- refill idle slots (slot-major ranks) ------------------------------------------------------
+    unsigned need[S], count = 0;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      need[k] = __ballot_sync(FULL, state[k] == IDLE && !exhausted);
+      count += (unsigned)__popc(need[k]);
+    }
+    if (count) {
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
+      }
+      unsigned before = 0;
+      bool ran_out = false;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        if (state[k] == IDLE && !exhausted) {
+          const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
+          const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
+          if (id < a.n) {
+            env[k] = id;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+              const float v = a.q_start[(size_t)id * NJ + i];
+              Slots<V>::set(qs[i], k, v);
+              qa[(k * NJ + i) * IK_BLOCK] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.goal[(size_t)id * 3 + i]);
+            step[k] = 0; accepted[k] = 0; iters_sum[k] = 0; fails[k] = 0; it[k] = 0;
+            state[k] = INIT;
+          } else {
+            ran_out = true;
+          }
+        }
+        before += (unsigned)__popc(need[k]);
+      }
+      exhausted = exhausted || ran_out;
+      if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
+      else pool_next += count;
+    }
+    bool any_live = false;
+#pragma unroll
+    for (int k = 0; k < S; ++k) any_live = any_live || state[k] != IDLE;
+    if (!__any_sync(FULL, any_live)) break;
+
+    // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
+    V p[3], n2, ev[3], J[21];
+    ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
+    bool fin[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const bool running = state[k] == RUN;
+      fin[k] = running && (it[k] >= a.k.max_iters || Slots<V>::get(n2, k) < thresh2);
+      Slots<V>::set(slim, k, (running && !fin[k]) ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
+    }
+    ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+
+    // ---- bookkeeping, branch-free: with ~2 passes per warm solve half of the slots finish a solve in
+    //      every pass, so this runs as predicated straight-line code; the waypoint geometry of both
+    //      slots (move.py:110-125) is packed arithmetic ---------------------------------------------------
+    bool adv[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const bool init = state[k] == INIT;
+      const bool f = fin[k];
+      const bool conv = it[k] < a.k.max_iters;
+      const float err = finish_sqrt(Slots<V>::get(n2, k));
+      const int iters = it[k] + (conv ? 1 : 0);
+      const bool success = conv && (err < a.k.pos_thresh * 2.0f);
+      const bool accept = f && success && (err < a.step_size * 2.0f);                // :131-138
+      iters_sum[k] += f ? iters : 0;
+      c_n += f ? 1u : 0u; c_conv += (f && conv) ? 1u : 0u; c_iter += f ? (unsigned)iters : 0u;
+      const bool keep = accept && it[k] > 0;  // qs becomes q_current
+      if (keep) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) qa[(k * NJ + i) * IK_BLOCK] = Slots<V>::get(qs[i], k);
+      }
+      // rejected solve: the next one restarts from q_current; INIT pass / solve accepted on its first
+      // pass: q_current itself, reloaded because the frozen limit clip may have moved an out-of-limits q_start
+      if (init || (f && !keep)) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
+      }
+      if (init || accept) {                                                          // :91 start_pos / :136
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Slots<V>::set(pos[i], k, Slots<V>::get(p[i], k));
+      }
+      accepted[k] += accept ? 1 : 0;
+      fails[k] = accept ? 0 : fails[k] + (f ? 1 : 0);                                // :142
+      step[k] += f ? 1 : 0;
+      adv[k] = init || f;
+      it[k] = adv[k] ? 0 : it[k] + 1;
+      state[k] = init ? RUN : state[k];
+    }
+    {
+      const V dx = v_sub(goal[0], pos[0]), dy = v_sub(goal[1], pos[1]), dz = v_sub(goal[2], pos[2]);   // :110
+      const V d2 = pnp_fma(dz, dz, pnp_fma(dy, dy, pnp_mul(dx, dx)));
+      V dist, stp, inv;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float dk = finish_sqrt(Slots<V>::get(d2, k));                          // :111
+        float sk = fminf(fminf(a.step_size, dk * 0.1f), 0.02f);                      // :114-117
+        sk = fails[k] > 0 ? sk * 0.5f : sk;                                          // :118-119
+        Slots<V>::set(dist, k, dk);
+        Slots<V>::set(stp, k, sk);
+        Slots<V>::set(inv, k, rcp_approx(dk));
+      }
+      const V fr = pnp_mul(stp, inv);
+      const V nx = pnp_fma(dx, fr, pos[0]), ny = pnp_fma(dy, fr, pos[1]), nz = pnp_fma(dz, fr, pos[2]);  // :122-125
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float dk = Slots<V>::get(dist, k);
+        const bool far = dk > Slots<V>::get(stp, k);
+        const bool moving = step[k] < a.n_steps && dk > a.reach_thresh;              // :106
+        if (adv[k]) {
+          Slots<V>::set(tgt[0], k, far ? Slots<V>::get(nx, k) : Slots<V>::get(goal[0], k));
+          Slots<V>::set(tgt[1], k, far ? Slots<V>::get(ny, k) : Slots<V>::get(goal[1], k));
+          Slots<V>::set(tgt[2], k, far ? Slots<V>::get(nz, k) : Slots<V>::get(goal[2], k));
+        }
+        if (adv[k] && !moving) {  // nothing left to do for this env: write it back (once per env)
+          const unsigned id = env[k];
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) a.q_out[(size_t)id * NJ + i] = qa[(k * NJ + i) * IK_BLOCK];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) a.pos_out[(size_t)id * 3 + i] = Slots<V>::get(pos[i], k);
+          if (a.n_accepted) a.n_accepted[id] = accepted[k];
+          if (a.iters_total) a.iters_total[id] = iters_sum[k];
+          state[k] = IDLE;
+        }
+      }
+    }
+  }
+  if (a.counters) {
+    c_n = warp_sum(c_n); c_conv = warp_sum(c_conv); c_iter = warp_sum(c_iter);
+    if (lane == 0) {
+      atomicAdd(a.counters + PNP_IK_CNT_N, c_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, c_iter);
+    }
+  }
+}
+
 // =============================================================================================
 // Pose-mode IK (an EXTENSION: the reference's FrankaEnv.solve_ik(target_pos,
 // target_quat, q_init) at envs/panda_env.py:399-409 imports a function that does not exist, so

@@ -305,3 +305,32 @@ def test_waypoint_sequences_vs_oracle(tree, oracle_model, oracle_chain):
         assert int(out["n_accepted"][e]) == accepted
         np.testing.assert_allclose(out["pos"][e].cpu().numpy(), pos, atol=5e-5)
         np.testing.assert_allclose(out["q"][e].cpu().numpy(), q, atol=2e-3)
+
+
+def test_waypoint_pair_kernel_is_bit_identical_to_lane_kernel(tree, oracle_chain):
+    """ik_waypoints_v_kernel<F2> (two envs per lane, packed FP32) vs <float> (one env per lane): same
+    operations per env, so every output is bit-identical; both agree with the scalar-template kernel
+    (generic kinematics) within the FP32 tolerance."""
+    for n, steps in ((1, 50), (63, 50), (65, 7), (5000, 50), (200_001, 20)):
+        w = synthetic.waypoint_envs(n, seed=n % 13, device="cuda")
+        outs = {}
+        for kin in ("spec_lane", "spec_pair", "generic"):
+            cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+            outs[kin] = (engine.ik_waypoints(w["q_start"], w["goal"], steps, engine.ik_params(kinematics=kin), counters=cnt), cnt)
+        (a, ca), (b, cb), (g, cg) = outs["spec_lane"], outs["spec_pair"], outs["generic"]
+        for f in ("q", "pos", "n_accepted", "iters_total"):
+            assert torch.equal(a[f], b[f]), (n, f)
+        assert torch.equal(ca, cb)
+        same = a["n_accepted"] == g["n_accepted"]
+        assert float(same.float().mean()) > 0.999
+        diff = (a["pos"][same] - g["pos"][same]).abs().amax(dim=1)
+        # the two kernels round differently; a waypoint solve is only converged to pos_thresh = 1e-3, so
+        # a rare iteration-count flip moves an end point by up to that much
+        assert float((diff < 5e-5).float().mean()) > 0.99 and float(diff.max()) < 2.5e-3
+    # an env whose q_start violates a joint limit and already sits at its goal: returned untouched
+    q0 = torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda").repeat(64, 1)
+    q0[:, 0] = 3.2
+    goal = engine.fk_jac(q0, want_quat=False, want_jac=False)[0]
+    for kin in ("spec_lane", "spec_pair"):
+        r = engine.ik_waypoints(q0, goal, 10, engine.ik_params(kinematics=kin))
+        assert torch.equal(r["q"], q0) and int(r["n_accepted"].sum()) == 0
