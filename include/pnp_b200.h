@@ -286,6 +286,15 @@ int pnp_ik_solve_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_
 int pnp_ik_solve_packed_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_init,
                                  int32_t q_init_stride, int64_t n, const PnpIkParams* params,
                                  float* out_q8, float* out_aux4, unsigned long long* counters);
+/* ONE query, host in / host out, lowest latency - what JacobianIKController.solve(target_pos, q_init)
+ * (ik_solver.py:35) costs when it is called one pose at a time (test/ik_test.py, MoveIKSkill in a BT).
+ * No cudaMemcpy: the kernel reads target3 / q_init7 from, and writes the result to, a pinned host
+ * mailbox mapped into the device address space; one launch + one stream synchronisation.
+ * out12 = q0..q6, pos_error | final_pos xyz, word (iterations | flags << 24): the two packed records of
+ * pnp_ik_solve_packed_f32.  FP32; same arithmetic as the batch kernels (bit-identical results on the
+ * specialised tree).  Not thread-safe per ctx (one mailbox). */
+int pnp_ik_solve_one_host_f32(PnpHostCtx* ctx, const float* target3, const float* q_init7,
+                              const PnpIkParams* params, float* out12);
 int pnp_reward_host_f32(PnpHostCtx* ctx, const float* ag, const float* dg, const float* ee_pos,
                         const float* ee_quat, const float* width, const int32_t* task_index,
                         int64_t n, const PnpRewardParams* params, float* reward, float* is_success,

@@ -100,6 +100,7 @@ SIGNATURES = {
     "pnp_her_relabel_table_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams),
                                           POINTER(PnpNormalizeParams), _P, _P, _P, _P, _P, _P]),
     "pnp_goal_distance_f64": (c_int, [_P, _P, c_int64, _P, _P]),
+    "pnp_ik_solve_one_host_f32": (c_int, [c_void_p, _P, _P, POINTER(PnpIkParams), _P]),
     "pnp_host_ctx_create": (c_int, [POINTER(c_void_p), c_int64]),
     "pnp_host_ctx_destroy": (c_int, [c_void_p]),
     "pnp_ik_solve_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),

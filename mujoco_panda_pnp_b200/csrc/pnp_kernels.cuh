@@ -510,6 +510,88 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One query, lowest latency (JacobianIKController.solve called from Python, one pose at a time:
+// test/ik_test.py, MoveIKSkill stepping through a BT).  `in` and `out` point into a pinned host mailbox
+// mapped into the device address space: the kernel reads target + q_init over PCIe and writes the two
+// packed result records straight back, so a solve costs one kernel launch and one stream
+// synchronisation - no cudaMemcpy, no ticket memset.  Same arithmetic as the batch kernels
+// (kSpec: ik_eval_v / ik_step_v, bit-identical to ik_solve_v_kernel; else the generic-tree template).
+//   in [10] = target xyz, q_init[7];   out[12] = q0..q6, pos_error | final_pos xyz, iterations|flags<<24
+// ---------------------------------------------------------------------------------------------
+template <bool kSpec>
+__global__ void __launch_bounds__(IK_BLOCK) ik_solve_one_kernel(const float* __restrict__ in, const IkConst<float> k,
+                                                                float* __restrict__ out) {
+  __shared__ __align__(16) float s_sin[kTrigTabN];
+  __shared__ __align__(16) float s_cos[kTrigTabN];
+  __shared__ float s_in[10];
+  load_trig_table_split(s_sin, s_cos);
+  if (threadIdx.x < 10) s_in[threadIdx.x] = in[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float q[NJ], tgt[3] = {s_in[0], s_in[1], s_in[2]}, p[3], n2;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) q[i] = s_in[3 + i];
+  const float thresh2 = k.pos_thresh * k.pos_thresh;
+  int it = 0;
+  bool conv = false;
+  while (true) {
+    const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
+    if (kSpec) {
+      const TrigV trig{s_sin, s_cos};
+      float e[3], J[21];
+      ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
+      conv = !last && n2 < thresh2;                            // :61-64
+      if (conv || last) break;
+      ik_step_v<float>(q, J, e, k.damping, k.step_limit);
+    } else {
+      // generic tree: Trig<float> wants the interleaved table; s_sin/s_cos hold the same entries
+      float s[NJ], c[NJ], J[21], A[6];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const TrigV trig{s_sin, s_cos};
+        trig(q[i] - GenericKin::template qref<float>(i), &s[i], &c[i]);
+      }
+      GenericKin::template fk_jacp<float>(s, c, p, J);
+      const float e0 = tgt[0] - p[0], e1 = tgt[1] - p[1], e2 = tgt[2] - p[2];
+      n2 = (e0 * e0 + e1 * e1) + e2 * e2;
+      conv = !last && n2 < thresh2;
+      if (conv || last) break;
+      GenericKin::template jjt<float>(J, A);
+      const float a00 = A[0] + k.damping, a11 = A[3] + k.damping, a22 = A[5] + k.damping;
+      const float i0 = rcp_t(a00);
+      const float l10 = A[1] * i0, l20 = A[2] * i0;
+      const float d1 = a11 - l10 * A[1];
+      const float u12 = A[4] - l10 * A[2];
+      const float i1 = rcp_t(d1);
+      const float l21 = u12 * i1;
+      const float d2 = a22 - l20 * A[2] - l21 * u12;
+      const float i2 = rcp_t(d2);
+      const float z1 = e1 - l10 * e0;
+      const float z2 = e2 - l20 * e0 - l21 * z1;
+      float y[3], dq[NJ];
+      y[2] = z2 * i2;
+      y[1] = z1 * i1 - l21 * y[2];
+      y[0] = e0 * i0 - l10 * y[1] - l20 * y[2];
+      GenericKin::template jty<float>(J, y, dq);
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const float d = clamp_t(dq[i], -k.step_limit, k.step_limit);                                   // :80
+        q[i] = clamp_t(q[i] + d, GenericKin::template lower<float>(i), GenericKin::template upper<float>(i));  // :81
+      }
+    }
+    ++it;
+  }
+  const float err = finish_sqrt(n2);
+  const int iterations = conv ? it + 1 : it;                   // :66 / :85
+  const bool success = conv && (err < k.pos_thresh * 2.0f);    // :88-92
+  const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+  float4* o = reinterpret_cast<float4*>(out);
+  o[0] = make_float4(q[0], q[1], q[2], q[3]);
+  o[1] = make_float4(q[4], q[5], q[6], err);
+  o[2] = make_float4(p[0], p[1], p[2], __int_as_float((int)((unsigned)iterations | (fl << 24))));
+}
+
 // =============================================================================================
 // Warm-started waypoint sequences (MoveIKSkill.reset inner loop, skills/move.py:106-137):
 // one lane per env, q carried in registers across the n_steps solves.

@@ -19,6 +19,8 @@ from ._lib import KINEMATICS, PnpIkParams, PnpMoveParams, PnpNormalizeParams, Pn
 from .tree import KinematicTree, PnpTreeStruct
 
 _uploaded: Dict[int, bytes] = {}  # device index -> bytes of the PnpTree currently in constant memory
+_uploaded_obj: Dict[int, tuple] = {}  # device index -> (the KinematicTree object last uploaded, specialised?); trees are
+#                                       treated as immutable once uploaded
 _host_ctx: Dict[Tuple[int, int], ctypes.c_void_p] = {}
 
 
@@ -39,15 +41,21 @@ def set_tree(tree: KinematicTree) -> bool:
     """Upload ``tree`` to the current device's constant memory (no-op if already there).
 
     Returns True when the library will use its build-time specialised kinematics for it."""
+    dev = torch.cuda.current_device() if _uploaded_obj else -1
+    hit = _uploaded_obj.get(dev)
+    if hit is not None and hit[0] is tree:  # same object as last time on this device: nothing to do
+        return hit[1]
     _require_cuda()
-    lib = _lib.load()
     dev = torch.cuda.current_device()
+    lib = _lib.load()
     s = tree.to_struct()
     blob = bytes(s)
     if _uploaded.get(dev) != blob:
         _lib.check(lib.pnp_set_tree(ctypes.byref(s)), "pnp_set_tree")
         _uploaded[dev] = blob
-    return bool(lib.pnp_tree_is_specialized())
+    spec = bool(lib.pnp_tree_is_specialized())
+    _uploaded_obj[dev] = (tree, spec)
+    return spec
 
 
 def specialized_tree() -> KinematicTree:
@@ -541,6 +549,18 @@ def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out
     )
     return dict(q=q, final_pos=fpos, pos_error=err, iterations=iters, flags=flags,
                 converged=(flags & 1).astype(bool), success=(flags & 2).astype(bool), counters=counters)
+
+
+def ik_solve_one_host(target3: np.ndarray, q_init7: np.ndarray, params: PnpIkParams, out12: Optional[np.ndarray] = None):
+    """One query through the mapped-mailbox path (pnp_ik_solve_one_host_f32): float32 arrays in, the 12
+    result words out (q0..q6, pos_error, final_pos xyz, iterations | flags << 24)."""
+    lib = _lib.load()
+    out = out12 if out12 is not None else np.empty(12, np.float32)
+    rc = lib.pnp_ik_solve_one_host_f32(host_ctx(0), target3.ctypes.data, q_init7.ctypes.data, ctypes.byref(params),
+                                       out.ctypes.data)
+    if rc:
+        _lib.check(rc, "pnp_ik_solve_one_host")
+    return out
 
 
 def reward_host(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, want_success=True,

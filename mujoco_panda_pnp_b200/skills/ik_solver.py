@@ -63,6 +63,12 @@ class JacobianIKController:
         self.tree = KinematicTree.from_mjmodel(model, site_name)
         with torch.cuda.device(self.device):
             self.specialized = engine.set_tree(self.tree)
+        # single-query fast path: preallocated staging arrays and cached parameter structs
+        self._param_cache = {}
+        self._one_in_t = np.empty(3, np.float32)
+        self._one_in_q = np.empty(7, np.float32)
+        self._one_out = np.empty(12, np.float32)
+        self._one_word = self._one_out[11:12].view(np.int32)
 
     # ------------------------------------------------------------------------------------
     def _dtype(self):
@@ -81,16 +87,27 @@ class JacobianIKController:
         if target_pos.shape != (3,) or q_init.shape != (7,):
             raise ValueError("solve expects target_pos (3,) and q_init (7,)")
         if self.precision == "fp32":
-            # one C call: H2D of 10 floats, one kernel, D2H of the two packed records
-            with torch.cuda.device(self.device):
+            # one C call, no memcpy: the kernel reads the query from and writes the result to a mapped
+            # pinned mailbox (pnp_ik_solve_one_host_f32)
+            key = (max_iters, pos_thresh, damping, step_limit)
+            params = self._param_cache.get(key)
+            if params is None:
+                params = self._param_cache[key] = self._params(max_iters, pos_thresh, damping, step_limit)
+            t32, q32, o = self._one_in_t, self._one_in_q, self._one_out
+            t32[:] = target_pos
+            q32[:] = q_init
+            if torch.cuda.current_device() == self.device.index:
                 engine.set_tree(self.tree)
-                h = engine.ik_solve_host(target_pos[None].astype(np.float32), q_init.astype(np.float32),
-                                         self._params(max_iters, pos_thresh, damping, step_limit))
-            word = int(h["aux4"][0, 3:4].view(np.int32)[0])
-            q = h["q"][0].astype(np.float64)
-            final_pos = h["final_pos"][0].astype(np.float64)
+                engine.ik_solve_one_host(t32, q32, params, o)
+            else:
+                with torch.cuda.device(self.device):
+                    engine.set_tree(self.tree)
+                    engine.ik_solve_one_host(t32, q32, params, o)
+            word = int(self._one_word[0])
+            q = o[0:7].astype(np.float64)
+            final_pos = o[8:11].astype(np.float64)
             self._write_back(q, final_pos)
-            return IKResult(success=bool(word & (2 << 24)), q=q, final_pos=final_pos, pos_error=float(h["pos_error"][0]),
+            return IKResult(success=bool(word & (2 << 24)), q=q, final_pos=final_pos, pos_error=float(o[7]),
                             iterations=word & 0xFFFFFF, converged=bool(word & (1 << 24)))
         r = self.solve_batch(target_pos[None], q_init[None], max_iters, pos_thresh, damping, step_limit)
         q = r.q[0].double().cpu().numpy()
@@ -144,16 +161,27 @@ class JacobianIKController:
         if d is None:
             return
         d.qpos[:7] = q  # ik_solver.py:82
-        try:
-            import mujoco  # real MjData: keep the simulator consistent (ik_solver.py:83)
-
-            if isinstance(d, mujoco.MjData):
-                mujoco.mj_forward(self.model, d)
-                return
-        except ImportError:
-            pass
+        mj = _mujoco_module()
+        if mj is not None and isinstance(d, mj.MjData):  # real MjData: keep the simulator consistent (ik_solver.py:83)
+            mj.mj_forward(self.model, d)
+            return
         if hasattr(d, "site_xpos"):
             d.site_xpos[self.site_id] = final_pos
+
+
+_MUJOCO = [False, None]  # [looked up?, module or None]: a failing import on every solve() cost ~25 us
+
+
+def _mujoco_module():
+    if not _MUJOCO[0]:
+        try:
+            import mujoco
+
+            _MUJOCO[1] = mujoco
+        except ImportError:
+            _MUJOCO[1] = None
+        _MUJOCO[0] = True
+    return _MUJOCO[1]
 
 
 IKSolver = JacobianIKController  # north_star calls the class IKSolver

@@ -334,3 +334,24 @@ def test_waypoint_pair_kernel_is_bit_identical_to_lane_kernel(tree, oracle_chain
     for kin in ("spec_lane", "spec_pair"):
         r = engine.ik_waypoints(q0, goal, 10, engine.ik_params(kinematics=kin))
         assert torch.equal(r["q"], q0) and int(r["n_accepted"].sum()) == 0
+
+
+def test_single_query_mailbox_path_equals_batch_kernel(kin_model, golden_ik, tree):
+    """JacobianIKController.solve goes through pnp_ik_solve_one_host_f32 (mapped pinned mailbox, one
+    launch, no memcpy); it runs the arithmetic of the batch kernels, so a batch of one gives the same bits."""
+    g = golden_ik
+    ctl = JacobianIKController(kin_model, KinematicData(kin_model))
+    for k in range(0, len(g["tag"]), 3):
+        kw = _kw(g, k)
+        r = ctl.solve(g["target"][k], g["q_init"][k], **kw)
+        b = engine.ik_solve(torch.tensor(g["target"][k][None], dtype=torch.float32, device="cuda"),
+                            torch.tensor(g["q_init"][k], dtype=torch.float32, device="cuda"),
+                            engine.ik_params(kinematics="spec_lane", **kw))
+        assert r.iterations == int(b.iterations[0]) and r.converged == bool(b.converged[0]) and r.success == bool(b.success[0])
+        np.testing.assert_array_equal(r.q.astype(np.float32), b.q[0].cpu().numpy())
+        np.testing.assert_array_equal(r.final_pos.astype(np.float32), b.final_pos[0].cpu().numpy())
+        assert np.float32(r.pos_error) == b.pos_error[0].cpu().numpy()
+    # generic tree path of the same entry point
+    ctl_g = JacobianIKController(kin_model, KinematicData(kin_model), kinematics="generic")
+    r = ctl_g.solve(np.array([1.415, 0.0, 0.73]), NEUTRAL)
+    assert r.success and r.iterations == 7 and np.linalg.norm(r.final_pos - [1.415, 0.0, 0.73]) < 1e-3
