@@ -355,3 +355,34 @@ def test_single_query_mailbox_path_equals_batch_kernel(kin_model, golden_ik, tre
     ctl_g = JacobianIKController(kin_model, KinematicData(kin_model), kinematics="generic")
     r = ctl_g.solve(np.array([1.415, 0.0, 0.73]), NEUTRAL)
     assert r.success and r.iterations == 7 and np.linalg.norm(r.final_pos - [1.415, 0.0, 0.73]) < 1e-3
+
+
+def test_cfg5_full_size_batch_properties(tree):
+    """BASELINE cfg5 at the bench size (2^24 cold targets, one launch): size-independent properties.
+    The pair and lane kernels must agree bit for bit on all 16.7 M queries, the counters must equal the
+    per-query outputs, every converged query must satisfy the threshold under the FK kernel, and the
+    result must not depend on how the dynamic slot refill interleaved the queries (two runs equal)."""
+    n = 1 << 24
+    targets = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    for off in range(0, n, 1 << 22):
+        q = synthetic.random_joint_configs(1 << 22, tree.lower, tree.upper, seed=77 + off, device="cuda")
+        targets[off:off + (1 << 22)] = engine.fk_jac(q, want_quat=False, want_jac=False)[0]
+        del q
+    neutral = torch.tensor(NEUTRAL, dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    a = engine.ik_solve(targets, neutral, engine.ik_params(kinematics="spec_pair"), counters=cnt)
+    c = cnt.cpu().numpy()
+    assert c[0] == n and c[1] == int(a.converged.sum()) and c[2] == c[1] and c[3] == int(a.iterations.long().sum())
+    assert 0.997 < c[1] / n < 0.999 and 15.7 < c[3] / n < 16.0   # SURVEY 8d workload statistics
+    b = engine.ik_solve(targets, neutral, engine.ik_params(kinematics="spec_lane"))
+    for f in ("q", "final_pos", "pos_error", "iterations", "converged"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    del b
+    a2 = engine.ik_solve(targets, neutral, engine.ik_params(kinematics="spec_pair"))
+    assert torch.equal(a.q, a2.q) and torch.equal(a.iterations, a2.iterations)
+    del a2
+    fk = engine.fk_jac(a.q, want_quat=False, want_jac=False)[0]
+    assert float((fk - a.final_pos).abs().max()) < 2e-6
+    err = (fk - targets).norm(dim=1)
+    assert float(err[a.converged].max()) < 1e-3 + 2e-6
+    assert bool((a.iterations[~a.converged] == 100).all())
