@@ -579,16 +579,32 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
   bool spec;
   if ((rc = pick_kin(s, params->kinematics, &spec))) return rc;
   if (n == 0) return PNP_OK;
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_pose_solve: n must be < 2^31 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ticket;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
+  }
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::PoseIkArgs<T> a;
-  a.target_pos = tpos; a.target_quat = tquat; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = n;
+  a.target_pos = tpos; a.target_quat = tquat; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
   a.k = make_ik_const<T>(params);
   a.rot_thresh = (T)rot_thresh; a.rot_weight = (T)rot_weight;
   a.q_out = q_out; a.final_pos = final_pos; a.final_quat = final_quat; a.pos_err = pos_err; a.rot_err = rot_err;
-  a.iters = iters; a.flags = flags; a.counters = counters;
+  a.iters = iters; a.flags = flags; a.counters = counters; a.ticket = ticket;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = small ? 32 : pnp::IK_BLOCK;
-  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, 64);
-  cudaStream_t st = (cudaStream_t)stream;
+  int occ = 4;
+  if (!small) {
+    cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_pose_solve_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_pose_solve_kernel<T, pnp::GenericKin>, pnp::IK_BLOCK, 0);
+    if (e != cudaSuccess || occ < 1) occ = 4;
+  }
+  const int grid = small ? (int)((n + 31) / 32) : grid_for(n, block, s->sm_count, occ);
+  long long chunk = n / ((long long)grid * (block / 32) * 16);
+  chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : chunk);
+  a.chunk = (unsigned)(chunk & ~31ll);
   if (spec)
     pnp::ik_pose_solve_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
   else

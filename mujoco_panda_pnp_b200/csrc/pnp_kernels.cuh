@@ -949,7 +949,7 @@ struct PoseIkArgs {
   const T* target_quat;
   const T* q_init;
   int q_init_stride;
-  long long n;
+  unsigned n;       // < 2^31 (checked on the host)
   IkConst<T> k;
   T rot_thresh, rot_weight;
   T* q_out;
@@ -960,6 +960,8 @@ struct PoseIkArgs {
   int32_t* iters;
   uint8_t* flags;
   unsigned long long* counters;
+  unsigned* ticket; // zeroed before launch
+  unsigned chunk;   // queries a warp reserves per ticket atomic
 };
 
 // mju_quat2Vel(res, quat, 1): rotation vector of a unit quaternion, angle folded into (-pi, pi]
@@ -1003,100 +1005,123 @@ __device__ __forceinline__ void ldlt_solve(T (&A)[N][N], T (&b)[N]) {
     for (int k = i + 1; k < N; ++k) b[i] -= A[k][i] * b[k];
 }
 
+// Persistent warps with lane refill, like ik_solve_kernel: pose solves take 4-30 passes, and a grid of
+// one-shot lanes ran every warp at the pace of its slowest query (25.9 of 32 lanes active per
+// instruction, twice the mean pass count).  The FP32 instantiation uses the table trig.
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
+  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __syncthreads();
+  const Trig<T> trig{s_tab};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
   unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
-  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < a.n;
-       base += (long long)gridDim.x * blockDim.x) {
-    const long long e = base + lane;
-    const bool valid = e < a.n;
-    T q[NJ], tp[3], tq[4];
-    const T* qi = a.q_init + (valid ? (long long)a.q_init_stride * e : 0);
+  unsigned pool_next = 0, pool_end = 0;
+  bool exhausted = false, active = false;
+  unsigned e = 0;
+  int it = 0;
+  T q[NJ], tp[3] = {T(0), T(0), T(0)}, tq[4] = {T(1), T(0), T(0), T(0)};
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+  for (int i = 0; i < NJ; ++i) q[i] = T(0);
+
+  while (true) {
+    // ---- refill idle lanes -------------------------------------------------------------------
+    const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+    if (need) {
+      const unsigned count = (unsigned)__popc(need);
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
+      }
+      if (!active && !exhausted) {
+        const unsigned rank = (unsigned)__popc(need & lanemask_lt);
+        const unsigned idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
+        if (idx < a.n) {
+          e = idx;
+          const T* qi = a.q_init + (size_t)a.q_init_stride * e;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) tp[i] = valid ? a.target_pos[e * 3 + i] : T(0);
+          for (int i = 0; i < NJ; ++i) q[i] = qi[i];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tq[i] = valid ? a.target_quat[e * 4 + i] : (i == 0 ? T(1) : T(0));
-    {
-      const T nq = sqrt_t(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+          for (int i = 0; i < 3; ++i) tp[i] = a.target_pos[(size_t)e * 3 + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tq[i] = tq[i] / nq;
-    }
-    int it = 0;
-    bool done = !valid, conv = false;
-    T p[3] = {T(0), T(0), T(0)}, qc[4] = {T(1), T(0), T(0), T(0)}, perr = T(0), rerr = T(0);
-    while (__any_sync(FULL, !done)) {
-      T s[NJ], c[NJ];
+          for (int i = 0; i < 4; ++i) tq[i] = a.target_quat[(size_t)e * 4 + i];
+          const T nq = sqrt_t(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) sincos_t(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
-      T pp[3], J[42], R[9], qcur[4];
-      Kin::template fk_full<T>(s, c, pp, J, R);
-      mat2quat<T>(R, qcur);
-      // err_quat = target (x) conj(current); rotation vector in the world frame
-      const T eq[4] = {tq[0] * qcur[0] + tq[1] * qcur[1] + tq[2] * qcur[2] + tq[3] * qcur[3],
-                       -tq[0] * qcur[1] + tq[1] * qcur[0] - tq[2] * qcur[3] + tq[3] * qcur[2],
-                       -tq[0] * qcur[2] + tq[1] * qcur[3] + tq[2] * qcur[0] - tq[3] * qcur[1],
-                       -tq[0] * qcur[3] - tq[1] * qcur[2] + tq[2] * qcur[1] + tq[3] * qcur[0]};
-      T rv[3];
-      quat2vel<T>(eq, rv);
-      T err[6] = {tp[0] - pp[0], tp[1] - pp[1], tp[2] - pp[2], rv[0] * a.rot_weight, rv[1] * a.rot_weight,
-                  rv[2] * a.rot_weight};
-      const T pe = sqrt_t((err[0] * err[0] + err[1] * err[1]) + err[2] * err[2]);
-      const T re = sqrt_t((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
-      if (!done) {
-        const bool last = it >= a.k.max_iters;
-        conv = !last && (pe < a.k.pos_thresh) && (re < a.rot_thresh);
-        if (conv || last) {
-          p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) qc[i] = qcur[i];
-          perr = pe; rerr = re;
-          it = conv ? it + 1 : it;
-          done = true;
+          for (int i = 0; i < 4; ++i) tq[i] = tq[i] / nq;
+          it = 0;
+          active = true;
+        } else {
+          exhausted = true;
         }
       }
-      if (!done) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) { J[21 + j] *= a.rot_weight; J[28 + j] *= a.rot_weight; J[35 + j] *= a.rot_weight; }
-        T A[6][6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int c2 = 0; c2 <= r; ++c2) {
-            T acc = T(0);
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * J[c2 * 7 + j];
-            A[r][c2] = acc + (r == c2 ? a.k.damping : T(0));
-          }
-        ldlt_solve<T, 6>(A, err);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          T dq = T(0);
-#pragma unroll
-          for (int r = 0; r < 6; ++r) dq = dq + J[r * 7 + j] * err[r];
-          dq = clamp_t(dq, -a.k.step_limit, a.k.step_limit);
-          q[j] = clamp_t(q[j] + dq, Kin::template lower<T>(j), Kin::template upper<T>(j));
-        }
-        ++it;
-      }
+      if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
+      else pool_next += count;
     }
-    if (valid) {
-      const bool success = conv && (perr < a.k.pos_thresh * T(2)) && (rerr < a.rot_thresh * T(2));
+    if (!__any_sync(FULL, active)) break;
+
+    // ---- one 6-row DLS pass for all lanes --------------------------------------------------------
+    T s[NJ], c[NJ];
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) a.q_out[e * NJ + i] = q[i];
-      if (a.final_pos) { a.final_pos[e * 3] = p[0]; a.final_pos[e * 3 + 1] = p[1]; a.final_pos[e * 3 + 2] = p[2]; }
+    for (int i = 0; i < NJ; ++i) trig(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
+    T pp[3], J[42], R[9], qcur[4];
+    Kin::template fk_full<T>(s, c, pp, J, R);
+    mat2quat<T>(R, qcur);
+    // err_quat = target (x) conj(current); rotation vector in the world frame
+    const T eq[4] = {tq[0] * qcur[0] + tq[1] * qcur[1] + tq[2] * qcur[2] + tq[3] * qcur[3],
+                     -tq[0] * qcur[1] + tq[1] * qcur[0] - tq[2] * qcur[3] + tq[3] * qcur[2],
+                     -tq[0] * qcur[2] + tq[1] * qcur[3] + tq[2] * qcur[0] - tq[3] * qcur[1],
+                     -tq[0] * qcur[3] - tq[1] * qcur[2] + tq[2] * qcur[1] + tq[3] * qcur[0]};
+    T rv[3];
+    quat2vel<T>(eq, rv);
+    T err[6] = {tp[0] - pp[0], tp[1] - pp[1], tp[2] - pp[2], rv[0] * a.rot_weight, rv[1] * a.rot_weight,
+                rv[2] * a.rot_weight};
+    const T pe = sqrt_t((err[0] * err[0] + err[1] * err[1]) + err[2] * err[2]);
+    const T re = sqrt_t((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+    const bool last = it >= a.k.max_iters;
+    const bool conv = !last && (pe < a.k.pos_thresh) && (re < a.rot_thresh);
+    if (active && (conv || last)) {
+      const int iterations = conv ? it + 1 : it;
+      const bool success = conv && (pe < a.k.pos_thresh * T(2)) && (re < a.rot_thresh * T(2));
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) a.q_out[(size_t)e * NJ + i] = q[i];
+      if (a.final_pos) { a.final_pos[(size_t)e * 3] = pp[0]; a.final_pos[(size_t)e * 3 + 1] = pp[1]; a.final_pos[(size_t)e * 3 + 2] = pp[2]; }
       if (a.final_quat) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a.final_quat[e * 4 + i] = qc[i];
+        for (int i = 0; i < 4; ++i) a.final_quat[(size_t)e * 4 + i] = qcur[i];
       }
-      if (a.pos_err) a.pos_err[e] = perr;
-      if (a.rot_err) a.rot_err[e] = rerr;
-      if (a.iters) a.iters[e] = it;
+      if (a.pos_err) a.pos_err[e] = pe;
+      if (a.rot_err) a.rot_err[e] = re;
+      if (a.iters) a.iters[e] = iterations;
       if (a.flags) a.flags[e] = (uint8_t)((conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u));
-      c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)it;
+      c_n += 1; c_conv += conv ? 1 : 0; c_iter += (unsigned long long)iterations;
+      active = false;
     }
+    // unconditional update (a lane that just finished is idle and is overwritten by the next refill)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { J[21 + j] *= a.rot_weight; J[28 + j] *= a.rot_weight; J[35 + j] *= a.rot_weight; }
+    T A[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c2 = 0; c2 <= r; ++c2) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc = acc + J[r * 7 + j] * J[c2 * 7 + j];
+        A[r][c2] = acc + (r == c2 ? a.k.damping : T(0));
+      }
+    ldlt_solve<T, 6>(A, err);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      T dq = T(0);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) dq = dq + J[r * 7 + j] * err[r];
+      dq = clamp_t(dq, -a.k.step_limit, a.k.step_limit);
+      q[j] = clamp_t(q[j] + dq, Kin::template lower<T>(j), Kin::template upper<T>(j));
+    }
+    ++it;
   }
   if (a.counters) {
     c_n = warp_sum(c_n); c_conv = warp_sum(c_conv); c_iter = warp_sum(c_iter);
