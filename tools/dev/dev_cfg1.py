@@ -1,6 +1,6 @@
 """Developer scratch: single-query solve() latency (cfg1)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from mujoco_panda_pnp_b200 import KinematicData, KinematicModel, engine, synthetic

@@ -1,6 +1,6 @@
 """Developer scratch check on a GPU box: smoke + rough timings (not the bench)."""
 import os, sys, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import __graft_entry__ as g

@@ -1,6 +1,6 @@
 """Developer scratch: time HER relabel with and without the goal table."""
 import os, sys, statistics
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from mujoco_panda_pnp_b200 import engine

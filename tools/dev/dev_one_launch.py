@@ -1,6 +1,6 @@
 """One IK launch per kinematics selector given on the command line (for ncu captures)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from mujoco_panda_pnp_b200 import engine, synthetic, KinematicTree

@@ -1,6 +1,6 @@
 """Developer scratch check: pair (FFMA2) IK kernel vs lane kernels - bit identity and timing."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from mujoco_panda_pnp_b200 import engine, synthetic, KinematicTree

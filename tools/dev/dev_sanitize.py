@@ -1,6 +1,6 @@
 """Small-size pass over every kernel family, meant to run under compute-sanitizer (memcheck)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from mujoco_panda_pnp_b200 import engine, synthetic, KinematicTree

@@ -1,6 +1,6 @@
 """Developer scratch: cfg4 waypoint kernel variants."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from mujoco_panda_pnp_b200 import engine, synthetic, KinematicTree
