@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(OBS_TILE) get_obs_kernel(const ObsArgs<T> a) {
 
 // =============================================================================================
 // Batched JacobianIKController.solve: one LANE per query, persistent warps with lane refill.
+// This scalar-template kernel serves FP64 (the parity kernel) and any non-specialised tree; FP32 on the
+// specialised tree runs ik_solve_v_kernel below (same control flow, value-type arithmetic).
 //
 // Every pass of the loop evaluates FK/J/DLS once for all 32 lanes.  A lane whose query
 // finished (converged, or max_iters passes done) stores its result and immediately takes the
