@@ -198,12 +198,28 @@ def cpu_ik_baseline(budget_s: float = 12.0) -> dict:
     t0 = time.perf_counter()
     r = c_oracle.ik_solve(chain, targets, NEUTRAL, nthreads=cores)
     dt = time.perf_counter() - t0
-    return {
+    out = {
         "value": float(r["converged"].sum() / dt), "unit": "solves/s", "cores": cores, "kind": "port",
         "sample": f"{n} cold targets (same generator as the GPU batch), {dt:.1f} s, FP64 C restatement of "
                   "ik_solver.py:50-101 without mj_forward's collision stages (faster than the real reference)",
         "mean_iterations": float(r["iterations"].mean()),
     }
+    # the NumPy restatement on one core - the closest thing here to the reference's own
+    # Python (same control flow and NumPy/LAPACK calls, MuJoCo replaced by the restated engine)
+    try:
+        from oracle import ik_oracle, mj_oracle
+
+        ctl = ik_oracle.JacobianIKController(model, mj_oracle.MjData(model))
+        m, t0, conv = 0, time.perf_counter(), 0
+        while m < len(targets) and (time.perf_counter() - t0 < 2.0 or m < 8):
+            conv += int(ctl.solve(targets[m], NEUTRAL).converged)
+            m += 1
+        dt1 = time.perf_counter() - t0
+        out["numpy_port_1core"] = {"value": conv / dt1, "unit": "solves/s", "cores": 1,
+                                   "sample": f"{m} of the same targets, {dt1:.1f} s, oracle/ik_oracle.py"}
+    except Exception as exc:  # the C port above is the baseline; this line is informational
+        out["numpy_port_1core"] = {"unavailable": repr(exc)}
+    return out
 
 
 def cpu_reward_rows(n, seed=0):
