@@ -386,3 +386,35 @@ def test_cfg5_full_size_batch_properties(tree):
     err = (fk - targets).norm(dim=1)
     assert float(err[a.converged].max()) < 1e-3 + 2e-6
     assert bool((a.iterations[~a.converged] == 100).all())
+
+
+def test_cfg4_full_size_waypoint_properties(tree):
+    """BASELINE cfg4 at full size (2^20 envs x 50 warm-started waypoint solves, one launch): the pair and
+    lane kernels agree bit for bit on every env; counters equal the per-env outputs; every env ends closer
+    to its goal than it started, within the waypoint budget; warm solves take ~2 passes."""
+    n, steps = 1 << 20, 50
+    w = synthetic.waypoint_envs(n, seed=0, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    a = engine.ik_waypoints(w["q_start"], w["goal"], steps, engine.ik_params(kinematics="spec_pair"), counters=cnt)
+    b = engine.ik_waypoints(w["q_start"], w["goal"], steps, engine.ik_params(kinematics="spec_lane"))
+    for f in ("q", "pos", "n_accepted", "iters_total"):
+        assert torch.equal(a[f], b[f]), f
+    c = cnt.cpu().numpy()
+    assert c[3] == int(a["iters_total"].long().sum()) and c[1] == c[0]       # every warm solve converges
+    assert int(a["n_accepted"].max()) <= steps and int(a["n_accepted"].min()) >= 0
+    assert c[0] >= int(a["n_accepted"].long().sum())                        # solves >= accepted waypoints
+    assert 1.9 < c[3] / c[0] < 2.3
+    start = engine.fk_jac(w["q_start"], want_quat=False, want_jac=False)[0]
+    d0 = (w["goal"] - start).norm(dim=1)
+    d1 = (w["goal"] - a["pos"]).norm(dim=1)
+    assert bool((d1 <= d0 + 1e-6).all())
+    moved = a["n_accepted"] > 0
+    assert bool((d1[moved] < d0[moved]).all())
+    # pos is FK(q) of the returned joints
+    fk = engine.fk_jac(a["q"], want_quat=False, want_jac=False)[0]
+    assert float((fk - a["pos"]).abs().max()) < 2e-6
+    # no failed solves in this workload: an env with fewer than `steps` accepted waypoints stopped because
+    # it reached its goal (move.py:106, |goal - pos| <= 0.01)
+    if c[0] == int(a["n_accepted"].long().sum()):
+        early = a["n_accepted"] < steps
+        assert float(d1[early].max()) <= 0.01 + 1e-6
