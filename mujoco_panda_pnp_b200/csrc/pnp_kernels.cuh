@@ -326,6 +326,26 @@ struct Slots<F2> {
   static __device__ __forceinline__ void set(F2& v, int k, float x) { if (k == 0) v.v.x = x; else v.v.y = x; }
 };
 
+// Predicated global accesses for the store + refill block of ik_solve_v_kernel: as plain `if`s the
+// four per-slot blocks (store slot 0/1, refill slot 0/1) were four divergent branches executed one after
+// the other by a handful of lanes (24 % of all warp samples for 15 % of the instructions); predicated,
+// the block is straight-line code and the two slots' dependency chains interleave.
+__device__ __forceinline__ void stg128_if(bool pred, float* ptr, float x, float y, float z, float w) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+      :: "r"((unsigned)pred), "l"(ptr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void ldg3_if(bool pred, const float* ptr, float& x, float& y, float& z) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.f32 %0, [%4];\n\t@p ld.global.nc.f32 %1, [%4+4];\n\t"
+      "@p ld.global.nc.f32 %2, [%4+8];\n\t}"
+      : "+f"(x), "+f"(y), "+f"(z) : "r"((unsigned)pred), "l"(ptr));
+}
+__device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
+               : "+f"(x) : "r"((unsigned)pred), "l"(ptr));
+}
+
 // Deferred flush: a finished slot is FROZEN (its step limit becomes 0, so qn == q and the next passes
 // recompute the same p / n2) instead of being stored and refilled at once; the divergent store +
 // refill code runs only when at least `flush_min` lanes hold a finished slot, when nothing is
@@ -387,31 +407,28 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         unsigned before = 0;
         bool ran_out = false;
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
-          if (st[k] == IDLE && !exhausted) {
-            const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
-            const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
-            if (id < a.n) {
-              idx[k] = id;
-              const float* tp = a.targets + (size_t)id * 3u;
-              Slots<V>::set(tgt[0], k, tp[0]);
-              Slots<V>::set(tgt[1], k, tp[1]);
-              Slots<V>::set(tgt[2], k, tp[2]);
-              if (kBcast) {
+        for (int k = 0; k < S; ++k) {  // predicated, no per-slot branch
+          const bool want = st[k] == IDLE && !exhausted;
+          const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
+          const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
+          const bool ok = want && id < a.n;
+          ran_out = ran_out || (want && !ok);
+          float t0 = Slots<V>::get(tgt[0], k), t1 = Slots<V>::get(tgt[1], k), t2 = Slots<V>::get(tgt[2], k);
+          ldg3_if(ok, a.targets + (size_t)id * 3u, t0, t1, t2);
+          Slots<V>::set(tgt[0], k, t0);
+          Slots<V>::set(tgt[1], k, t1);
+          Slots<V>::set(tgt[2], k, t2);
 #pragma unroll
-                for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, s_q0[i]);
-              } else {
-                const float* qi = a.q_init + (size_t)id * NJ;
-#pragma unroll
-                for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, qi[i]);
-              }
-              it[k] = 0;
-              st[k] = RUN;
-              Slots<V>::set(slim, k, a.k.step_limit);
-            } else {
-              ran_out = true;
-            }
+          for (int i = 0; i < NJ; ++i) {
+            float qi = Slots<V>::get(q[i], k);
+            if (kBcast) qi = ok ? s_q0[i] : qi;
+            else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
+            Slots<V>::set(q[i], k, qi);
           }
+          idx[k] = ok ? id : idx[k];
+          it[k] = ok ? 0 : it[k];
+          st[k] = ok ? (int)RUN : st[k];
+          Slots<V>::set(slim, k, ok ? a.k.step_limit : Slots<V>::get(slim, k));
           before += (unsigned)__popc(need[k]);
         }
         exhausted = exhausted || ran_out;
@@ -457,45 +474,43 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       //      moved it: those are flushed in the same pass (imm) and re-read their q_init.
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        if (st[k] >= FIN_CONV) {
-          const float err = finish_sqrt(Slots<V>::get(n2, k));
-          const bool conv = st[k] == FIN_CONV;
-          const int iterations = it[k];
-          const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
-          const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
-          const unsigned id = idx[k];
-          float qf[NJ];
+        const bool f = st[k] >= FIN_CONV;
+        const bool conv = st[k] == FIN_CONV;
+        const float err = finish_sqrt(Slots<V>::get(n2, k));
+        const int iterations = it[k];
+        const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
+        const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+        const unsigned id = idx[k];
+        float qf[NJ];
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
-          if (iterations == (conv ? 1 : 0)) {  // finished on the first pass (non-converged: max_iters == 0)
-            const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
+        for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
+        if (f && iterations == (conv ? 1 : 0)) {  // finished on the first pass (non-converged: max_iters == 0); rare
+          const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
-          }
-          if (kPacked) {
-            float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
-            oq[0] = make_float4(qf[0], qf[1], qf[2], qf[3]);
-            oq[1] = make_float4(qf[4], qf[5], qf[6], err);
-            reinterpret_cast<float4*>(a.final_pos)[id] =
-                make_float4(Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k),
-                            __int_as_float((int)((unsigned)iterations | (fl << 24))));
-          } else {
-            float* qo = a.q_out + (size_t)id * NJ;
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
-            if (a.final_pos) {
-              float* fp = a.final_pos + (size_t)id * 3u;
-              fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
-            }
-            if (a.pos_err) a.pos_err[id] = err;
-            if (a.iters) a.iters[id] = iterations;
-            if (a.flags) a.flags[id] = (uint8_t)fl;
-          }
-          c_n += 1u;
-          c_conv += conv ? 1u : 0u;
-          c_iter += (unsigned)iterations;
-          st[k] = IDLE;
+          for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
         }
+        if (kPacked) {
+          float* oq = a.q_out + (size_t)id * 8u;
+          stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
+          stg128_if(f, oq + 4, qf[4], qf[5], qf[6], err);
+          stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k),
+                    __int_as_float((int)((unsigned)iterations | (fl << 24))));
+        } else if (f) {
+          float* qo = a.q_out + (size_t)id * NJ;
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
+          if (a.final_pos) {
+            float* fp = a.final_pos + (size_t)id * 3u;
+            fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
+          }
+          if (a.pos_err) a.pos_err[id] = err;
+          if (a.iters) a.iters[id] = iterations;
+          if (a.flags) a.flags[id] = (uint8_t)fl;
+        }
+        c_n += f ? 1u : 0u;
+        c_conv += (f && conv) ? 1u : 0u;
+        c_iter += f ? (unsigned)iterations : 0u;
+        st[k] = f ? (int)IDLE : st[k];
       }
     }
   }
