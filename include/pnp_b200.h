@@ -143,6 +143,8 @@ int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double
 int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err,
                      int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
+/* FP32 IK kernels evaluate sin/cos of the joint angles by table look-up with magic-number range reduction:
+ * joint angles must satisfy |q| < 3.2e3 rad (any sane configuration; q_init outside the joint limits is fine). */
 /* Same solve with PACKED outputs (the fast path: 3 x 128-bit stores per query instead of 13):
  *   out_q8  [n][8] float = q0..q6, pos_error
  *   out_aux4[n][4] float = final_pos xyz, then a 32-bit word (iterations | flags << 24)

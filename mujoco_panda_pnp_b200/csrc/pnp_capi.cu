@@ -440,6 +440,11 @@ int pnp_set_tree(const PnpTree* t) {
       tab[k] = make_float2((float)std::sin(x), (float)std::cos(x));
     }
     CUDA_TRY(cudaMemcpyToSymbol(pnp::g_trig_tab, tab, sizeof tab));
+    // sin(k * 2*pi/8192), k < 8192 + 2048, for the value-type kernels' first-order table trig
+    static float tabv[pnp::kTrigVWords];
+    for (int k = 0; k < pnp::kTrigVWords; ++k)
+      tabv[k] = (float)std::sin((double)k * (6.283185307179586476925286766559 / pnp::kTrigVN));
+    CUDA_TRY(cudaMemcpyToSymbol(pnp::g_trigv_tab, tabv, sizeof tabv));
   }
   s->tree = *t;
   s->have_tree = true;

@@ -53,8 +53,9 @@ __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sinco
 //     sin x = sk + (ck*r - sk*h),  cos x = ck - (sk*r + ck*h),  h = r*r/2
 // 12 instructions for the pair (sincosf: ~27 plus a Payne-Hanek branch), no F2I/I2F, no state.
 // Max abs error 9.1e-8 (1.5 ulp), rms 2.5e-8 for |x| < 2.5e4 rad, measured against float64
-// (tools/check_trig.py).  The magic-number quadrant needs |x| * 163 < 2^22: the FP32 IK kernels
-// document |q| < 2.5e4 rad as their domain (FP64 kernels call sincos()).
+// (tools/check_trig.py).  The magic-number quadrant needs |x| * 163 < 2^22: the scalar-template FP32
+// kernels document |q| < 2.5e4 rad as their domain (FP64 kernels call sincos()).  The value-type kernels
+// use TrigV below.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTrigTabN = 1024;
 __device__ float2 g_trig_tab[kTrigTabN];  // (sin, cos)(k * 2*pi/1024), filled by pnp_set_tree
@@ -355,41 +356,48 @@ __device__ __forceinline__ F2 v_clamp(F2 x, float lo, float hi) {
   return F2(fminf(fmaxf(x.v.x, lo), hi), fminf(fmaxf(x.v.y, lo), hi));
 }
 
-// Table trig for V (same arithmetic as Trig<float>; the table is split into a sin and a cos array so
-// that the two slots of an F2 load straight into the halves of a register pair).
+// Table trig of the value-type kernels: FIRST order on a fine table.
+//   x = k*delta + r, delta = 2*pi/8192, k = rint(x/delta) by magic-number rounding, r by a 2-term Cody-Waite
+//   reduction (|r| <= delta/2 = 3.83e-4);  sin x = sk + ck*r,  cos x = ck - sk*r   (truncation r^2/2 <= 7.4e-8).
+// One table of sin(k*delta) with 8192 + 2048 entries (40 KB of shared memory): cos(k*delta) = sin((k + 2048)*delta) is
+// the same table read 2048 entries further on, an immediate offset on the LDS, and the two slots of an F2 load
+// straight into the halves of a register pair.  6 packed FP32 instructions per joint for both slots (the
+// second-order 1024-entry scheme of Trig<float> needs 10, four of them with three register-pair operands, which is
+// what the packed pipe is short of); max abs error 1.3e-7, rms 2.9e-8 for |x| < 100 rad, 1.8e-7 up to 3.2e3 rad
+// (tools/check_trig.py; the magic-number quadrant needs |x| * 1304 < 2^22: the value-type kernels document
+// |q| < 3.2e3 rad as their domain).
+constexpr int kTrigVN = 8192;
+constexpr int kTrigVWords = kTrigVN + kTrigVN / 4;  // + a quarter turn for the cosine
+__device__ float g_trigv_tab[kTrigVWords];          // sin(k * 2*pi/8192), filled by pnp_set_tree
+
 struct TrigV {
-  const float* sin_tab;  // shared memory, kTrigTabN entries each
-  const float* cos_tab;
+  const float* tab;  // shared memory copy of g_trigv_tab
   __device__ __forceinline__ void operator()(float x, float* s, float* c) const {
-    const float t = fmaf(x, 162.974655f, 12582912.0f);
-    const int ji = __float_as_int(t) & (kTrigTabN - 1);
+    const float t = fmaf(x, 1303.7972412109375f, 12582912.0f);
+    const int ji = __float_as_int(t) & (kTrigVN - 1);
     const float k = t + (-12582912.0f);
-    float r = fmaf(k, -0.0061359233222901821f, x);
-    r = fmaf(k, 1.7074761049507003e-10f, r);
-    const float es = sin_tab[ji], ec = cos_tab[ji];
-    const float h = (r * 0.5f) * r;
-    *s = fmaf(ec, r, fmaf(-es, h, es));
-    *c = fmaf(-es, r, fmaf(-ec, h, ec));
+    float r = fmaf(k, -7.669904152862728e-4f, x);
+    r = fmaf(k, 2.1343451311883754e-11f, r);
+    const float es = tab[ji], ec = tab[ji + kTrigVN / 4];
+    *s = fmaf(ec, r, es);
+    *c = fmaf(-es, r, ec);
   }
   __device__ __forceinline__ void operator()(F2 x, F2* s, F2* c) const {
-    const F2 t = pnp_fma(x, F2(162.974655f), F2(12582912.0f));
-    const int ja = __float_as_int(t.v.x) & (kTrigTabN - 1), jb = __float_as_int(t.v.y) & (kTrigTabN - 1);
+    const F2 t = pnp_fma(x, F2(1303.7972412109375f), F2(12582912.0f));
+    const int ja = __float_as_int(t.v.x) & (kTrigVN - 1), jb = __float_as_int(t.v.y) & (kTrigVN - 1);
     const F2 k = pnp_add(t, F2(-12582912.0f));
-    F2 r = pnp_fma(k, F2(-0.0061359233222901821f), x);
-    r = pnp_fma(k, F2(1.7074761049507003e-10f), r);
-    const F2 es(sin_tab[ja], sin_tab[jb]), ec(cos_tab[ja], cos_tab[jb]);
-    const F2 h = pnp_mul(pnp_mul(r, F2(0.5f)), r);
-    *s = pnp_fma(ec, r, pnp_fma(pnp_neg(es), h, es));
-    *c = pnp_fma(pnp_neg(es), r, pnp_fma(pnp_neg(ec), h, ec));
+    F2 r = pnp_fma(k, F2(-7.669904152862728e-4f), x);
+    r = pnp_fma(k, F2(2.1343451311883754e-11f), r);
+    const F2 es(tab[ja], tab[jb]), ec(tab[ja + kTrigVN / 4], tab[jb + kTrigVN / 4]);
+    *s = pnp_fma(ec, r, es);
+    *c = pnp_fma(pnp_neg(es), r, ec);
   }
 };
 
-__device__ __forceinline__ void load_trig_table_split(float* s_sin, float* s_cos) {
-  for (int i = threadIdx.x; i < kTrigTabN; i += blockDim.x) {
-    const float2 e = g_trig_tab[i];
-    s_sin[i] = e.x;
-    s_cos[i] = e.y;
-  }
+__device__ __forceinline__ void load_trigv_table(float* s_tab) {
+  const float4* src = reinterpret_cast<const float4*>(g_trigv_tab);
+  float4* dst = reinterpret_cast<float4*>(s_tab);
+  for (int i = threadIdx.x; i < kTrigVWords / 4; i += blockDim.x) dst[i] = src[i];
 }
 
 // Split in two so that a kernel can decide between the halves (from n2) whether a slot takes the step:

@@ -363,12 +363,11 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
-  __shared__ __align__(16) float s_sin[kTrigTabN];
-  __shared__ __align__(16) float s_cos[kTrigTabN];
-  load_trig_table_split(s_sin, s_cos);
+  __shared__ __align__(16) float s_trig[kTrigVWords];
+  load_trigv_table(s_trig);
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   __syncthreads();
-  const TrigV trig{s_sin, s_cos};
+  const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
@@ -539,10 +538,9 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 template <bool kSpec>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_one_kernel(const float* __restrict__ in, const IkConst<float> k,
                                                                 float* __restrict__ out) {
-  __shared__ __align__(16) float s_sin[kTrigTabN];
-  __shared__ __align__(16) float s_cos[kTrigTabN];
+  __shared__ __align__(16) float s_trig[kTrigVWords];
   __shared__ float s_in[10];
-  load_trig_table_split(s_sin, s_cos);
+  load_trigv_table(s_trig);
   if (threadIdx.x < 10) s_in[threadIdx.x] = in[threadIdx.x];
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -555,18 +553,18 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_one_kernel(const float* __r
   while (true) {
     const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
     if (kSpec) {
-      const TrigV trig{s_sin, s_cos};
+      const TrigV trig{s_trig};
       float e[3], J[21];
       ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
       conv = !last && n2 < thresh2;                            // :61-64
       if (conv || last) break;
       ik_step_v<float>(q, J, e, k.damping, k.step_limit);
     } else {
-      // generic tree: Trig<float> wants the interleaved table; s_sin/s_cos hold the same entries
+      // generic tree: same table trig as the specialised path
       float s[NJ], c[NJ], J[21], A[6];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
-        const TrigV trig{s_sin, s_cos};
+        const TrigV trig{s_trig};
         trig(q[i] - GenericKin::template qref<float>(i), &s[i], &c[i]);
       }
       GenericKin::template fk_jacp<float>(s, c, p, J);
@@ -780,12 +778,11 @@ template <typename V>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_waypoints_v_kernel(const WaypointArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float s_sin[kTrigTabN];
-  __shared__ __align__(16) float s_cos[kTrigTabN];
+  __shared__ __align__(16) float s_trig[kTrigVWords];
   __shared__ float s_qa[S * NJ * IK_BLOCK];  // accepted q of every slot: [(k * NJ + i) * IK_BLOCK + thread]
-  load_trig_table_split(s_sin, s_cos);
+  load_trigv_table(s_trig);
   __syncthreads();
-  const TrigV trig{s_sin, s_cos};
+  const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   float* const qa = s_qa + threadIdx.x;

@@ -32,12 +32,40 @@ def sincos_tab(x):
     return fma(ck, r, fma(-sk, h, sk)), fma(-sk, r, fma(-ck, h, ck))
 
 
-if __name__ == "__main__":
-    print(f"INV={INV:.9g} D_HI={D_HI:.17g} D_LO={D_LO:.17g}")
+# ---- TrigV of the value-type kernels: first order on an 8192-entry table (one sin table, cos = +2048 entries)
+NV = 8192
+DV = 2 * np.pi / NV
+DV_HI = f32(DV)
+DV_LO = f32(DV - float(DV_HI))
+INVV = f32(NV / (2 * np.pi))
+TABV = np.sin(np.arange(NV + NV // 4) * DV).astype(f32)
+
+
+def sincos_tabv(x):
+    x = x.astype(f32)
+    full = lambda v: np.full_like(x, f32(v))  # noqa: E731
+    mag = f32(12582912.0)
+    t = fma(x, full(INVV), full(mag))
+    ji = t.view(np.int32) & (NV - 1)
+    k = (t - mag).astype(f32)
+    r = fma(k, full(-DV_HI), x)
+    r = fma(k, full(-DV_LO), r)
+    sk, ck = TABV[ji], TABV[ji + NV // 4]
+    return fma(ck, r, sk), fma(-sk, r, ck)
+
+
+def report(name, fn, lims):
     rng = np.random.default_rng(0)
-    for lim in (4.0, 100.0, 1e4, 2.5e4):
+    for lim in lims:
         x = rng.uniform(-lim, lim, 2_000_000).astype(f32)
-        s, c = sincos_tab(x)
+        s, c = fn(x)
         xs = x.astype(np.float64)
         es, ec = np.abs(s - np.sin(xs)), np.abs(c - np.cos(xs))
-        print(f"|x| < {lim:8g}: max abs err sin {es.max():.3e} cos {ec.max():.3e}  rms {np.sqrt(np.mean(es ** 2)):.2e}")
+        print(f"{name} |x| < {lim:8g}: max abs err sin {es.max():.3e} cos {ec.max():.3e}  rms {np.sqrt(np.mean(es ** 2)):.2e}")
+
+
+if __name__ == "__main__":
+    print(f"Trig<float>: INV={INV:.9g} D_HI={D_HI:.17g} D_LO={D_LO:.17g}")
+    report("Trig<float> (1024, 2nd order)", sincos_tab, (4.0, 100.0, 1e4, 2.5e4))
+    print(f"TrigV: INV={INVV:.17g} D_HI={DV_HI:.17g} -D_LO={-DV_LO:.17g}")
+    report("TrigV (8192, 1st order)     ", sincos_tabv, (4.0, 100.0, 1e3, 3.2e3))
