@@ -433,14 +433,7 @@ int pnp_set_tree(const PnpTree* t) {
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
   if (!s->tickets) {
     CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned)));
-    // (sin, cos)(k * 2*pi/1024) for the FP32 IK kernels' table trig, evaluated in FP64
-    static float2 tab[pnp::kTrigTabN];
-    for (int k = 0; k < pnp::kTrigTabN; ++k) {
-      const double x = (double)k * (6.283185307179586476925286766559 / pnp::kTrigTabN);
-      tab[k] = make_float2((float)std::sin(x), (float)std::cos(x));
-    }
-    CUDA_TRY(cudaMemcpyToSymbol(pnp::g_trig_tab, tab, sizeof tab));
-    // sin(k * 2*pi/8192), k < 8192 + 2048, for the value-type kernels' first-order table trig
+    // sin(k * 2*pi/8192), k < 8192 + 2048, for the FP32 IK kernels' first-order table trig, evaluated in FP64
     static float tabv[pnp::kTrigVWords];
     for (int k = 0; k < pnp::kTrigVWords; ++k)
       tabv[k] = (float)std::sin((double)k * (6.283185307179586476925286766559 / pnp::kTrigVN));

@@ -46,19 +46,22 @@ __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
 
 // ---------------------------------------------------------------------------------------------
-// Trig for the IK inner loop.  FP32: table + second-order correction.  x = k*delta + r with
-// delta = 2*pi/1024, k = rint(x/delta) by magic-number rounding, r by a 2-term Cody-Waite
-// reduction (|r| <= delta/2 = 3.07e-3), (sin,cos)(k*delta) from a 1024-entry float2 table held
-// in shared memory, then sin r ~ r (error r^3/6 = 4.8e-9), cos r ~ 1 - r^2/2:
-//     sin x = sk + (ck*r - sk*h),  cos x = ck - (sk*r + ck*h),  h = r*r/2
-// 12 instructions for the pair (sincosf: ~27 plus a Payne-Hanek branch), no F2I/I2F, no state.
-// Max abs error 9.1e-8 (1.5 ulp), rms 2.5e-8 for |x| < 2.5e4 rad, measured against float64
-// (tools/check_trig.py).  The magic-number quadrant needs |x| * 163 < 2^22: the scalar-template FP32
-// kernels document |q| < 2.5e4 rad as their domain (FP64 kernels call sincos()).  The value-type kernels
-// use TrigV below.
+// Trig for the IK inner loops.  FP32: FIRST-order table look-up on a fine table (all FP32 IK kernels, the
+// scalar-template ones through Trig<float>, the value-type ones through TrigV below - same arithmetic):
+//   x = k*delta + r, delta = 2*pi/8192, k = rint(x/delta) by magic-number rounding, r by a 2-term Cody-Waite
+//   reduction (|r| <= delta/2 = 3.83e-4);  sin x = sk + ck*r,  cos x = ck - sk*r   (truncation r^2/2 <= 7.4e-8).
+// One table of sin(k*delta) with 8192 + 2048 entries (40 KB of shared memory): cos(k*delta) = sin((k + 2048)*delta)
+// is the same table read 2048 entries further on, an immediate offset on the LDS.  8 instructions for the pair
+// (sincosf: ~27 plus a Payne-Hanek branch), no F2I/I2F, no state; max abs error 1.3e-7, rms 2.9e-8 for |x| < 100 rad,
+// 1.8e-7 up to 3.2e3 rad (tools/check_trig.py; the magic-number quadrant needs |x| * 1304 < 2^22: the FP32 IK
+// kernels document |q| < 3.2e3 rad as their domain).  FP64 kernels call sincos().
+// (The first session used a 1024-entry (sin, cos) table with a second-order correction: 9.1e-8 / 2.5e-8, but 12
+// instructions per pair - on the packed path 10, four of them with three register-pair operands, which is what that
+// pipe is short of.)
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrigTabN = 1024;
-__device__ float2 g_trig_tab[kTrigTabN];  // (sin, cos)(k * 2*pi/1024), filled by pnp_set_tree
+constexpr int kTrigVN = 8192;
+constexpr int kTrigVWords = kTrigVN + kTrigVN / 4;  // + a quarter turn for the cosine
+__device__ float g_trigv_tab[kTrigVWords];          // sin(k * 2*pi/8192), filled by pnp_set_tree
 
 template <typename T>
 struct Trig;
@@ -66,32 +69,31 @@ struct Trig;
 template <>
 struct Trig<float> {
   static constexpr bool kUsesTable = true;
-  const float2* tab;  // shared-memory copy of g_trig_tab
+  const float* tab;  // shared-memory copy of g_trigv_tab
   __device__ __forceinline__ void operator()(float x, float* s, float* c) const {
-    const float t = fmaf(x, 162.974655f, 12582912.0f);
-    const int ji = __float_as_int(t);
-    const float k = t - 12582912.0f;
-    float r = fmaf(k, -0.0061359233222901821f, x);
-    r = fmaf(k, 1.7074761049507003e-10f, r);
-    const float2 e = tab[ji & (kTrigTabN - 1)];
-    const float h = (0.5f * r) * r;
-    *s = fmaf(e.y, r, fmaf(-e.x, h, e.x));
-    *c = fmaf(-e.x, r, fmaf(-e.y, h, e.y));
+    const float t = fmaf(x, 1303.7972412109375f, 12582912.0f);
+    const int ji = __float_as_int(t) & (kTrigVN - 1);
+    const float k = t + (-12582912.0f);
+    float r = fmaf(k, -7.669904152862728e-4f, x);
+    r = fmaf(k, 2.1343451311883754e-11f, r);
+    const float es = tab[ji], ec = tab[ji + kTrigVN / 4];
+    *s = fmaf(ec, r, es);
+    *c = fmaf(-es, r, ec);
   }
 };
 
 template <>
 struct Trig<double> {
   static constexpr bool kUsesTable = false;
-  const float2* tab;  // unused
+  const float* tab;  // unused
   __device__ __forceinline__ void operator()(double x, double* s, double* c) const { sincos(x, s, c); }
 };
 
 // Cooperative load of the trig table into shared memory (call by every thread of the block).
-__device__ __forceinline__ void load_trig_table(float2* s_tab) {
-  const float4* src = reinterpret_cast<const float4*>(g_trig_tab);
+__device__ __forceinline__ void load_trigv_table(float* s_tab) {
+  const float4* src = reinterpret_cast<const float4*>(g_trigv_tab);
   float4* dst = reinterpret_cast<float4*>(s_tab);
-  for (int i = threadIdx.x; i < kTrigTabN / 2; i += blockDim.x) dst[i] = src[i];
+  for (int i = threadIdx.x; i < kTrigVWords / 4; i += blockDim.x) dst[i] = src[i];
 }
 
 // one MUFU.RCP (callers pass pivots of J J^T + damping I in [damping, ~10] or distances > 1e-3: no
@@ -356,20 +358,8 @@ __device__ __forceinline__ F2 v_clamp(F2 x, float lo, float hi) {
   return F2(fminf(fmaxf(x.v.x, lo), hi), fminf(fmaxf(x.v.y, lo), hi));
 }
 
-// Table trig of the value-type kernels: FIRST order on a fine table.
-//   x = k*delta + r, delta = 2*pi/8192, k = rint(x/delta) by magic-number rounding, r by a 2-term Cody-Waite
-//   reduction (|r| <= delta/2 = 3.83e-4);  sin x = sk + ck*r,  cos x = ck - sk*r   (truncation r^2/2 <= 7.4e-8).
-// One table of sin(k*delta) with 8192 + 2048 entries (40 KB of shared memory): cos(k*delta) = sin((k + 2048)*delta) is
-// the same table read 2048 entries further on, an immediate offset on the LDS, and the two slots of an F2 load
-// straight into the halves of a register pair.  6 packed FP32 instructions per joint for both slots (the
-// second-order 1024-entry scheme of Trig<float> needs 10, four of them with three register-pair operands, which is
-// what the packed pipe is short of); max abs error 1.3e-7, rms 2.9e-8 for |x| < 100 rad, 1.8e-7 up to 3.2e3 rad
-// (tools/check_trig.py; the magic-number quadrant needs |x| * 1304 < 2^22: the value-type kernels document
-// |q| < 3.2e3 rad as their domain).
-constexpr int kTrigVN = 8192;
-constexpr int kTrigVWords = kTrigVN + kTrigVN / 4;  // + a quarter turn for the cosine
-__device__ float g_trigv_tab[kTrigVWords];          // sin(k * 2*pi/8192), filled by pnp_set_tree
-
+// Table trig of the value-type kernels: Trig<float>'s arithmetic for V = float and, packed, for V = F2 (the two
+// slots of an F2 load straight into the halves of a register pair): 6 packed FP32 instructions per joint.
 struct TrigV {
   const float* tab;  // shared memory copy of g_trigv_tab
   __device__ __forceinline__ void operator()(float x, float* s, float* c) const {
@@ -393,12 +383,6 @@ struct TrigV {
     *c = pnp_fma(pnp_neg(es), r, ec);
   }
 };
-
-__device__ __forceinline__ void load_trigv_table(float* s_tab) {
-  const float4* src = reinterpret_cast<const float4*>(g_trigv_tab);
-  float4* dst = reinterpret_cast<float4*>(s_tab);
-  for (int i = threadIdx.x; i < kTrigVWords / 4; i += blockDim.x) dst[i] = src[i];
-}
 
 // Split in two so that a kernel can decide between the halves (from n2) whether a slot takes the step:
 //   ik_eval_v : p = FK(q), J = jacp, e = target - p, n2 = |e|^2          (ik_solver.py:58-61, 70-72)

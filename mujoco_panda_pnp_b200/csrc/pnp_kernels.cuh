@@ -185,8 +185,8 @@ template <typename T, typename Kin, bool kPacked>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) T s_q0[8];  // broadcast q_init: refills read it from shared memory
-  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
-  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
+  if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   if (a.q_init_stride == 0 && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   __syncthreads();
   const Trig<T> trig{s_tab};
@@ -640,8 +640,8 @@ struct WaypointArgs {
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
-  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
+  if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
@@ -1025,8 +1025,8 @@ __device__ __forceinline__ void ldlt_solve(T (&A)[N][N], T (&b)[N]) {
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
-  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
+  if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
@@ -1205,8 +1205,8 @@ __device__ __forceinline__ float divmul(float a, float c, float b) { return a * 
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float2 s_tab[Trig<T>::kUsesTable ? kTrigTabN : 1];
-  if (Trig<T>::kUsesTable) load_trig_table(s_tab);
+  __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
+  if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;

@@ -1,4 +1,5 @@
-"""Accuracy of the table trig used by the FP32 IK kernels (csrc/pnp_common.cuh, Trig<float>),
+"""Accuracy of the table trig used by the FP32 IK kernels (csrc/pnp_common.cuh, Trig<float> / TrigV: first order on an
+8192-entry sine table) and, for comparison, of the first session's 1024-entry second-order scheme,
 emulated in NumPy with exact FMA semantics (products of two floats are exact in float64).
 Prints the max abs / rms error against float64 sin/cos over several ranges."""
 import numpy as np
@@ -65,7 +66,7 @@ def report(name, fn, lims):
 
 
 if __name__ == "__main__":
-    print(f"Trig<float>: INV={INV:.9g} D_HI={D_HI:.17g} D_LO={D_LO:.17g}")
-    report("Trig<float> (1024, 2nd order)", sincos_tab, (4.0, 100.0, 1e4, 2.5e4))
-    print(f"TrigV: INV={INVV:.17g} D_HI={DV_HI:.17g} -D_LO={-DV_LO:.17g}")
-    report("TrigV (8192, 1st order)     ", sincos_tabv, (4.0, 100.0, 1e3, 3.2e3))
+    print(f"first session: INV={INV:.9g} D_HI={D_HI:.17g} D_LO={D_LO:.17g}")
+    report("first session (1024, 2nd order)", sincos_tab, (4.0, 100.0, 1e4, 2.5e4))
+    print(f"Trig<float> / TrigV: INV={INVV:.17g} D_HI={DV_HI:.17g} -D_LO={-DV_LO:.17g}")
+    report("Trig<float>/TrigV (8192, 1st order)", sincos_tabv, (4.0, 100.0, 1e3, 3.2e3))
