@@ -536,6 +536,18 @@ def run_ours(args) -> int:
         ms = statistics.median(ts)
         side["get_obs"] = {"workload": "2^22 envs, FrankaEnv._get_obs from kinematic state -> [obs19|ag3|dg3] rows",
                            "ms_per_launch": ms, "envs_per_s": n_o / (ms * 1e-3), "GBps_algorithmic": 228.0 * n_o / (ms * 1e-3) / 1e9}
+        # K3/K4: mj_kinematics + mj_jacSite + mju_mat2Quat for the EE site (28 B in, 12 + 16 + 168 B out per configuration)
+        n_f = 1 << 22
+        qf = synthetic.random_joint_configs(n_f, tree.lower, tree.upper, seed=9, device=dev)
+        f_fk = lambda: engine.fk_jac(qf)  # noqa: E731
+        for _ in range(3):
+            f_fk()
+        _, ts = cuda_time_steps(f_fk, 10, torch)
+        ms = statistics.median(ts)
+        side["fk_jac"] = {"workload": "2^22 joint configurations -> EE position, wxyz quaternion, 6x7 Jacobian (FP32)",
+                          "ms_per_launch": ms, "configs_per_s": n_f / (ms * 1e-3), "GBps_algorithmic": 224.0 * n_f / (ms * 1e-3) / 1e9,
+                          "note": "includes the torch.empty of the three outputs"}
+        del qf
         # pose-mode (6x6) IK extension, reachable poses near neutral
         n_p = 1 << 20
         qp = synthetic.reachable_move_envs(n_p, tree.lower, tree.upper, seed=5, device=dev, spread=0.5)["q_goal"]

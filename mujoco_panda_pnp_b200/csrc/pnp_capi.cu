@@ -28,6 +28,7 @@ struct DeviceState {
   unsigned ticket_seq = 0;
   int occ_ik[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool obs_smem_set = false;
+  bool fk_smem_set = false;
 };
 constexpr int kMaxDevices = 16;
 constexpr int kTicketSlots = 64;
@@ -148,14 +149,42 @@ int fk_jac_impl(const T* q, int64_t n, T* pos, T* quat, T* jac, int32_t kinemati
   bool spec;
   if ((rc = pick_kin(s, kinematics, &spec))) return rc;
   if (n == 0) return PNP_OK;
-  const int grid = grid_for(n, 128, s->sm_count, 16);
   cudaStream_t st = (cudaStream_t)stream;
-  if (spec)
-    pnp::fk_jac_kernel<T, pnp::SpecKin><<<grid, 128, 0, st>>>(q, n, pos, quat, jac);
-  else
-    pnp::fk_jac_kernel<T, pnp::GenericKin><<<grid, 128, 0, st>>>(q, n, pos, quat, jac);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  // FP32, 16-byte aligned outputs: full 128-configuration tiles go through the kernel with staged, bulk-stored
+  // outputs; the ragged tail (and everything else) through the per-lane kernel
+  int64_t done = 0;
+  if constexpr (std::is_same<T, float>::value) {
+    // (position / quaternion only: 12-28 B out per configuration, the per-lane kernel at full occupancy is faster)
+    const bool aligned = aligned16(pos) && (!quat || aligned16(quat)) && aligned16(jac);
+    if (jac && aligned && n >= pnp::FK_TILE) {
+      if (!s->fk_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(pnp::fk_jac_bulk_kernel<pnp::SpecKin>, cudaFuncAttributeMaxDynamicSharedMemorySize, pnp::FK_BULK_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(pnp::fk_jac_bulk_kernel<pnp::GenericKin>, cudaFuncAttributeMaxDynamicSharedMemorySize, pnp::FK_BULK_SMEM));
+        s->fk_smem_set = true;
+      }
+      const int64_t tiles = n / pnp::FK_TILE;
+      const int grid = (int)std::min<int64_t>(tiles, (int64_t)s->sm_count * 4);  // 4 x 49 KB of shared memory per SM
+      if (spec)
+        pnp::fk_jac_bulk_kernel<pnp::SpecKin><<<grid, pnp::FK_TILE, pnp::FK_BULK_SMEM, st>>>(q, tiles, pos, quat, jac);
+      else
+        pnp::fk_jac_bulk_kernel<pnp::GenericKin><<<grid, pnp::FK_TILE, pnp::FK_BULK_SMEM, st>>>(q, tiles, pos, quat, jac);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+      done = tiles * pnp::FK_TILE;
+    }
+  }
+  if (done < n) {
+    const int64_t m = n - done;
+    const int grid = grid_for(m, 128, s->sm_count, 16);
+    T* quat_t = quat ? quat + done * 4 : nullptr;
+    T* jac_t = jac ? jac + done * 42 : nullptr;
+    if (spec)
+      pnp::fk_jac_kernel<T, pnp::SpecKin><<<grid, 128, 0, st>>>(q + done * 7, m, pos + done * 3, quat_t, jac_t);
+    else
+      pnp::fk_jac_kernel<T, pnp::GenericKin><<<grid, 128, 0, st>>>(q + done * 7, m, pos + done * 3, quat_t, jac_t);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   return PNP_OK;
 }
 
