@@ -291,7 +291,7 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     // lanes with a finished slot that trigger a store + refill (PNP_IK_FLUSH_MIN overrides, for tuning)
     static const int env_flush = [] { const char* e = getenv("PNP_IK_FLUSH_MIN"); return e ? atoi(e) : 0; }();
     const bool oversubscribed = (long long)a.n >= (long long)s->sm_count * 8192;
-    args.flush_min = env_flush > 0 ? (unsigned)env_flush : (S == 2 ? (small ? 1u : 8u) : (oversubscribed ? 4u : 1u));
+    args.flush_min = env_flush > 0 ? (unsigned)env_flush : (S == 2 ? (small ? 1u : 10u) : (oversubscribed ? 4u : 1u));
   }
   if (a.q_init_stride == 0)
     pnp::ik_solve_v_kernel<V, kPacked, true><<<grid, block, 0, st>>>(args);
