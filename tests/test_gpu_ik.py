@@ -418,3 +418,39 @@ def test_cfg4_full_size_waypoint_properties(tree):
     if c[0] == int(a["n_accepted"].long().sum()):
         early = a["n_accepted"] < steps
         assert float(d1[early].max()) <= 0.01 + 1e-6
+
+
+def test_solver_parameter_sweep_vs_oracle(tree, oracle_chain):
+    """The solve kwargs are part of the reference signature (ik_solver.py:35-37): sweep them - thresholds,
+    damping, step limit, iteration budget, warm and cold starts - on all three FP32 kernels (generic tree,
+    one query per lane, two per lane) against the FP64 C restatement."""
+    rng = np.random.default_rng(99)
+    lo, hi = tree.lower, tree.upper
+    cases = [dict(max_iters=100, pos_thresh=1e-3, damping=1e-2, step_limit=0.1),     # defaults
+             dict(max_iters=100, pos_thresh=1e-4, damping=0.05, step_limit=0.1),     # test/ik_test.py
+             dict(max_iters=25, pos_thresh=2e-3, damping=1e-3, step_limit=0.05),
+             dict(max_iters=200, pos_thresh=5e-4, damping=0.1, step_limit=0.2),
+             dict(max_iters=3, pos_thresh=1e-3, damping=1e-2, step_limit=0.1),       # most queries run out
+             dict(max_iters=60, pos_thresh=1e-2, damping=1.0, step_limit=1.0)]
+    n = 3000
+    for ci, kw in enumerate(cases):
+        qstar = rng.uniform(lo, hi, (n, 7))
+        targets = c_oracle.fk_jac(oracle_chain, qstar, nthreads=8)[0].astype(np.float32).astype(np.float64)
+        warm = ci % 2 == 1
+        q0 = np.clip(qstar + rng.uniform(-0.2, 0.2, (n, 7)), lo, hi).astype(np.float32).astype(np.float64) if warm else NEUTRAL
+        ref = c_oracle.ik_solve(oracle_chain, targets, q0, nthreads=8, **kw)
+        tg = torch.tensor(targets, dtype=torch.float32, device="cuda")
+        qi = torch.tensor(q0, dtype=torch.float32, device="cuda")
+        for kin in ("generic", "spec_lane", "spec_pair"):
+            res = engine.ik_solve(tg, qi, engine.ik_params(kinematics=kin, **kw))
+            iters = res.iterations.cpu().numpy()
+            conv = res.converged.cpu().numpy()
+            flips = int((iters != ref["iterations"]).sum())
+            assert flips <= max(6, n // 250), (kw, kin, flips)
+            assert int((conv != ref["converged"]).sum()) <= max(3, n // 500), (kw, kin)
+            same = conv & ref["converged"] & (iters == ref["iterations"])
+            q = res.q.double().cpu().numpy()
+            ee = c_oracle.fk_jac(oracle_chain, q, nthreads=8)[0]
+            assert np.linalg.norm(ee[same] - ref["final_pos"][same], axis=1).max() < EE_TOL_M, (kw, kin)
+            assert np.linalg.norm(ee[conv] - targets[conv], axis=1).max() < kw["pos_thresh"] + 1e-5
+            assert (q >= lo - 1e-6).all() and (q <= hi + 1e-6).all() or warm  # cold start stays within limits
