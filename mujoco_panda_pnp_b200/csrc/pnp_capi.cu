@@ -219,7 +219,7 @@ int get_obs_impl(const T* q_arm, const T* qvel_arm, const T* fingers, const T* o
         s->obs_smem_set = true;
       }
       const int64_t tiles = n / pnp::OBS_TILE;
-      const int grid = (int)std::min<int64_t>(tiles, (int64_t)s->sm_count * 7);  // 7 x 32 KB of shared memory per SM
+      const int grid = (int)std::min<int64_t>(tiles, (int64_t)s->sm_count * 3);  // 3 x 72 KB of shared memory per SM
       if (spec)
         pnp::get_obs_bulk_kernel<pnp::SpecKin><<<grid, pnp::OBS_TILE, pnp::OBS_BULK_SMEM, st>>>(a);
       else

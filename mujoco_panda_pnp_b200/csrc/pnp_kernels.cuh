@@ -1785,7 +1785,7 @@ __global__ void __launch_bounds__(HER_TILE) her_relabel_kernel(const HerArgs a) 
 // goal 1536 B) are contiguous in their arrays, so one elected thread fetches them with seven
 // cp.async.bulk copies completing on an mbarrier, double buffered against the compute of the previous
 // tile; the 12.8 KB of assembled rows overwrite the tile's own consumed input stage and leave with
-// one bulk store (32 KB of shared memory per block, 7 blocks per SM).  The per-lane strided loads of
+// one bulk store.  72 KB of shared memory per block (two stages + the trig table), 3 blocks per SM.  The per-lane strided loads of
 // get_obs_kernel left the warps on the long scoreboard for half of their time (ncu: 0.60 of the DRAM
 // peak); here no lane ever issues a global load.  Full tiles of 16-byte aligned arrays only; tails and
 // unaligned views run get_obs_kernel.
@@ -1797,14 +1797,18 @@ struct ObsTileLayout {  // word offsets of the input slices inside one stage
 };
 constexpr int OBS_STAGE_BYTES = ObsTileLayout::words * 4;
 constexpr int OBS_OUT_BYTES = OBS_TILE * 25 * 4;
-constexpr int OBS_BULK_SMEM = 2 * OBS_STAGE_BYTES;  // 32 KB: the rows of a tile overwrite its own (consumed) input stage
+constexpr int OBS_BULK_SMEM = 2 * OBS_STAGE_BYTES + kTrigVWords * 4;  // 32 KB of stages (the rows of a tile overwrite its own
+                                                                     // consumed input stage) + the 40 KB trig table
 
 template <typename Kin>
 __global__ void __launch_bounds__(OBS_TILE) get_obs_bulk_kernel(const ObsArgs<float> a) {
   using L = ObsTileLayout;
   extern __shared__ __align__(128) unsigned char obs_smem[];
   float* buf = reinterpret_cast<float*>(obs_smem);  // [2][L::words]
+  float* s_trig = buf + 2 * L::words;               // [kTrigVWords]: the IK kernels' table trig
   __shared__ unsigned long long bar[2];
+  load_trigv_table(s_trig);
+  const Trig<float> trig{s_trig};
   const int tid = threadIdx.x;
   const long long n_tiles = a.n / OBS_TILE;  // full tiles only
   const bool per_env_goal = a.goal_stride != 0;
@@ -1842,7 +1846,7 @@ __global__ void __launch_bounds__(OBS_TILE) get_obs_bulk_kernel(const ObsArgs<fl
       float s[NJ], c[NJ], qv[NJ];
 #pragma unroll
       for (int k = 0; k < NJ; ++k) {
-        sincos_t(in[L::q + tid * 7 + k] - Kin::template qref<float>(k), &s[k], &c[k]);
+        trig(in[L::q + tid * 7 + k] - Kin::template qref<float>(k), &s[k], &c[k]);
         qv[k] = in[L::qv + tid * 7 + k];
       }
       float p[3], J[21];
