@@ -281,7 +281,9 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   }
   const int block = small ? 32 : pnp::IK_BLOCK;
   const long long lanes_needed = ((long long)a.n + S - 1) / S;
-  const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, s->occ_ik[slot]);
+  static const int env_occ = [] { const char* e = getenv("PNP_IK_OCC"); return e ? atoi(e) : 0; }();
+  const int occ_use = env_occ > 0 && env_occ < s->occ_ik[slot] ? env_occ : s->occ_ik[slot];
+  const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occ_use);
   pnp::IkArgs<float> args = a;
   const long long warps = (long long)grid * (block / 32);
   long long chunk = (long long)a.n / (warps * 16);
