@@ -45,6 +45,29 @@ def test_struct_layouts_match_header(cuda_lib):
     assert bytes(s) == bytes(KinematicTree.from_mjcf().to_struct())
 
 
+def test_header_constants_match_binding():
+    """#define values of the header (kinematics selectors, flag bits, counter slots) = the binding's constants."""
+    text = open(HEADER).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u")) for m in re.finditer(r"#define\s+(PNP_[A-Z0-9_]+)\s+(-?\d+u?)\b", text)}
+    for name in ("PNP_KIN_AUTO", "PNP_KIN_GENERIC", "PNP_KIN_SPECIALIZED", "PNP_KIN_SPEC_LANE", "PNP_KIN_SPEC_PAIR",
+                 "PNP_IK_CONVERGED", "PNP_IK_SUCCESS"):
+        assert defs[name] == getattr(_lib, name), name
+    assert _lib.KINEMATICS == {"auto": 0, "generic": 1, "specialized": 2, "spec_lane": 3, "spec_pair": 4}
+    assert [defs[f"PNP_IK_CNT_{k}"] for k in ("N", "CONVERGED", "SUCCESS", "ITERATIONS")] == [0, 1, 2, 3]
+
+
+def test_packed_sass_is_present():
+    """The shipped library really contains Blackwell's packed FP32 instructions and the bulk-copy engine ops
+    the design relies on (FFMA2/FMUL2/FADD2, UBLKCP) - a build that silently lost them would still pass parity."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.check_output([cuobjdump, "-sass", _lib.LIB_PATH], text=True)
+    for op in ("FFMA2", "FMUL2", "FADD2", "UBLKCP", "SYNCS"):
+        assert op in sass, op
+    assert sass.count("FFMA2") > 400
+
+
 def test_argument_errors_do_not_need_a_gpu(cuda_lib):
     assert cuda_lib.pnp_set_tree(None) == -1
     assert b"NULL" in cuda_lib.pnp_last_error()
