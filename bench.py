@@ -535,7 +535,10 @@ def run_ours(args) -> int:
         _, ts = cuda_time_steps(f_obs, 10, torch)
         ms = statistics.median(ts)
         side["get_obs"] = {"workload": "2^22 envs, FrankaEnv._get_obs from kinematic state -> [obs19|ag3|dg3] rows",
-                           "ms_per_launch": ms, "envs_per_s": n_o / (ms * 1e-3), "GBps_algorithmic": 228.0 * n_o / (ms * 1e-3) / 1e9}
+                           "ms_per_launch": ms, "envs_per_s": n_o / (ms * 1e-3), "GBps_algorithmic": 228.0 * n_o / (ms * 1e-3) / 1e9,
+                           "roofline": {"bound": "hbm", "achieved": 228.0 * n_o / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "frac": 228.0 * n_o / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                        "algorithmic": "228 B/env (128 in + 100 out)", "kernel": "get_obs_bulk_kernel<SpecKin>"}}
         # K3/K4: mj_kinematics + mj_jacSite + mju_mat2Quat for the EE site (28 B in, 12 + 16 + 168 B out per configuration)
         n_f = 1 << 22
         qf = synthetic.random_joint_configs(n_f, tree.lower, tree.upper, seed=9, device=dev)
@@ -546,6 +549,9 @@ def run_ours(args) -> int:
         ms = statistics.median(ts)
         side["fk_jac"] = {"workload": "2^22 joint configurations -> EE position, wxyz quaternion, 6x7 Jacobian (FP32)",
                           "ms_per_launch": ms, "configs_per_s": n_f / (ms * 1e-3), "GBps_algorithmic": 224.0 * n_f / (ms * 1e-3) / 1e9,
+                          "roofline": {"bound": "hbm", "achieved": 224.0 * n_f / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": 224.0 * n_f / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                       "algorithmic": "224 B/configuration (28 in + 12 + 16 + 168 out)", "kernel": "fk_jac_bulk_kernel<SpecKin>"},
                           "note": "includes the torch.empty of the three outputs"}
         del qf
         # pose-mode (6x6) IK extension, reachable poses near neutral
