@@ -279,13 +279,16 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
                                                                   pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
-  const int block = small ? 32 : pnp::IK_BLOCK;
+  // small batches: one solving warp per block (spreads the batch over all SMs), plus three helper warps that
+  // only load the trig table (a lone warp needs ~5 us for its 40 KB)
+  const int block = pnp::IK_BLOCK;
   const long long lanes_needed = ((long long)a.n + S - 1) / S;
   static const int env_occ = [] { const char* e = getenv("PNP_IK_OCC"); return e ? atoi(e) : 0; }();
   const int occ_use = env_occ > 0 && env_occ < s->occ_ik[slot] ? env_occ : s->occ_ik[slot];
   const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occ_use);
   pnp::IkArgs<float> args = a;
-  const long long warps = (long long)grid * (block / 32);
+  args.solo_warp = small ? 1u : 0u;
+  const long long warps = small ? (long long)grid : (long long)grid * (block / 32);
   long long chunk = (long long)a.n / (warps * 16);
   chunk = chunk < 32 * S ? 32 * S : (chunk > 256 ? 256 : chunk);
   args.chunk = (unsigned)(chunk & ~31ll);
@@ -345,7 +348,7 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
-  a.counters = counters; a.ticket = ticket;
+  a.counters = counters; a.ticket = ticket; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   if (spec) {
     if constexpr (std::is_same<T, float>::value)

@@ -172,6 +172,8 @@ struct IkArgs {
   unsigned* ticket;   // zeroed before launch
   unsigned chunk;     // queries a warp reserves per ticket atomic (>= 32)
   unsigned flush_min; // ik_solve_v_kernel: lanes with a finished slot that trigger a store + refill
+  unsigned solo_warp; // ik_solve_v_kernel, small batches: the block has 4 warps to load the 40 KB trig table quickly,
+                      // only warp 0 solves (one warp per block spreads a small batch over all SMs)
 };
 
 // convergence test (ik_solver.py:61-64).  FP64 follows the reference literally (sqrt, then
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   load_trigv_table(s_trig);
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
