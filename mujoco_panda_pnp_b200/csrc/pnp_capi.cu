@@ -252,9 +252,9 @@ int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t 
                                                                   pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
-  // Persistent grid: every resident lane keeps pulling queries.  Small batches use 32-lane
-  // blocks so the few warps spread over as many SMs as possible (latency bound).
-  const int block = small ? 32 : pnp::IK_BLOCK;
+  // Persistent grid: every resident lane keeps pulling queries.  Small batches use one working warp
+  // per block so the few warps spread over as many SMs as possible (latency bound).
+  const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   const int grid = small ? (int)((a.n + 31u) / 32u) : grid_for(a.n, block, s->sm_count, s->occ_ik[slot]);
   // queries reserved per ticket atomic: ~1/16 of a warp's share, within [32, 256]
   pnp::IkArgs<T> args = a;
@@ -262,6 +262,7 @@ int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t 
   long long chunk = (long long)a.n / (warps * 16);
   chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : chunk);
   args.chunk = (unsigned)(chunk & ~31ll);
+  args.solo_warp = small ? 1u : 0u;
   pnp::ik_solve_kernel<T, Kin, kPacked><<<grid, block, 0, st>>>(args);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -562,7 +563,7 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   a.q_out = q_out; a.pos_out = pos_out; a.n_accepted = n_accepted; a.iters_total = iters_total;
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   // specialised tree: the value-type kernels (same arithmetic in both): two envs per lane once the
   // batch oversubscribes the machine, one per lane below that; other trees: the scalar-template kernel
   const bool pair = spec && params->kinematics != PNP_KIN_SPEC_LANE &&
@@ -581,6 +582,7 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   long long chunk = n / ((long long)grid * (block / 32) * 8);
   chunk = chunk < 32 * S ? 32 * S : (chunk > 128 ? 128 : chunk);
   a.chunk = (unsigned)(chunk & ~31ll);
+  a.solo_warp = small ? 1u : 0u;
   if (!spec)
     pnp::ik_waypoints_kernel<float, pnp::GenericKin><<<grid, block, 0, st>>>(a);
   else if (pair)
@@ -626,7 +628,7 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
   a.q_out = q_out; a.final_pos = final_pos; a.final_quat = final_quat; a.pos_err = pos_err; a.rot_err = rot_err;
   a.iters = iters; a.flags = flags; a.counters = counters; a.ticket = ticket;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   int occ = 4;
   if (!small) {
     cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_pose_solve_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)
@@ -637,6 +639,7 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
   long long chunk = n / ((long long)grid * (block / 32) * 16);
   chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : chunk);
   a.chunk = (unsigned)(chunk & ~31ll);
+  a.solo_warp = small ? 1u : 0u;
   if (spec)
     pnp::ik_pose_solve_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
   else
@@ -680,7 +683,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   a.traj = traj; a.traj_len = traj_len; a.q_final = q_final; a.n_solves = n_solves; a.status = status;
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  const int block = small ? 32 : pnp::IK_BLOCK;
+  const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   int occ = 4;
   if (!small) {
     cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::move_ik_plan_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)
@@ -692,6 +695,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   long long chunk = n / ((long long)grid * (block / 32) * 8);
   chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk);
   a.chunk = (unsigned)(chunk & ~31ll);
+  a.solo_warp = small ? 1u : 0u;
   if (spec)
     pnp::move_ik_plan_kernel<T, pnp::SpecKin><<<grid, block, 0, st>>>(a);
   else

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
   if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   if (a.q_init_stride == 0 && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
 
@@ -630,6 +631,7 @@ struct WaypointArgs {
   unsigned long long* counters;
   unsigned* ticket; // zeroed before launch
   unsigned chunk;   // envs a warp reserves per ticket atomic
+  unsigned solo_warp;  // small batches: 4 warps load the trig table, only warp 0 works (see IkArgs)
 };
 
 // The two loop levels (waypoints x DLS passes) are FLATTENED and the lanes are PERSISTENT: every pass
@@ -646,6 +648,7 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
   __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
   if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   enum { IDLE = 0, INIT = 1, RUN = 2 };
@@ -785,6 +788,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   __shared__ float s_qa[S * NJ * IK_BLOCK];  // accepted q of every slot: [(k * NJ + i) * IK_BLOCK + thread]
   load_trigv_table(s_trig);
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
@@ -979,6 +983,7 @@ struct PoseIkArgs {
   unsigned long long* counters;
   unsigned* ticket; // zeroed before launch
   unsigned chunk;   // queries a warp reserves per ticket atomic
+  unsigned solo_warp;  // small batches: 4 warps load the trig table, only warp 0 works (see IkArgs)
 };
 
 // mju_quat2Vel(res, quat, 1): rotation vector of a unit quaternion, angle folded into (-pi, pi]
@@ -1031,6 +1036,7 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArg
   __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
   if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
@@ -1183,6 +1189,7 @@ struct MoveArgs {
   unsigned long long* counters;
   unsigned* ticket; // zeroed before launch
   unsigned chunk;   // envs a warp reserves per ticket atomic
+  unsigned solo_warp;  // small batches: 4 warps load the trig table, only warp 0 works (see IkArgs)
 };
 
 // The planner's scalar bookkeeping in the two precisions: FP64 follows the reference's operations
@@ -1211,6 +1218,7 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
   __shared__ __align__(16) float s_tab[Trig<T>::kUsesTable ? kTrigVWords : 4];
   if (Trig<T>::kUsesTable) load_trigv_table(s_tab);
   __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const Trig<T> trig{s_tab};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   enum { NORMAL = 0, FB1 = 1, FB2 = 2, DONE = 3, INIT = 4, IDLE = 5 };
