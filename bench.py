@@ -469,8 +469,9 @@ def run_ours(args) -> int:
         side["cfg1"] = {"workload": "single-query solve() to the 3 shelf grasp poses from neutral (test/ik_test.py path)",
                         "us_per_solve_host_to_host": (time.perf_counter() - t0) / (3 * reps) * 1e6,
                         "iterations": its[:3]}
-        # whole MoveIKSkill.reset planner, 2^18 envs in one launch
-        n_pl = 1 << 18
+        # whole MoveIKSkill.reset planner, 2^20 envs in one launch (plans are 40-200 solves long and a lane
+        # owns one env at a time: below ~2^20 envs the launch is dominated by load imbalance, 2^18 runs at 0.7 of this rate)
+        n_pl = 1 << 20
         wp = synthetic.reachable_move_envs(n_pl, tree.lower, tree.upper, seed=1, device=dev)
         wp["goal"] = engine.fk_jac(wp["q_goal"], want_quat=False, want_jac=False)[0]
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -478,7 +479,7 @@ def run_ours(args) -> int:
         torch.cuda.synchronize()
         cp = cnt.cpu().numpy()
         _, ts = cuda_time_steps(lambda: engine.move_ik_plan(wp["q_start"], wp["goal"], params), 2, torch)
-        side["move_planner"] = {"workload": "2^18 MoveIKSkill.reset plans, reachable goals FK(neutral +- 0.6 rad), 1 launch",
+        side["move_planner"] = {"workload": "2^20 MoveIKSkill.reset plans, reachable goals FK(neutral +- 0.6 rad), 1 launch",
                                 "ms_per_launch": min(ts),
                                 "plans_per_s": n_pl / (min(ts) * 1e-3), "ik_solves_per_s": float(cp[0]) / (min(ts) * 1e-3),
                                 "mean_solves_per_plan": float(cp[0]) / n_pl}

@@ -684,6 +684,32 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
+  if constexpr (std::is_same<T, float>::value) {
+    if (spec) {
+      // specialised tree, FP32: the value-type kernels (same arithmetic in both, branch-free common path)
+      const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR;
+      const int S = pair ? 2 : 1;
+      int occv = 4;
+      if (!small) {
+        cudaError_t e = pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<pnp::F2>, pnp::IK_BLOCK, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float>, pnp::IK_BLOCK, 0);
+        if (e != cudaSuccess || occv < 1) occv = 4;
+      }
+      const long long lanes_needed = (n + S - 1) / S;
+      const int gridv = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occv);
+      long long chunkv = n / ((long long)gridv * (block / 32) * 8);
+      chunkv = chunkv < 32 * S ? 32 * S : (chunkv > 128 ? 128 : chunkv);
+      a.chunk = (unsigned)(chunkv & ~31ll);
+      a.solo_warp = small ? 1u : 0u;
+      if (pair)
+        pnp::move_ik_plan_v_kernel<pnp::F2><<<gridv, block, 0, st>>>(a);
+      else
+        pnp::move_ik_plan_v_kernel<float><<<gridv, block, 0, st>>>(a);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+      return PNP_OK;
+    }
+  }
   int occ = 4;
   if (!small) {
     cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::move_ik_plan_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)

@@ -1593,6 +1593,263 @@ __global__ void __launch_bounds__(256) reward_kernel(const RewardArgs<TIn> a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The planner over the value types of pnp_vec.cuh (specialised tree, FP32): V = float plans one env per
+// lane, V = F2 two (packed FFMA2/FMUL2/FADD2) - same operations, bit-identical results.  Same state
+// machine and reference line numbers as move_ik_plan_kernel above, restructured so that the COMMON
+// transitions run branch-free: with ~2 passes per warm solve half of the slots finish a solve in every
+// pass, and as `if` blocks the post-processing was executed divergently on every trip (the scalar kernel
+// runs at 0.23 of the FP32 peak, the waypoint kernel with branch-free bookkeeping at 0.50).
+//   predicated : INIT, an accepted solve (append the point, q_current = result.q, pos = final_pos), the
+//                adaptive waypoint of the next NORMAL solve (packed geometry for both slots)
+//   divergent  : a rejected solve and the fallback chain (rare), the end of an env (once per env)
+// A slot whose solve finishes in a pass is frozen for that pass (step limit 0); q_current of every slot
+// lives in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stg1_if(bool pred, float* ptr, float x) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.f32 [%1], %2;\n\t}"
+               :: "r"((unsigned)pred), "l"(ptr), "f"(x) : "memory");
+}
+
+template <typename V>
+__global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) move_ik_plan_v_kernel(const MoveArgs<float> a) {
+  constexpr int S = Slots<V>::kN;
+  const unsigned lane = threadIdx.x & 31u;
+  __shared__ __align__(16) float s_trig[kTrigVWords];
+  __shared__ float s_qa[S * NJ * IK_BLOCK];  // q_current of every slot: [(k * NJ + i) * IK_BLOCK + thread]
+  load_trigv_table(s_trig);
+  __syncthreads();
+  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
+  const TrigV trig{s_trig};
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
+  float* const qa = s_qa + threadIdx.x;
+  enum { NORMAL = 0, FB1 = 1, FB2 = 2, DONE = 3, INIT = 4, IDLE = 5 };
+
+  V qs[NJ], tgt[3], pos[3], goal[3], slim(0.0f);
+  int state[S], it[S], len[S], solves[S], st[S], point_count[S], cf[S], outer[S];
+  float astep[S];
+  unsigned env[S];
+  bool exhausted = false;
+  unsigned long long c_n = 0, c_conv = 0, c_iter = 0;
+  unsigned pool_next = 0, pool_end = 0;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) qs[i] = V(0.0f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tgt[i] = pos[i] = goal[i] = V(0.0f);
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    state[k] = IDLE; it[k] = len[k] = solves[k] = st[k] = point_count[k] = cf[k] = outer[k] = 0; astep[k] = 0.0f; env[k] = 0;
+  }
+  // traj[len] = point (move.py:98,135,157,173,191), predicated; beyond traj_cap the point is dropped (status bit 4)
+  auto append_if = [&](bool pred, int k, float x, float y, float z) {
+    const bool room = len[k] < a.traj_cap;
+    float* t = a.traj + ((size_t)env[k] * a.traj_cap + (room ? len[k] : 0)) * 3;
+    stg1_if(pred && room, t, x);
+    stg1_if(pred && room, t + 1, y);
+    stg1_if(pred && room, t + 2, z);
+    st[k] |= (pred && !room) ? 4 : 0;
+    len[k] += pred ? 1 : 0;
+  };
+
+  while (true) {
+    // ---- write back finished envs (once per env), refill idle slots ----------------------------------
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      if (state[k] == DONE) {
+        const unsigned id = env[k];
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) a.q_final[(size_t)id * NJ + i] = qa[(k * NJ + i) * IK_BLOCK];
+        a.traj_len[id] = len[k];
+        if (a.n_solves) a.n_solves[id] = solves[k];
+        if (a.status) a.status[id] = st[k];
+        state[k] = IDLE;
+      }
+    }
+    unsigned need[S], count = 0;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      need[k] = __ballot_sync(FULL, state[k] == IDLE && !exhausted);
+      count += (unsigned)__popc(need[k]);
+    }
+    if (count) {
+      const unsigned avail = pool_end - pool_next;
+      unsigned fresh = 0;
+      if (count > avail) {
+        if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+        fresh = __shfl_sync(FULL, fresh, 0);
+      }
+      unsigned before = 0;
+      bool ran_out = false;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        if (state[k] == IDLE && !exhausted) {
+          const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
+          const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
+          if (id < a.n) {
+            env[k] = id;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+              const float v = a.q_start[(size_t)id * NJ + i];
+              Slots<V>::set(qs[i], k, v);
+              qa[(k * NJ + i) * IK_BLOCK] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)id * 3 + i]);
+            len[k] = 0; solves[k] = 0; st[k] = 0; point_count[k] = 0; cf[k] = 0; outer[k] = 0; astep[k] = 0.0f; it[k] = 0;
+            state[k] = INIT;
+          } else {
+            ran_out = true;
+          }
+        }
+        before += (unsigned)__popc(need[k]);
+      }
+      exhausted = exhausted || ran_out;
+      if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
+      else pool_next += count;
+    }
+    bool any_live = false;
+#pragma unroll
+    for (int k = 0; k < S; ++k) any_live = any_live || state[k] != IDLE;
+    if (!__any_sync(FULL, any_live)) break;
+
+    // ---- one DLS pass for all slots of all lanes (ik_solver.py:58-83) ---------------------------------
+    V p[3], n2, ev[3], J[21];
+    ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
+    bool fin[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const bool solving = state[k] <= FB2;
+      fin[k] = solving && (it[k] >= a.k.max_iters || Slots<V>::get(n2, k) < thresh2);
+      Slots<V>::set(slim, k, (solving && !fin[k]) ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
+    }
+    ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+
+    // ---- post-processing: common transitions predicated, rejected solves divergent -----------------------
+    bool choose[S];  // slot needs the adaptive NORMAL waypoint of its next solve
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const bool init = state[k] == INIT;
+      const bool f = fin[k];
+      const bool conv = it[k] < a.k.max_iters;
+      const float err = finish_sqrt(Slots<V>::get(n2, k));
+      const int iters = it[k] + (conv ? 1 : 0);
+      const bool success = conv && (err < a.k.pos_thresh * 2.0f);                     // ik_solver.py:92
+      const bool acc = f && (state[k] == NORMAL ? (success && err < a.step_size * 2.0f) : success);  // :131/:154/:170
+      const bool rej = f && !acc;
+      const bool take = init || acc;  // INIT: start_pos = FK(q_start) (:91,:98); accepted solve (:131-138 / :154-160 / :170-176)
+      solves[k] += f ? 1 : 0;
+      c_n += f ? 1u : 0u; c_conv += (f && conv) ? 1u : 0u; c_iter += f ? (unsigned)iters : 0u;
+      const float px = Slots<V>::get(p[0], k), py = Slots<V>::get(p[1], k), pz = Slots<V>::get(p[2], k);
+      append_if(take, k, px, py, pz);
+      if (take) { Slots<V>::set(pos[0], k, px); Slots<V>::set(pos[1], k, py); Slots<V>::set(pos[2], k, pz); }
+      const bool keep = acc && it[k] > 0;  // q_current = result.q
+      if (keep) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) qa[(k * NJ + i) * IK_BLOCK] = Slots<V>::get(qs[i], k);
+      }
+      // rejected: the next solve restarts from q_current; INIT / accepted on the first pass: q_current itself
+      // (reloaded: the frozen limit clip may have moved an out-of-limits q_start)
+      if (init || (f && !keep)) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
+      }
+      point_count[k] += (acc && state[k] == NORMAL) ? 1 : 0;                          // :186 (fallbacks `continue`)
+      cf[k] = take ? 0 : cf[k];
+      state[k] = take ? (int)NORMAL : state[k];
+      choose[k] = take;
+      if (rej) {
+        // ---- rare: the scalar kernel's logic for a rejected solve, verbatim --------------------------------
+        const float qx = Slots<V>::get(pos[0], k), qy = Slots<V>::get(pos[1], k), qz = Slots<V>::get(pos[2], k);
+        const float gx = Slots<V>::get(goal[0], k), gy = Slots<V>::get(goal[1], k), gz = Slots<V>::get(goal[2], k);
+        const float dx = gx - qx, dy = gy - qy, dz = gz - qz;                          // :110 (pos of this solve)
+        const float dist = finish_sqrt((dx * dx + dy * dy) + dz * dz);                // :111
+        bool try_fb2 = false;
+        if (state[k] == NORMAL) {
+          ++cf[k];                                                                    // :142
+          if (cf[k] >= 3) {                                                           // :144
+            if (dist > astep[k] * 0.1f) state[k] = FB1; else try_fb2 = true;          // :150
+          } else {
+            ++cf[k];                                                                  // :183
+            choose[k] = true;                                                         // stays NORMAL, halved step next
+          }
+        } else if (state[k] == FB1) {
+          try_fb2 = true;
+        } else {                                                                      // FB2 failed
+          st[k] |= 1;                                                                 // :178-180
+          state[k] = DONE;
+          append_if(dist > a.pos_thresh, k, gx, gy, gz);                              // :189-191
+        }
+        if (try_fb2) {
+          const float an = finish_sqrt((dx * dx + 0.0f) + dz * dz);                   // :165
+          if (an > 0.001f) {
+            state[k] = FB2;
+          } else {
+            st[k] |= 1;
+            state[k] = DONE;
+            append_if(dist > a.pos_thresh, k, gx, gy, gz);
+          }
+        }
+        if (state[k] == FB1) {
+          const float f1 = astep[k] * 0.1f * rcp_approx(dist);                        // :149-151
+          Slots<V>::set(tgt[0], k, qx + dx * f1); Slots<V>::set(tgt[1], k, qy + dy * f1); Slots<V>::set(tgt[2], k, qz + dz * f1);
+        } else if (state[k] == FB2) {
+          const float an = finish_sqrt((dx * dx + 0.0f) + dz * dz);                   // :163-167
+          const float f2 = astep[k] * rcp_approx(an);
+          Slots<V>::set(tgt[0], k, qx + dx * f2); Slots<V>::set(tgt[1], k, qy + 0.0f * f2); Slots<V>::set(tgt[2], k, qz + dz * f2);
+        }
+      }
+      it[k] = (init || f) ? 0 : it[k] + 1;
+    }
+    // ---- the adaptive waypoint of the next NORMAL solve (:106-125), both slots in packed arithmetic ------
+    {
+      const V dx = v_sub(goal[0], pos[0]), dy = v_sub(goal[1], pos[1]), dz = v_sub(goal[2], pos[2]);   // :110
+      const V d2 = pnp_fma(dz, dz, pnp_fma(dy, dy, pnp_mul(dx, dx)));
+      V dist, stp, inv;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float dk = finish_sqrt(Slots<V>::get(d2, k));                           // :111 (== :106 norm)
+        float sk = fminf(fminf(a.step_size, dk * 0.1f), 0.02f);                       // :114-117
+        sk = cf[k] > 0 ? sk * 0.5f : sk;                                              // :118-119
+        Slots<V>::set(dist, k, dk);
+        Slots<V>::set(stp, k, sk);
+        Slots<V>::set(inv, k, rcp_approx(dk));
+      }
+      const V fr = pnp_mul(stp, inv);
+      const V nx = pnp_fma(dx, fr, pos[0]), ny = pnp_fma(dy, fr, pos[1]), nz = pnp_fma(dz, fr, pos[2]);  // :122-125
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float dk = Slots<V>::get(dist, k), sk = Slots<V>::get(stp, k);
+        const bool loop_ok = dk > a.pos_thresh && point_count[k] < a.max_traj_points;  // :106-107
+        const bool capped = loop_ok && outer[k] >= a.max_outer;
+        const bool go = choose[k] && loop_ok && !capped;
+        const bool far = dk > sk;
+        outer[k] += go ? 1 : 0;
+        astep[k] = go ? sk : astep[k];
+        if (go) {
+          Slots<V>::set(tgt[0], k, far ? Slots<V>::get(nx, k) : Slots<V>::get(goal[0], k));
+          Slots<V>::set(tgt[1], k, far ? Slots<V>::get(ny, k) : Slots<V>::get(goal[1], k));
+          Slots<V>::set(tgt[2], k, far ? Slots<V>::get(nz, k) : Slots<V>::get(goal[2], k));
+        }
+        if (choose[k] && !go) {  // end of the env (once per env)
+          st[k] |= capped ? 2 : 0;
+          state[k] = DONE;
+          append_if(dk > a.pos_thresh, k, Slots<V>::get(goal[0], k), Slots<V>::get(goal[1], k), Slots<V>::get(goal[2], k));  // :189-191
+        }
+      }
+    }
+  }
+  if (a.counters) {
+    c_n = warp_sum(c_n); c_conv = warp_sum(c_conv); c_iter = warp_sum(c_iter);
+    if (lane == 0) {
+      atomicAdd(a.counters + PNP_IK_CNT_N, c_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, c_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, c_iter);
+    }
+  }
+}
+
 // =============================================================================================
 // HER relabel + obs assembly: what `train.py:4` promises ("TQC(+HER)") and SB3's
 // HerReplayBuffer would do per sampled transition - done in one streaming pass:

@@ -90,3 +90,41 @@ def test_planner_batch_vs_c_oracle_fp64(golden, oracle_chain):
     for k in np.nonzero(same)[0][:256]:
         np.testing.assert_allclose(traj[k, : tl[k]], ref["traj"][k, : tl[k]], atol=1e-8)
     assert int(cnt[0]) == int(out["n_solves"].sum())
+
+
+def test_value_type_planner_pair_equals_lane_and_follows_the_reference(golden, oracle_chain):
+    """move_ik_plan_v_kernel<float> (what FP32 on the specialised tree runs) and <F2> (two envs per lane,
+    packed FP32): the same operations per env, so every output is bit-identical - including envs that go
+    through the fallback strategies, run into the round bound, or overflow the trajectory capacity.
+    Against the reference's own trajectories both keep the waypoint counts on ordinary moves and every
+    waypoint within 1e-4 m; against the scalar-template kernel (generic tree) the structure agrees."""
+    for n, seed in ((1, 0), (65, 1), (3000, 2), (70_001, 3)):
+        w = synthetic.waypoint_envs(n, seed=seed, device="cuda")   # part of the shelf box is out of reach
+        goal = w["goal"].clone()
+        goal[::41] = torch.tensor([2.5, 0.0, 0.5], device="cuda")  # plus some hopeless goals
+        kw = dict(max_outer=40, traj_cap=96)
+        outs = {}
+        for kin in ("spec_lane", "spec_pair", "generic"):
+            cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+            outs[kin] = (engine.move_ik_plan(w["q_start"], goal, engine.ik_params(kinematics=kin), counters=cnt, **kw), cnt)
+        (a, ca), (b, cb), (g, cg) = outs["spec_lane"], outs["spec_pair"], outs["generic"]
+        for f in ("traj_len", "n_solves", "status", "q_final", "traj"):
+            assert torch.equal(a[f], b[f]), (n, f)
+        assert torch.equal(ca, cb) and int(ca[0]) == int(a["n_solves"].sum())
+        assert int((a["status"] & 2).ne(0).sum()) >= (n + 40) // 41 - 1     # the hopeless goals hit the round bound
+        same = (a["traj_len"] == g["traj_len"]) & (a["status"] == g["status"])
+        assert float(same.float().mean()) > 0.98
+    g = golden
+    ref = c_oracle.move_plan(oracle_chain, g["q_start"], g["target"], traj_cap=g["traj"].shape[1])
+    clean = ref["n_solves"] < ref["traj_len"]
+    for kin in ("spec_lane", "spec_pair"):
+        out = engine.move_ik_plan(torch.tensor(g["q_start"], dtype=torch.float32, device="cuda"),
+                                  torch.tensor(g["target"], dtype=torch.float32, device="cuda"),
+                                  engine.ik_params(kinematics=kin), traj_cap=g["traj"].shape[1])
+        tl, traj = out["traj_len"].cpu().numpy(), out["traj"].double().cpu().numpy()
+        for k in np.nonzero(clean)[0]:
+            L = int(g["traj_len"][k])
+            assert tl[k] == L, (kin, k)
+            assert np.abs(traj[k, :L] - g["traj"][k, :L]).max() < 1e-4
+        for k in np.nonzero(~clean)[0]:
+            assert tl[k] == 202 and int(out["status"][k]) == 0

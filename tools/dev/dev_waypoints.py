@@ -45,3 +45,9 @@ cnt.zero_(); out = engine.move_ik_plan(qsm, goal_mx, p, counters=cnt); torch.cud
 cp = cnt.cpu().numpy()
 best = timeit(lambda: engine.move_ik_plan(qsm, goal_mx, p), warm=0, rep=2)
 print(f"planner mixed (1/64 unreachable) 2^18: best {best:.3f} ms -> {n_mx / best / 1e3:.2f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, mean it {cp[3] / cp[0]:.2f}, status!=0: {(out['status'] != 0).sum().item()}")
+for kin in ("generic", "spec_lane", "spec_pair"):
+    pk = engine.ik_params(kinematics=kin)
+    cnt.zero_(); engine.move_ik_plan(wp["q_start"], goal, pk, counters=cnt); torch.cuda.synchronize()
+    cp = cnt.cpu().numpy()
+    best = timeit(lambda: engine.move_ik_plan(wp["q_start"], goal, pk), warm=1, rep=3)
+    print(f"planner {kin:10s} reachable 2^18: best {best:.3f} ms -> {n_pl / best / 1e3:.1f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, mean it {cp[3] / cp[0]:.2f}")
