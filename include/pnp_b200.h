@@ -195,7 +195,8 @@ typedef struct PnpMoveParams {
   int32_t max_outer;        /* bound on planner rounds; 0 = 4*max_traj_points + 64.  The reference
                                has no bound and never returns for unreachable targets. */
   int32_t traj_cap;         /* points of storage per env in traj (>= 2) */
-  int32_t reserved;
+  int32_t compute_order;    /* pnp_move_ik_plan_ordered_* only: 1 = `order` is scratch, fill it first
+                               (pnp_move_plan_order_*) and then take the envs in that order; 0 = `order` is an input */
 } PnpMoveParams;
 #define PNP_MOVE_BROKE 1u      /* fallback strategies exhausted (reference `break`, move.py:178-180) */
 #define PNP_MOVE_CAPPED 2u     /* max_outer reached */
@@ -211,6 +212,25 @@ int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, c
 int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n, const PnpMoveParams* move,
                          const PnpIkParams* params, double* traj, int32_t* traj_len, double* q_final,
                          int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream);
+/* Longest plan first.  A plan is 2-200 warm-started solves long (move.py:106-137) and its length follows
+ * d0 = |target - FK(q_start)|; a launch that takes its envs in index order ends with most lanes idle behind
+ * the last long plans.  pnp_move_plan_order_* writes order[n] = the env indices sorted by descending d0
+ * (counting sort on 1/64 m buckets; the order inside a bucket is unspecified), pnp_move_ik_plan_ordered_*
+ * takes its envs in that order (order NULL = index order; with move->compute_order = 1 it fills `order`
+ * itself first, one call instead of two).  Every output stays indexed by env and is bit-identical to the
+ * unordered call; only the time changes. */
+int pnp_move_plan_order_f32(const float* q_start, const float* target, int64_t n, uint32_t* order,
+                            int32_t kinematics, void* stream);
+int pnp_move_plan_order_f64(const double* q_start, const double* target, int64_t n, uint32_t* order,
+                            int32_t kinematics, void* stream);
+int pnp_move_ik_plan_ordered_f32(const float* q_start, const float* target, uint32_t* order, int64_t n,
+                                 const PnpMoveParams* move, const PnpIkParams* params, float* traj,
+                                 int32_t* traj_len, float* q_final, int32_t* n_solves, int32_t* status,
+                                 unsigned long long* counters, void* stream);
+int pnp_move_ik_plan_ordered_f64(const double* q_start, const double* target, uint32_t* order, int64_t n,
+                                 const PnpMoveParams* move, const PnpIkParams* params, double* traj,
+                                 int32_t* traj_len, double* q_final, int32_t* n_solves, int32_t* status,
+                                 unsigned long long* counters, void* stream);
 
 /* ---- compute_reward / _is_success, row-wise --------------------------------------------- */
 /* Per row: achieved_goal[n,3], desired_goal[n,3], ee_pos[n,3], ee_quat[n,4] wxyz,

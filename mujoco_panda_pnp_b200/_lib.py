@@ -51,7 +51,7 @@ class PnpMoveParams(ctypes.Structure):
         ("max_traj_points", c_int32),
         ("max_outer", c_int32),
         ("traj_cap", c_int32),
-        ("reserved", c_int32),
+        ("compute_order", c_int32),
     ]
 
 
@@ -91,6 +91,10 @@ SIGNATURES = {
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pnp_move_ik_plan_f32": (c_int, [_P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_move_ik_plan_f64": (c_int, [_P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
+    "pnp_move_plan_order_f32": (c_int, [_P, _P, c_int64, _P, c_int32, _P]),
+    "pnp_move_plan_order_f64": (c_int, [_P, _P, c_int64, _P, c_int32, _P]),
+    "pnp_move_ik_plan_ordered_f32": (c_int, [_P, _P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
+    "pnp_move_ik_plan_ordered_f64": (c_int, [_P, _P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_reward_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
     "pnp_reward_f64": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
     "pnp_get_obs_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_double, _P, c_int32, _P]),

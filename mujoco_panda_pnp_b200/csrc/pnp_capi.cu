@@ -25,6 +25,7 @@ struct DeviceState {
   PnpTree tree{};
   int sm_count = 0;
   unsigned* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
+  unsigned* order_work = nullptr;  // plan-order histograms + cursors, one 2*PLAN_BUCKETS block per in-flight call
   unsigned ticket_seq = 0;
   int occ_ik[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool obs_smem_set = false;
@@ -468,6 +469,7 @@ int pnp_set_tree(const PnpTree* t) {
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
   if (!s->tickets) {
     CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&s->order_work, (size_t)kTicketSlots * 2 * pnp::PLAN_BUCKETS * sizeof(unsigned)));
     // sin(k * 2*pi/8192), k < 8192 + 2048, for the FP32 IK kernels' first-order table trig, evaluated in FP64
     static float tabv[pnp::kTrigVWords];
     for (int k = 0; k < pnp::kTrigVWords; ++k)
@@ -650,12 +652,46 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
 }
 
 template <typename T>
+int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* order, int32_t kinematics, void* stream) {
+  if (n < 0 || (n > 0 && (!q_start || !target || !order))) return fail(PNP_EINVAL, "move_plan_order: null pointer or negative n");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  bool spec;
+  if ((rc = pick_kin(s, kinematics, &spec))) return rc;
+  if (n == 0) return PNP_OK;
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "move_plan_order: n must be < 2^31 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* work;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    work = s->order_work + (size_t)(s->ticket_seq++ % kTicketSlots) * 2 * pnp::PLAN_BUCKETS;
+  }
+  CUDA_TRY(cudaMemsetAsync(work, 0, 2 * pnp::PLAN_BUCKETS * sizeof(unsigned), st));
+  const int per_block = pnp::PLAN_ORDER_BLOCK * pnp::PLAN_ORDER_PER_THREAD;
+  const int grid = (int)((n + per_block - 1) / per_block);
+  if (spec) {
+    pnp::plan_order_hist_kernel<T, pnp::SpecKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work);
+    pnp::plan_order_scatter_kernel<T, pnp::SpecKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order);
+  } else {
+    pnp::plan_order_hist_kernel<T, pnp::GenericKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work);
+    pnp::plan_order_scatter_kernel<T, pnp::GenericKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order);
+  }
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
+template <typename T>
 int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMoveParams* mp, const PnpIkParams* params,
                    T* traj, int32_t* traj_len, T* q_final, int32_t* n_solves, int32_t* status,
-                   unsigned long long* counters, void* stream) {
+                   unsigned long long* counters, uint32_t* order, void* stream) {
   int rc = check_ik_params(params);
   if (rc) return rc;
   if (!mp) return fail(PNP_EINVAL, "move params is NULL");
+  if (order && mp->compute_order) {
+    if ((rc = plan_order_impl<T>(q_start, target, n, order, params->kinematics, stream))) return rc;
+  }
   if (mp->traj_cap < 2 || mp->max_traj_points < 0 || !(mp->step_size > 0.0) || !(mp->pos_thresh >= 0.0))
     return fail(PNP_EINVAL, "move params: need traj_cap >= 2, max_traj_points >= 0, step_size > 0, pos_thresh >= 0");
   if (n < 0 || (n > 0 && (!q_start || !target || !traj || !traj_len || !q_final)))
@@ -682,6 +718,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   a.k = make_ik_const<T>(params);
   a.traj = traj; a.traj_len = traj_len; a.q_final = q_final; a.n_solves = n_solves; a.status = status;
   a.counters = counters;
+  a.order = order;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   if constexpr (std::is_same<T, float>::value) {
@@ -749,15 +786,40 @@ int pnp_ik_pose_solve_f64(const double* target_pos, const double* target_quat, c
                                  final_pos, final_quat, pos_err, rot_err, iters, flags, counters, stream);
 }
 
+int pnp_move_plan_order_f32(const float* q_start, const float* target, int64_t n, uint32_t* order, int32_t kinematics,
+                            void* stream) {
+  return plan_order_impl<float>(q_start, target, n, order, kinematics, stream);
+}
+int pnp_move_plan_order_f64(const double* q_start, const double* target, int64_t n, uint32_t* order, int32_t kinematics,
+                            void* stream) {
+  return plan_order_impl<double>(q_start, target, n, order, kinematics, stream);
+}
+
 int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, const PnpMoveParams* mp,
                          const PnpIkParams* params, float* traj, int32_t* traj_len, float* q_final,
                          int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
-  return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, stream);
+  return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, nullptr,
+                               stream);
+}
+int pnp_move_ik_plan_ordered_f32(const float* q_start, const float* target, uint32_t* order, int64_t n,
+                                 const PnpMoveParams* mp, const PnpIkParams* params, float* traj, int32_t* traj_len,
+                                 float* q_final, int32_t* n_solves, int32_t* status, unsigned long long* counters,
+                                 void* stream) {
+  return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, order,
+                               stream);
 }
 int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n, const PnpMoveParams* mp,
                          const PnpIkParams* params, double* traj, int32_t* traj_len, double* q_final,
                          int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
-  return move_plan_impl<double>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, stream);
+  return move_plan_impl<double>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, nullptr,
+                                stream);
+}
+int pnp_move_ik_plan_ordered_f64(const double* q_start, const double* target, uint32_t* order, int64_t n,
+                                 const PnpMoveParams* mp, const PnpIkParams* params, double* traj, int32_t* traj_len,
+                                 double* q_final, int32_t* n_solves, int32_t* status, unsigned long long* counters,
+                                 void* stream) {
+  return move_plan_impl<double>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, order,
+                                stream);
 }
 
 int pnp_reward_f32(const float* ag, const float* dg, const float* ee_pos, const float* ee_quat, const float* width,

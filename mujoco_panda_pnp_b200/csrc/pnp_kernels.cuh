@@ -1190,7 +1190,83 @@ struct MoveArgs {
   unsigned* ticket; // zeroed before launch
   unsigned chunk;   // envs a warp reserves per ticket atomic
   unsigned solo_warp;  // small batches: 4 warps load the trig table, only warp 0 works (see IkArgs)
+  const unsigned* order;  // nullable: env taken by the i-th ticket (longest plans first, plan_order_* kernels below)
 };
+
+// ---- longest plan first ------------------------------------------------------------------------------
+// A plan is 2-200 warm solves long and a lane owns one env at a time, so a launch ends with lanes idle
+// while the last long plans finish (2^18 envs in index order: 36 % over the balanced time).  The length of
+// a plan is, to 0.997 correlation, a function of d0 = |goal - FK(q_start)| (move.py:110-125: steps of
+// step_size, then the geometric tail), so the planner takes its envs in descending d0: a counting sort on
+// PLAN_BUCKETS buckets of d0, two small launches (histogram, scatter), FK recomputed instead of stored.
+// The order within a bucket is whatever the atomics give; the planner's outputs are indexed by env and do
+// not depend on it.
+constexpr int PLAN_BUCKETS = 128;     // 1/64 m per bucket, the last one open ended
+constexpr int PLAN_ORDER_BLOCK = 256;
+constexpr int PLAN_ORDER_PER_THREAD = 1;  // small batches want blocks, not work per thread: the sort sits in front of the planner
+
+template <typename T, typename Kin>
+__device__ __forceinline__ int plan_bucket(const T* q_start, const T* target, unsigned e) {
+  T q[NJ], p[3];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) q[i] = q_start[(size_t)e * NJ + i];
+  fk_position<T, Kin>(q, p);
+  const T dx = target[(size_t)e * 3] - p[0], dy = target[(size_t)e * 3 + 1] - p[1], dz = target[(size_t)e * 3 + 2] - p[2];
+  const float d0 = sqrtf((float)((dx * dx + dy * dy) + dz * dz));
+  const float b = fminf(d0 * 64.0f, (float)(PLAN_BUCKETS - 1));  // fminf drops a NaN: it lands with the longest plans
+  return PLAN_BUCKETS - 1 - (int)b;                              // bucket 0 = longest plans
+}
+
+// work[0..PLAN_BUCKETS) += histogram of the buckets (work zeroed before the launch)
+template <typename T, typename Kin>
+__global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_hist_kernel(const T* q_start, const T* target, unsigned n,
+                                                                            unsigned* work) {
+  __shared__ unsigned s_cnt[PLAN_BUCKETS];
+  if (threadIdx.x < PLAN_BUCKETS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned base = blockIdx.x * (PLAN_ORDER_BLOCK * PLAN_ORDER_PER_THREAD);
+#pragma unroll
+  for (int j = 0; j < PLAN_ORDER_PER_THREAD; ++j) {
+    const unsigned e = base + j * PLAN_ORDER_BLOCK + threadIdx.x;
+    if (e < n) atomicAdd(&s_cnt[plan_bucket<T, Kin>(q_start, target, e)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < PLAN_BUCKETS && s_cnt[threadIdx.x]) atomicAdd(&work[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// order[start(bucket) + rank within bucket] = env; work[PLAN_BUCKETS..2*PLAN_BUCKETS) are the bucket cursors
+template <typename T, typename Kin>
+__global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_scatter_kernel(const T* q_start, const T* target, unsigned n,
+                                                                               unsigned* work, unsigned* order) {
+  __shared__ unsigned s_hist[PLAN_BUCKETS], s_cnt[PLAN_BUCKETS], s_base[PLAN_BUCKETS];
+  if (threadIdx.x < PLAN_BUCKETS) { s_hist[threadIdx.x] = work[threadIdx.x]; s_cnt[threadIdx.x] = 0; }
+  __syncthreads();
+  const unsigned base = blockIdx.x * (PLAN_ORDER_BLOCK * PLAN_ORDER_PER_THREAD);
+  int bucket[PLAN_ORDER_PER_THREAD];
+  unsigned rank[PLAN_ORDER_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < PLAN_ORDER_PER_THREAD; ++j) {
+    const unsigned e = base + j * PLAN_ORDER_BLOCK + threadIdx.x;
+    bucket[j] = 0; rank[j] = 0;
+    if (e < n) {
+      bucket[j] = plan_bucket<T, Kin>(q_start, target, e);
+      rank[j] = atomicAdd(&s_cnt[bucket[j]], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < PLAN_BUCKETS) {
+    unsigned start = 0;
+    for (int b = 0; b < (int)threadIdx.x; ++b) start += s_hist[b];
+    const unsigned c = s_cnt[threadIdx.x];
+    s_base[threadIdx.x] = start + (c ? atomicAdd(&work[PLAN_BUCKETS + threadIdx.x], c) : 0u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PLAN_ORDER_PER_THREAD; ++j) {
+    const unsigned e = base + j * PLAN_ORDER_BLOCK + threadIdx.x;
+    if (e < n) order[s_base[bucket[j]] + rank[j]] = e;
+  }
+}
 
 // The planner's scalar bookkeeping in the two precisions: FP64 follows the reference's operations
 // literally (sqrt, a*b/c, (a/c)*b); FP32 - held to the 1e-4 m tolerance, not to bit parity - uses one
@@ -1262,7 +1338,7 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
         const unsigned rank = (unsigned)__popc(need & lanemask_lt);
         const unsigned idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
         if (idx < a.n) {
-          e = idx;
+          e = a.order ? a.order[idx] : idx;
 #pragma unroll
           for (int i = 0; i < NJ; ++i) q[i] = qs[i] = a.q_start[(size_t)e * NJ + i];
 #pragma unroll
@@ -1687,15 +1763,16 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
           if (id < a.n) {
-            env[k] = id;
+            const unsigned e = a.order ? a.order[id] : id;
+            env[k] = e;
 #pragma unroll
             for (int i = 0; i < NJ; ++i) {
-              const float v = a.q_start[(size_t)id * NJ + i];
+              const float v = a.q_start[(size_t)e * NJ + i];
               Slots<V>::set(qs[i], k, v);
               qa[(k * NJ + i) * IK_BLOCK] = v;
             }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)id * 3 + i]);
+            for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)e * 3 + i]);
             len[k] = 0; solves[k] = 0; st[k] = 0; point_count[k] = 0; cf[k] = 0; outer[k] = 0; astep[k] = 0.0f; it[k] = 0;
             state[k] = INIT;
           } else {

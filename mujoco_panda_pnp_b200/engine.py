@@ -302,10 +302,38 @@ def ik_pose_solve(target_pos: torch.Tensor, target_quat: torch.Tensor, q_init: t
                 converged=(flags & 1) != 0, success=(flags & 2) != 0)
 
 
+PLAN_ORDER_MIN = 1 << 16  # below this a launch has fewer envs than lanes: nothing to balance (2^14 measured slower)
+
+
+def move_plan_order(q_start: torch.Tensor, target: torch.Tensor, kinematics="auto") -> torch.Tensor:
+    """order[N] (int32 bit pattern of uint32): env indices by descending |target - FK(q_start)|, i.e. longest
+    MoveIKSkill plans first (skills/move.py:106-137); feed to move_ik_plan(order=...)."""
+    lib = _lib.load()
+    dt = q_start.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError("q_start must be float32 or float64")
+    q_start = _check_cuda("q_start", q_start, dt, (7,))
+    target = _check_cuda("target", target, dt, (3,))
+    n = q_start.shape[0]
+    if target.shape[0] != n:
+        raise ValueError("q_start and target disagree on N")
+    order = torch.empty((n,), dtype=torch.int32, device=q_start.device)
+    fn = lib.pnp_move_plan_order_f32 if dt == torch.float32 else lib.pnp_move_plan_order_f64
+    with torch.cuda.device(q_start.device):
+        kin = KINEMATICS[kinematics] if isinstance(kinematics, str) else int(kinematics)
+        _lib.check(fn(_ptr(q_start), _ptr(target), n, _ptr(order), kin, _stream()), "pnp_move_plan_order")
+    return order
+
+
 def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParams, pos_thresh: float = 0.01,
                  max_traj_points: int = 200, step_size: float = 0.01, max_outer: int = 0, traj_cap: int = 256,
-                 counters: Optional[torch.Tensor] = None):
+                 counters: Optional[torch.Tensor] = None, order="auto", out: Optional[dict] = None):
     """Batched MoveIKSkill.reset planner (skills/move.py:76-191): CUDA tensors f32 or f64.
+
+    ``order``: "auto" (longest plans first from N = 2^16 up, see move_plan_order), None (index order) or a
+    tensor from move_plan_order; it changes the schedule, never the result.  ``out``: the dict of a previous
+    call with the same N / traj_cap / dtype, whose buffers are then reused (trajectory rows beyond traj_len
+    keep their old contents); fresh trajectory storage is zero-filled.
 
     Returns dict(traj[N,traj_cap,3], traj_len[N], q_final[N,7], n_solves[N], status[N])."""
     lib = _lib.load()
@@ -319,16 +347,33 @@ def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParam
         raise ValueError("q_start and target disagree on N")
     dev = q_start.device
     mp = PnpMoveParams(float(pos_thresh), float(step_size), int(max_traj_points), int(max_outer), int(traj_cap), 0)
-    traj = torch.zeros((n, traj_cap, 3), dtype=dt, device=dev)
-    tlen = torch.empty((n,), dtype=torch.int32, device=dev)
-    qf = torch.empty((n, 7), dtype=dt, device=dev)
-    solves = torch.empty((n,), dtype=torch.int32, device=dev)
-    status = torch.empty((n,), dtype=torch.int32, device=dev)
-    fn = lib.pnp_move_ik_plan_f32 if dt == torch.float32 else lib.pnp_move_ik_plan_f64
+    if out is not None:
+        traj, tlen, qf, solves, status = (out[k] for k in ("traj", "traj_len", "q_final", "n_solves", "status"))
+        if (traj.shape != (n, traj_cap, 3) or traj.dtype != dt or traj.device != dev or not traj.is_contiguous()
+                or tlen.shape != (n,) or qf.shape != (n, 7) or qf.dtype != dt or solves.shape != (n,) or status.shape != (n,)):
+            raise ValueError("out does not match N / traj_cap / dtype / device of this call")
+    else:
+        traj = torch.zeros((n, traj_cap, 3), dtype=dt, device=dev)
+        tlen = torch.empty((n,), dtype=torch.int32, device=dev)
+        qf = torch.empty((n, 7), dtype=dt, device=dev)
+        solves = torch.empty((n,), dtype=torch.int32, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+    if isinstance(order, str):
+        if order != "auto":
+            raise ValueError("order must be 'auto', None or a tensor from move_plan_order")
+        order = None
+        if n >= PLAN_ORDER_MIN:  # scratch for the call to fill and use (PnpMoveParams.compute_order)
+            order = torch.empty((n,), dtype=torch.int32, device=dev)
+            mp.compute_order = 1
+    elif order is not None:
+        order = _check_cuda("order", order, torch.int32, ())
+        if order.shape[0] != n:
+            raise ValueError("order disagrees with q_start on N")
+    fn = lib.pnp_move_ik_plan_ordered_f32 if dt == torch.float32 else lib.pnp_move_ik_plan_ordered_f64
     with torch.cuda.device(dev):
         _lib.check(
-            fn(_ptr(q_start), _ptr(target), n, ctypes.byref(mp), ctypes.byref(params), _ptr(traj), _ptr(tlen), _ptr(qf),
-               _ptr(solves), _ptr(status), _ptr(counters), _stream()),
+            fn(_ptr(q_start), _ptr(target), _ptr(order), n, ctypes.byref(mp), ctypes.byref(params), _ptr(traj), _ptr(tlen),
+               _ptr(qf), _ptr(solves), _ptr(status), _ptr(counters), _stream()),
             "pnp_move_ik_plan",
         )
     return dict(traj=traj, traj_len=tlen, q_final=qf, n_solves=solves, status=status)

@@ -128,3 +128,47 @@ def test_value_type_planner_pair_equals_lane_and_follows_the_reference(golden, o
             assert np.abs(traj[k, :L] - g["traj"][k, :L]).max() < 1e-4
         for k in np.nonzero(~clean)[0]:
             assert tl[k] == 202 and int(out["status"][k]) == 0
+
+
+def test_longest_plan_first_order_is_a_permutation_and_changes_nothing_but_the_schedule():
+    """pnp_move_plan_order: env indices by descending |goal - FK(q_start)| (the length of a MoveIKSkill plan
+    follows it, move.py:106-137).  The planner's outputs are indexed by env, so every one of them must be
+    bit-identical with and without the order - f32 value-type kernels, the generic-tree kernel and f64."""
+    for n, seed in ((1, 0), (33, 1), (1025, 2), (40_000, 3)):
+        w = synthetic.waypoint_envs(n, seed=seed, device="cuda")
+        goal = w["goal"].clone()
+        goal[::57] = torch.tensor([2.5, 0.0, 0.5], device="cuda")
+        for dtype, kins in ((torch.float32, ("spec_lane", "spec_pair", "generic")), (torch.float64, ("specialized",))):
+            qs, gl = w["q_start"].to(dtype), goal.to(dtype)
+            for kin in kins:
+                order = engine.move_plan_order(qs, gl, kin)
+                o = order.cpu().numpy().astype(np.int64)
+                assert np.array_equal(np.sort(o), np.arange(n)), (n, kin)
+                p0 = engine.fk_jac(qs, want_quat=False, want_jac=False, kinematics="generic" if kin == "generic" else "auto")[0]
+                d0 = (gl - p0).norm(dim=1).cpu().numpy()[o]
+                bucket = np.minimum((d0 * 64.0).astype(np.int64), 127)
+                assert np.all(np.diff(bucket) <= 1)   # descending up to the float rounding of a bucket edge
+                assert np.all(np.diff(bucket.astype(np.float64)).cumsum() <= 1)
+                pk = engine.ik_params(kinematics=kin)
+                kw = dict(max_outer=30, traj_cap=80)
+                ca, cb = (torch.zeros(4, dtype=torch.int64, device="cuda") for _ in range(2))
+                a = engine.move_ik_plan(qs, gl, pk, counters=ca, order=None, **kw)
+                b = engine.move_ik_plan(qs, gl, pk, counters=cb, order=order, **kw)
+                for f in ("traj_len", "n_solves", "status", "q_final", "traj"):
+                    assert torch.equal(a[f], b[f]), (n, kin, f)
+                assert torch.equal(ca, cb)
+    # "auto" orders from 2^16 envs up (one call: PnpMoveParams.compute_order) and reuses the buffers of a
+    # previous call when asked to
+    n = engine.PLAN_ORDER_MIN
+    w = synthetic.waypoint_envs(n, seed=9, device="cuda")
+    pk = engine.ik_params()
+    a = engine.move_ik_plan(w["q_start"], w["goal"], pk, order=None, traj_cap=64, max_outer=30)
+    keep = {k: v.clone() for k, v in a.items()}
+    b = engine.move_ik_plan(w["q_start"], w["goal"], pk, traj_cap=64, max_outer=30, out=a)
+    assert b["traj"].data_ptr() == a["traj"].data_ptr()
+    for f in ("traj_len", "n_solves", "status", "q_final", "traj"):
+        assert torch.equal(keep[f], b[f]), f
+    with pytest.raises(ValueError):
+        engine.move_ik_plan(w["q_start"], w["goal"], pk, traj_cap=32, out=a)
+    with pytest.raises(ValueError):
+        engine.move_ik_plan(w["q_start"], w["goal"], pk, order=torch.zeros(3, dtype=torch.int32, device="cuda"))

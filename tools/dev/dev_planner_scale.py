@@ -13,15 +13,15 @@ def timeit(fn, warm=1, rep=3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return min(ts)
-for logn in (16, 18, 20):
+for logn in (14, 16, 18, 20):
     n = 1 << logn
     wp = synthetic.reachable_move_envs(n, tree.lower, tree.upper, seed=1, device=dev)
     goal = engine.fk_jac(wp["q_goal"], want_quat=False, want_jac=False)[0]
-    for kin in ("spec_lane", "spec_pair"):
+    for kin, order in (("spec_lane", None), ("spec_lane", "auto"), ("spec_pair", "auto")):
         pk = engine.ik_params(kinematics=kin)
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
         out = engine.move_ik_plan(wp["q_start"], goal, pk, counters=cnt, traj_cap=128); torch.cuda.synchronize()
         cp = cnt.cpu().numpy()
-        best = timeit(lambda: engine.move_ik_plan(wp["q_start"], goal, pk, traj_cap=128))
-        print(f"planner {kin} 2^{logn}: {best:.3f} ms -> {n / best / 1e3:.1f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, max len {int(out['traj_len'].max())}")
+        best = timeit(lambda: engine.move_ik_plan(wp["q_start"], goal, pk, traj_cap=128, order=order, out=out))
+        print(f"planner {kin} order={order} 2^{logn}: {best:.3f} ms -> {n / best / 1e3:.1f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, max len {int(out['traj_len'].max())}")
     del wp, goal, out
