@@ -566,16 +566,16 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   a.counters = counters;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
-  // specialised tree: the value-type kernels (same arithmetic in both): two envs per lane once the
-  // batch oversubscribes the machine, one per lane below that; other trees: the scalar-template kernel
-  const bool pair = spec && params->kinematics != PNP_KIN_SPEC_LANE &&
-                    (params->kinematics == PNP_KIN_SPEC_PAIR || n >= (long long)s->sm_count * 4096);
+  // specialised tree: the value-type kernels (same arithmetic in both), one env per lane unless two are asked
+  // for (with the fused accept / first-iteration pass the bookkeeping weighs more than the packed arithmetic
+  // saves: 2^20 envs x 50, 0.81 ms against 0.87); other trees: the scalar-template kernel
+  const bool pair = spec && params->kinematics == PNP_KIN_SPEC_PAIR;
   const int S = pair ? 2 : 1;
   int occ = 4;
   if (!small) {
     cudaError_t e = !spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_kernel<float, pnp::GenericKin>, pnp::IK_BLOCK, 0)
-                    : pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<pnp::F2>, pnp::IK_BLOCK, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<float>, pnp::IK_BLOCK, 0);
+                    : pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<pnp::F2, true>, pnp::IK_BLOCK, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_waypoints_v_kernel<float, true>, pnp::IK_BLOCK, 0);
     if (e != cudaSuccess || occ < 1) occ = 4;
   }
   const long long lanes_needed = (n + S - 1) / S;
@@ -587,10 +587,16 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   a.solo_warp = small ? 1u : 0u;
   if (!spec)
     pnp::ik_waypoints_kernel<float, pnp::GenericKin><<<grid, block, 0, st>>>(a);
-  else if (pair)
-    pnp::ik_waypoints_v_kernel<pnp::F2><<<grid, block, 0, st>>>(a);
-  else
-    pnp::ik_waypoints_v_kernel<float><<<grid, block, 0, st>>>(a);
+  else {
+    // PNP_WAYPOINT_FUSE=0 (read per call; tests and measurements only): the accepting pass of a solve is not also
+    // the first iteration of the next one - one pass more per solve, bit-identical results
+    const char* fe = getenv("PNP_WAYPOINT_FUSE");
+    const bool fuse = !fe || atoi(fe) != 0;
+    if (pair && fuse) pnp::ik_waypoints_v_kernel<pnp::F2, true><<<grid, block, 0, st>>>(a);
+    else if (pair) pnp::ik_waypoints_v_kernel<pnp::F2, false><<<grid, block, 0, st>>>(a);
+    else if (fuse) pnp::ik_waypoints_v_kernel<float, true><<<grid, block, 0, st>>>(a);
+    else pnp::ik_waypoints_v_kernel<float, false><<<grid, block, 0, st>>>(a);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;
@@ -728,8 +734,8 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
       const int S = pair ? 2 : 1;
       int occv = 4;
       if (!small) {
-        cudaError_t e = pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<pnp::F2>, pnp::IK_BLOCK, 0)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float>, pnp::IK_BLOCK, 0);
+        cudaError_t e = pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<pnp::F2, true>, pnp::IK_BLOCK, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float, true>, pnp::IK_BLOCK, 0);
         if (e != cudaSuccess || occv < 1) occv = 4;
       }
       const long long lanes_needed = (n + S - 1) / S;
@@ -738,10 +744,14 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
       chunkv = chunkv < 32 * S ? 32 * S : (chunkv > 128 ? 128 : chunkv);
       a.chunk = (unsigned)(chunkv & ~31ll);
       a.solo_warp = small ? 1u : 0u;
-      if (pair)
-        pnp::move_ik_plan_v_kernel<pnp::F2><<<gridv, block, 0, st>>>(a);
-      else
-        pnp::move_ik_plan_v_kernel<float><<<gridv, block, 0, st>>>(a);
+      // PNP_WAYPOINT_FUSE=0 (read per call; tests and measurements only): a separate pass for the first
+      // iteration of every solve, bit-identical results
+      const char* fe = getenv("PNP_WAYPOINT_FUSE");
+      const bool fuse = !fe || atoi(fe) != 0;
+      if (pair && fuse) pnp::move_ik_plan_v_kernel<pnp::F2, true><<<gridv, block, 0, st>>>(a);
+      else if (pair) pnp::move_ik_plan_v_kernel<pnp::F2, false><<<gridv, block, 0, st>>>(a);
+      else if (fuse) pnp::move_ik_plan_v_kernel<float, true><<<gridv, block, 0, st>>>(a);
+      else pnp::move_ik_plan_v_kernel<float, false><<<gridv, block, 0, st>>>(a);
       ++g_launches;
       CUDA_TRY(cudaGetLastError());
       return PNP_OK;

@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_waypoints_kernel(const WaypointAr
 // accepted joint vector of each slot lives in shared memory (written on accept, read on a rejected
 // solve and at write-back), which keeps the kernel at 4 blocks per SM.
 // ---------------------------------------------------------------------------------------------
-template <typename V>
+template <typename V, bool kFuse>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_waypoints_v_kernel(const WaypointArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
@@ -860,19 +860,22 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
     V p[3], n2, ev[3], J[21];
     ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
-    bool fin[S];
+    bool fin[S], iterating[S], reload[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const bool running = state[k] == RUN;
       fin[k] = running && (it[k] >= a.k.max_iters || Slots<V>::get(n2, k) < thresh2);
-      Slots<V>::set(slim, k, (running && !fin[k]) ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
+      iterating[k] = running && !fin[k];
+      Slots<V>::set(slim, k, iterating[k] ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
     }
-    ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+    // kFuse: the update moves behind the bookkeeping, so that the pass in which a solve is accepted (or the INIT
+    // pass) is also the first iteration of the next solve - same q, hence the same p and J, only the target changes
+    if (!kFuse) ik_step_v<V>(qs, J, ev, a.k.damping, slim);
 
     // ---- bookkeeping, branch-free: with ~2 passes per warm solve half of the slots finish a solve in
     //      every pass, so this runs as predicated straight-line code; the waypoint geometry of both
     //      slots (move.py:110-125) is packed arithmetic ---------------------------------------------------
-    bool adv[S];
+    bool adv[S], fused[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const bool init = state[k] == INIT;
@@ -891,10 +894,12 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       }
       // rejected solve: the next one restarts from q_current; INIT pass / solve accepted on its first
       // pass: q_current itself, reloaded because the frozen limit clip may have moved an out-of-limits q_start
-      if (init || (f && !keep)) {
+      reload[k] = init || (f && !keep);
+      if (!kFuse && reload[k]) {
 #pragma unroll
         for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
       }
+      fused[k] = init || accept;  // the next solve starts from the q this pass was evaluated at
       if (init || accept) {                                                          // :91 start_pos / :136
 #pragma unroll
         for (int i = 0; i < 3; ++i) Slots<V>::set(pos[i], k, Slots<V>::get(p[i], k));
@@ -940,6 +945,32 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           if (a.n_accepted) a.n_accepted[id] = accepted[k];
           if (a.iters_total) a.iters_total[id] = iters_sum[k];
           state[k] = IDLE;
+        }
+      }
+    }
+    if (kFuse) {
+      // error of the new targets at this pass's p: what the first pass of the next solve would compute
+      V en[3];
+      en[0] = v_sub(tgt[0], p[0]); en[1] = v_sub(tgt[1], p[1]); en[2] = v_sub(tgt[2], p[2]);
+      const V n2n = pnp_fma(en[2], en[2], pnp_fma(en[1], en[1], pnp_mul(en[0], en[0])));
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        // a new solve that is already within pos_thresh of its target (or an env that is done, or a rejected
+        // solve, which restarts from another q) stays frozen and is handled by the next pass as before
+        fused[k] = fused[k] && adv[k] && state[k] == RUN && a.k.max_iters > 0 && !(Slots<V>::get(n2n, k) < thresh2);
+        if (fused[k]) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) Slots<V>::set(ev[i], k, Slots<V>::get(en[i], k));
+          it[k] = 1;
+        }
+        Slots<V>::set(slim, k, (iterating[k] || fused[k]) ? a.k.step_limit : 0.0f);
+      }
+      ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        if (reload[k] && !fused[k]) {
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
         }
       }
     }
@@ -1687,7 +1718,7 @@ __device__ __forceinline__ void stg1_if(bool pred, float* ptr, float x) {
                :: "r"((unsigned)pred), "l"(ptr), "f"(x) : "memory");
 }
 
-template <typename V>
+template <typename V, bool kFuse>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) move_ik_plan_v_kernel(const MoveArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
@@ -1793,14 +1824,18 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     // ---- one DLS pass for all slots of all lanes (ik_solver.py:58-83) ---------------------------------
     V p[3], n2, ev[3], J[21];
     ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
-    bool fin[S];
+    bool fin[S], iterating[S], reload[S], fused[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const bool solving = state[k] <= FB2;
       fin[k] = solving && (it[k] >= a.k.max_iters || Slots<V>::get(n2, k) < thresh2);
-      Slots<V>::set(slim, k, (solving && !fin[k]) ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
+      iterating[k] = solving && !fin[k];
+      Slots<V>::set(slim, k, iterating[k] ? a.k.step_limit : 0.0f);  // INIT / finishing / idle slots: frozen
     }
-    ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+    // kFuse: the update moves behind the post-processing, so that the pass in which a solve is accepted (or the
+    // INIT pass) is also the first iteration of the next solve - q_current is the q this pass was evaluated at,
+    // hence the same p and J, only the target changes (see ik_waypoints_v_kernel)
+    if (!kFuse) ik_step_v<V>(qs, J, ev, a.k.damping, slim);
 
     // ---- post-processing: common transitions predicated, rejected solves divergent -----------------------
     bool choose[S];  // slot needs the adaptive NORMAL waypoint of its next solve
@@ -1827,7 +1862,9 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       }
       // rejected: the next solve restarts from q_current; INIT / accepted on the first pass: q_current itself
       // (reloaded: the frozen limit clip may have moved an out-of-limits q_start)
-      if (init || (f && !keep)) {
+      reload[k] = init || (f && !keep);
+      fused[k] = take;
+      if (!kFuse && reload[k]) {
 #pragma unroll
         for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
       }
@@ -1903,6 +1940,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         const bool far = dk > sk;
         outer[k] += go ? 1 : 0;
         astep[k] = go ? sk : astep[k];
+        fused[k] = fused[k] && go;
         if (go) {
           Slots<V>::set(tgt[0], k, far ? Slots<V>::get(nx, k) : Slots<V>::get(goal[0], k));
           Slots<V>::set(tgt[1], k, far ? Slots<V>::get(ny, k) : Slots<V>::get(goal[1], k));
@@ -1912,6 +1950,31 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           st[k] |= capped ? 2 : 0;
           state[k] = DONE;
           append_if(dk > a.pos_thresh, k, Slots<V>::get(goal[0], k), Slots<V>::get(goal[1], k), Slots<V>::get(goal[2], k));  // :189-191
+        }
+      }
+    }
+    if (kFuse) {
+      // error of the new targets at this pass's p: what the first pass of the next solve would compute
+      V en[3];
+      en[0] = v_sub(tgt[0], p[0]); en[1] = v_sub(tgt[1], p[1]); en[2] = v_sub(tgt[2], p[2]);
+      const V n2n = pnp_fma(en[2], en[2], pnp_fma(en[1], en[1], pnp_mul(en[0], en[0])));
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        // a new solve already within pos_thresh of its target stays frozen and is finished by the next pass
+        fused[k] = fused[k] && a.k.max_iters > 0 && !(Slots<V>::get(n2n, k) < thresh2);
+        if (fused[k]) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) Slots<V>::set(ev[i], k, Slots<V>::get(en[i], k));
+          it[k] = 1;
+        }
+        Slots<V>::set(slim, k, (iterating[k] || fused[k]) ? a.k.step_limit : 0.0f);
+      }
+      ik_step_v<V>(qs, J, ev, a.k.damping, slim);
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        if (reload[k] && !fused[k]) {
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
         }
       }
     }

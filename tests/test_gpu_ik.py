@@ -336,6 +336,32 @@ def test_waypoint_pair_kernel_is_bit_identical_to_lane_kernel(tree, oracle_chain
         assert torch.equal(r["q"], q0) and int(r["n_accepted"].sum()) == 0
 
 
+def test_waypoint_fused_pass_is_bit_identical_to_separate_passes(tree, monkeypatch):
+    """The pass in which a warm solve is accepted (or the INIT pass) is also the first iteration of the next
+    solve: same q, so the same FK and Jacobian, only the target changes (move.py:128-137).  One pass less
+    per solve, and every output bit-identical to the kernel that spends a separate pass on it
+    (PNP_WAYPOINT_FUSE=0) - including rejected solves, iteration caps of 1 and 2, targets already within
+    pos_thresh, and starts outside the joint limits."""
+    cases = [(1, 50, {}), (65, 50, {}), (3000, 50, {}), (3000, 12, dict(max_iters=1)), (3000, 12, dict(max_iters=2)),
+             (3000, 20, dict(pos_thresh=5e-3, damping=0.05)), (100_001, 30, {})]
+    for n, steps, kw in cases:
+        w = synthetic.waypoint_envs(n, seed=n % 7 + 1, device="cuda")
+        q0 = w["q_start"].clone()
+        q0[::5, 0] = 3.1     # beyond joint 1's limit: the first solve starts from it unclipped
+        q0[1::9, 3] = 0.2    # beyond joint 4's upper limit
+        for kin in ("spec_lane", "spec_pair"):
+            outs = []
+            for fuse in ("0", "1"):
+                monkeypatch.setenv("PNP_WAYPOINT_FUSE", fuse)
+                cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+                outs.append((engine.ik_waypoints(q0, w["goal"], steps, engine.ik_params(kinematics=kin, **kw), counters=cnt), cnt))
+            (a, ca), (b, cb) = outs
+            for f in ("q", "pos", "n_accepted", "iters_total"):
+                assert torch.equal(a[f], b[f]), (n, steps, kw, kin, f)
+            assert torch.equal(ca, cb) and int(ca[0]) > 0
+    monkeypatch.delenv("PNP_WAYPOINT_FUSE")
+
+
 def test_single_query_mailbox_path_equals_batch_kernel(kin_model, golden_ik, tree):
     """JacobianIKController.solve goes through pnp_ik_solve_one_host_f32 (mapped pinned mailbox, one
     launch, no memcpy); it runs the arithmetic of the batch kernels, so a batch of one gives the same bits."""

@@ -172,3 +172,30 @@ def test_longest_plan_first_order_is_a_permutation_and_changes_nothing_but_the_s
         engine.move_ik_plan(w["q_start"], w["goal"], pk, traj_cap=32, out=a)
     with pytest.raises(ValueError):
         engine.move_ik_plan(w["q_start"], w["goal"], pk, order=torch.zeros(3, dtype=torch.int32, device="cuda"))
+
+
+def test_planner_fused_pass_is_bit_identical_to_separate_passes(monkeypatch):
+    """The pass that accepts a solve (or takes FK(q_start)) is also the first iteration of the next solve
+    (same q_current, hence the same FK and Jacobian; only the target changes, move.py:128-137): one pass
+    less per solve and bit-identical outputs against PNP_WAYPOINT_FUSE=0, which spends a separate pass -
+    with fallback strategies, hopeless goals, iteration caps of 1 and 2, and starts outside the joint limits."""
+    for n, kw_ik in ((1, {}), (67, {}), (5000, {}), (5000, dict(max_iters=1)), (5000, dict(max_iters=2)),
+                     (5000, dict(pos_thresh=5e-3, damping=0.05)), (70_000, {})):
+        w = synthetic.waypoint_envs(n, seed=n % 11 + 2, device="cuda")
+        goal = w["goal"].clone()
+        goal[::43] = torch.tensor([2.5, 0.0, 0.5], device="cuda")
+        q0 = w["q_start"].clone()
+        q0[::5, 0] = 3.1
+        q0[1::9, 3] = 0.2
+        for kin in ("spec_lane", "spec_pair"):
+            outs = []
+            for fuse in ("0", "1"):
+                monkeypatch.setenv("PNP_WAYPOINT_FUSE", fuse)
+                cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+                outs.append((engine.move_ik_plan(q0, goal, engine.ik_params(kinematics=kin, **kw_ik), counters=cnt,
+                                                 max_outer=40, traj_cap=96), cnt))
+            (a, ca), (b, cb) = outs
+            for f in ("traj_len", "n_solves", "status", "q_final", "traj"):
+                assert torch.equal(a[f], b[f]), (n, kw_ik, kin, f)
+            assert torch.equal(ca, cb) and int(ca[0]) > 0
+    monkeypatch.delenv("PNP_WAYPOINT_FUSE")

@@ -17,11 +17,11 @@ for logn in (14, 16, 18, 20):
     n = 1 << logn
     wp = synthetic.reachable_move_envs(n, tree.lower, tree.upper, seed=1, device=dev)
     goal = engine.fk_jac(wp["q_goal"], want_quat=False, want_jac=False)[0]
-    for kin, order in (("spec_lane", None), ("spec_lane", "auto"), ("spec_pair", "auto")):
-        pk = engine.ik_params(kinematics=kin)
+    for kin, order, fuse in (("spec_lane", "auto", "0"), ("spec_lane", "auto", "1"), ("spec_pair", "auto", "1")):
+        pk = engine.ik_params(kinematics=kin); os.environ["PNP_WAYPOINT_FUSE"] = fuse
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
         out = engine.move_ik_plan(wp["q_start"], goal, pk, counters=cnt, traj_cap=128); torch.cuda.synchronize()
         cp = cnt.cpu().numpy()
         best = timeit(lambda: engine.move_ik_plan(wp["q_start"], goal, pk, traj_cap=128, order=order, out=out))
-        print(f"planner {kin} order={order} 2^{logn}: {best:.3f} ms -> {n / best / 1e3:.1f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, max len {int(out['traj_len'].max())}")
+        print(f"planner {kin} order={order} fuse={fuse} 2^{logn}: {best:.3f} ms -> {n / best / 1e3:.1f} M plans/s, {cp[0] / best / 1e6:.2f} G solves/s, max len {int(out['traj_len'].max())}")
     del wp, goal, out
