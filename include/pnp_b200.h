@@ -83,11 +83,13 @@ typedef struct PnpIkParams {
 #define PNP_KIN_AUTO 0         /* specialised code when the uploaded tree matches it, else generic */
 #define PNP_KIN_GENERIC 1      /* always read the tree from __constant__ memory */
 #define PNP_KIN_SPECIALIZED 2  /* require the build-time specialised tree (error if mismatch) */
-/* FP32 position IK only (pnp_ik_solve_f32 / _packed_f32 and the host-buffer variants); elsewhere
- * they mean PNP_KIN_SPECIALIZED.  Same arithmetic, bit-identical results, different lane mapping: */
-#define PNP_KIN_SPEC_LANE 3    /* one query per lane, explicit-FMA specialised code */
-#define PNP_KIN_SPEC_PAIR 4    /* two queries per lane on packed FFMA2/FMUL2/FADD2 (what AUTO picks for
-                                  large FP32 batches on the specialised tree) */
+/* FP32 position IK (pnp_ik_solve_f32 / _packed_f32 and the host-buffer variants), pnp_ik_waypoints_f32 and
+ * pnp_move_ik_plan*_f32; elsewhere they mean PNP_KIN_SPECIALIZED.  Same arithmetic, bit-identical results,
+ * different lane mapping: */
+#define PNP_KIN_SPEC_LANE 3    /* one query / env per lane, explicit-FMA specialised code (what AUTO picks for the
+                                  waypoint and planner kernels and for small IK batches) */
+#define PNP_KIN_SPEC_PAIR 4    /* two queries / envs per lane on packed FFMA2/FMUL2/FADD2 (what AUTO picks for
+                                  FP32 IK batches of >= 4096 queries per SM on the specialised tree) */
 
 /* flags[] bits written by the IK kernels (IKResult.converged / .success, ik_solver.py:92-100) */
 #define PNP_IK_CONVERGED 1u
