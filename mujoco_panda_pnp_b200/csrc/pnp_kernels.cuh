@@ -1027,6 +1027,41 @@ __device__ __forceinline__ void quat2vel(const T* q, T* v) {
   v[0] = q[1] * sc; v[1] = q[2] * sc; v[2] = q[3] * sc;
 }
 
+// FP32 pose kernel: the same, with x*rsqrt(x) and one rsqrt for the division (the pose extension is held to
+// tolerances, not to bit parity - there is no reference arithmetic for it)
+__device__ __forceinline__ void quat2vel_fast(const float* q, float* v) {
+  const float s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const float r = s2 > 0.0f ? rsqrtf(s2) : 0.0f;
+  float speed = 2.0f * atan2f(s2 * r, q[0]);
+  if (speed > 3.14159265358979323846f) speed -= 6.28318530717958647692f;
+  const float sc = speed * r;
+  v[0] = q[1] * sc; v[1] = q[2] * sc; v[2] = q[3] * sc;
+}
+__device__ __forceinline__ void quat2vel_fast(const double* q, double* v) { quat2vel<double>(q, v); }
+
+// mju_mat2Quat with the case chosen by selects instead of branches (the four cases of random targets diverge)
+// and rsqrt for the square roots / divisions; same case rule and formulas as mat2quat<T>
+__device__ __forceinline__ void mat2quat_fast(const float* m, float* q) {
+  const bool c0 = m[0] + m[4] + m[8] > 0.0f;
+  const bool c1 = !c0 && m[0] > m[4] && m[0] > m[8];
+  const bool c2 = !c0 && !c1 && m[4] > m[8];
+  const float s0 = (c0 || c1) ? m[0] : -m[0];
+  const float s1 = (c0 || c2) ? m[4] : -m[4];
+  const float s2 = (c0 || (!c1 && !c2)) ? m[8] : -m[8];
+  const float t = 1.0f + s0 + s1 + s2;
+  const float r = rsqrtf(t);
+  const float big = 0.5f * t * r, k = 0.5f * r;
+  const float a75 = k * (m[7] - m[5]), a26 = k * (m[2] - m[6]), a31 = k * (m[3] - m[1]);
+  const float b13 = k * (m[1] + m[3]), b26 = k * (m[2] + m[6]), b57 = k * (m[5] + m[7]);
+  float w = c0 ? big : (c1 ? a75 : (c2 ? a26 : a31));
+  float x = c0 ? a75 : (c1 ? big : (c2 ? b13 : b26));
+  float y = c0 ? a26 : (c1 ? b13 : (c2 ? big : b57));
+  float z = c0 ? a31 : (c1 ? b26 : (c2 ? b57 : big));
+  const float inv = rsqrtf(w * w + x * x + y * y + z * z);
+  q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = z * inv;
+}
+__device__ __forceinline__ void mat2quat_fast(const double* m, double* q) { mat2quat<double>(m, q); }
+
 // solve the SPD system A y = b, A given by its lower triangle L[i][j] (j <= i), in place (LDL^T)
 template <typename T, int N>
 __device__ __forceinline__ void ldlt_solve(T (&A)[N][N], T (&b)[N]) {
@@ -1037,7 +1072,7 @@ __device__ __forceinline__ void ldlt_solve(T (&A)[N][N], T (&b)[N]) {
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k] * dg[k];
     dg[j] = d;
-    dinv[j] = T(1) / d;
+    dinv[j] = rcp_t(d);  // FP32: one MUFU.RCP (1 ulp); FP64: 1.0 / d
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
       T v = A[i][j];
@@ -1122,18 +1157,18 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArg
     for (int i = 0; i < NJ; ++i) trig(q[i] - Kin::template qref<T>(i), &s[i], &c[i]);
     T pp[3], J[42], R[9], qcur[4];
     Kin::template fk_full<T>(s, c, pp, J, R);
-    mat2quat<T>(R, qcur);
+    mat2quat_fast(R, qcur);
     // err_quat = target (x) conj(current); rotation vector in the world frame
     const T eq[4] = {tq[0] * qcur[0] + tq[1] * qcur[1] + tq[2] * qcur[2] + tq[3] * qcur[3],
                      -tq[0] * qcur[1] + tq[1] * qcur[0] - tq[2] * qcur[3] + tq[3] * qcur[2],
                      -tq[0] * qcur[2] + tq[1] * qcur[3] + tq[2] * qcur[0] - tq[3] * qcur[1],
                      -tq[0] * qcur[3] - tq[1] * qcur[2] + tq[2] * qcur[1] + tq[3] * qcur[0]};
     T rv[3];
-    quat2vel<T>(eq, rv);
+    quat2vel_fast(eq, rv);
     T err[6] = {tp[0] - pp[0], tp[1] - pp[1], tp[2] - pp[2], rv[0] * a.rot_weight, rv[1] * a.rot_weight,
                 rv[2] * a.rot_weight};
-    const T pe = sqrt_t((err[0] * err[0] + err[1] * err[1]) + err[2] * err[2]);
-    const T re = sqrt_t((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+    const T pe = finish_sqrt((err[0] * err[0] + err[1] * err[1]) + err[2] * err[2]);
+    const T re = finish_sqrt((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
     const bool last = it >= a.k.max_iters;
     const bool conv = !last && (pe < a.k.pos_thresh) && (re < a.rot_thresh);
     if (active && (conv || last)) {
