@@ -199,3 +199,42 @@ def test_planner_fused_pass_is_bit_identical_to_separate_passes(monkeypatch):
                 assert torch.equal(a[f], b[f]), (n, kw_ik, kin, f)
             assert torch.equal(ca, cb) and int(ca[0]) > 0
     monkeypatch.delenv("PNP_WAYPOINT_FUSE")
+
+
+def test_planner_full_size_properties():
+    """The bench's planner workload (2^20 reachable plans, one launch, longest plan first) through properties that
+    need no oracle (skills/move.py:91-191): the trajectory starts at FK(q_start); every step between accepted
+    points is at most step_size + the accept tolerance; the plan ends within pos_thresh of the goal, the goal
+    itself being appended when the last accepted point is further away; q_final reproduces the last accepted
+    point under FK; the solve counters agree with the per-env counts; no env breaks, caps or overflows."""
+    n = 1 << 20
+    tree = KinematicTree.from_mjcf()
+    engine.set_tree(tree)
+    w = synthetic.reachable_move_envs(n, tree.lower, tree.upper, seed=11, device="cuda")
+    goal = engine.fk_jac(w["q_goal"], want_quat=False, want_jac=False)[0]
+    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    out = engine.move_ik_plan(w["q_start"], goal, engine.ik_params(), counters=cnt)   # order="auto": sorted
+    L, traj, st = out["traj_len"].long(), out["traj"], out["status"]
+    assert int(st.ne(0).sum()) == 0
+    assert int(L.min()) >= 1 and int(L.max()) <= 202
+    assert int(cnt[0]) == int(out["n_solves"].sum()) and int(cnt[1]) <= int(cnt[0])
+    start = engine.fk_jac(w["q_start"], want_quat=False, want_jac=False)[0]
+    assert float((traj[:, 0] - start).abs().max()) < 1e-6
+    idx = torch.arange(traj.shape[1], device="cuda")[None, :]
+    seg = (traj[:, 1:] - traj[:, :-1]).norm(dim=2)
+    inner = idx[:, 1:] < (L[:, None] - 1)          # steps between accepted points (the last step may be the appended goal)
+    assert float(seg[inner].max()) < 0.01 + 0.02 + 1e-4   # step_size + accept tolerance (move.py:131)
+    last = traj[torch.arange(n, device="cuda"), L - 1]
+    d_last = (last - goal).norm(dim=1)
+    assert float(d_last.max()) <= 0.01 + 1e-6              # pos_thresh (move.py:106) - or exactly the goal:
+    appended = (last == goal).all(dim=1)
+    fk_final = engine.fk_jac(out["q_final"], want_quat=False, want_jac=False)[0]
+    prev = traj[torch.arange(n, device="cuda"), (L - 2).clamp(min=0)]
+    last_accepted = torch.where(appended[:, None] & (L[:, None] > 1), prev, last)
+    assert float((fk_final - last_accepted).abs().max()) < 2e-5
+    # the same batch in index order: bit-identical (the schedule is not part of the result)
+    ref = engine.move_ik_plan(w["q_start"], goal, engine.ik_params(), order=None)
+    for f in ("traj_len", "n_solves", "status", "q_final"):
+        assert torch.equal(out[f], ref[f]), f
+    mask = idx < L[:, None]
+    assert torch.equal(traj[mask], ref["traj"][mask])
