@@ -219,7 +219,8 @@ int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n,
  * the last long plans.  pnp_move_plan_order_* writes order[n] = the env indices sorted by descending d0
  * (counting sort on 1/64 m buckets; the order inside a bucket is unspecified), pnp_move_ik_plan_ordered_*
  * takes its envs in that order (order NULL = index order; with move->compute_order = 1 it fills `order`
- * itself first, one call instead of two).  Every output stays indexed by env and is bit-identical to the
+ * itself first, one call instead of two).  A caller-made `order` must be a permutation of [0, n): it is not
+ * checked, an index outside the batch reads and writes out of bounds, a repeated one plans that env twice.  Every output stays indexed by env and is bit-identical to the
  * unordered call; only the time changes. */
 int pnp_move_plan_order_f32(const float* q_start, const float* target, int64_t n, uint32_t* order,
                             int32_t kinematics, void* stream);
