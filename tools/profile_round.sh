@@ -12,11 +12,14 @@ $CMD > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
 SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --log2-n-ik 22 --log2-n-reward 24"
-$SMALL > $OUT/plain_small_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ik_solve_v_kernel -s 3 -c 1 -f -o $OUT/ik_${TAG} $SMALL > $OUT/ncu_ik_${TAG}.log 2>&1
-echo "ik full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:reward_kernel -s 3 -c 1 -f -o $OUT/reward_${TAG} $SMALL > $OUT/ncu_reward_${TAG}.log 2>&1
-echo "reward full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:her_relabel_kernel -s 3 -c 1 -f -o $OUT/her_${TAG} $SMALL > $OUT/ncu_her_${TAG}.log 2>&1
-echo "her full rc=$?"
+# every --set full capture sits behind ONE successful plain run of the same command: ncu on a program that
+# faulted leaves the GPU unusable until a reset (B200_PROFILING.md)
+if $SMALL > $OUT/plain_small_${TAG}.log 2>&1; then
+  for K in ik_solve_v_kernel reward_kernel her_relabel_kernel; do
+    ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
+    echo "$K full rc=$?"
+  done
+else
+  echo "plain run failed: no ncu captures"; tail -5 $OUT/plain_small_${TAG}.log
+fi
 ls -la $OUT
