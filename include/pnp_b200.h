@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define PNP_ABI_VERSION 1
+#define PNP_ABI_VERSION 2
 #define PNP_NJOINT 7
 
 /* error codes (negative; positive values are cudaError_t) */
@@ -90,6 +90,9 @@ typedef struct PnpIkParams {
                                   waypoint and planner kernels and for small IK batches) */
 #define PNP_KIN_SPEC_PAIR 4    /* two queries / envs per lane on packed FFMA2/FMUL2/FADD2 (what AUTO picks for
                                   FP32 IK batches of >= 4096 queries per SM on the specialised tree) */
+#define PNP_KIN_SPEC_PAIR_HYBRID 5 /* pnp_ik_solve_*_f32 only: two queries per lane, FMAs whose three operands are three
+                                  distinct register pairs issued as two scalar FFMAs (an FFMA2 reading three fresh pairs
+                                  costs 3 clocks, two FFMAs 2.2), everything else packed; elsewhere = PNP_KIN_SPEC_PAIR */
 
 /* flags[] bits written by the IK kernels (IKResult.converged / .success, ik_solver.py:92-100) */
 #define PNP_IK_CONVERGED 1u
@@ -154,9 +157,20 @@ int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_s
 int pnp_ik_solve_packed_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                             const PnpIkParams* params, float* out_q8, float* out_aux4,
                             unsigned long long* counters, void* stream);
+/* COMPACT outputs: one 32-byte record per query, out_q8[n][8] float = q0..q6, then the 32-bit word
+ * (iterations | flags << 24).  final_pos / pos_error are not written (final_pos = FK(q): pnp_fk_jac_f32; a converged
+ * query lies within pos_thresh of its target by construction).  For callers that want IKResult.q / .success /
+ * .converged / .iterations only: 2/3 of the bytes of the packed layout, which is what the host-buffer operator
+ * spends its time moving. */
+int pnp_ik_solve_compact_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                             const PnpIkParams* params, float* out_q8, unsigned long long* counters, void* stream);
 int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err,
                      int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
+/* Launch scratch (the refill ticket of the IK / waypoint / pose / planner kernels, the plan-order histograms) is kept
+ * per STREAM: any number of launches may be queued on a stream, and up to 64 distinct streams per device may have
+ * library launches in flight at the same time.  A captured CUDA graph keeps the scratch of its capture stream - do
+ * not replay it concurrently with other library launches issued on that same stream object. */
 
 /* ---- warm-started waypoint sequences (MoveIKSkill.reset inner loop, move.py:106-137) ----- */
 /* Per env: start joints q_start[n,7], goal[n,3].  n_steps times: pos = FK(q); dist = |goal-pos|;
@@ -219,9 +233,12 @@ int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n,
  * the last long plans.  pnp_move_plan_order_* writes order[n] = the env indices sorted by descending d0
  * (counting sort on 1/64 m buckets; the order inside a bucket is unspecified), pnp_move_ik_plan_ordered_*
  * takes its envs in that order (order NULL = index order; with move->compute_order = 1 it fills `order`
- * itself first, one call instead of two).  A caller-made `order` must be a permutation of [0, n): it is not
- * checked, an index outside the batch reads and writes out of bounds, a repeated one plans that env twice.  Every output stays indexed by env and is bit-identical to the
- * unordered call; only the time changes. */
+ * itself first, one call instead of two).  A caller-made `order` must be a permutation of [0, n).  The planner skips
+ * an entry outside the batch (nothing is read or written for it); a repeated entry plans that env twice (same
+ * outputs) and leaves another env unplanned.  pnp_move_plan_order_check tells: bitmap_scratch[(n + 31) / 32] is
+ * device scratch, *n_bad (device, overwritten) = entries that are out of range or repeat an earlier one; 0 = a
+ * permutation.  Every output stays indexed by env and is bit-identical to the unordered call; only the time changes. */
+int pnp_move_plan_order_check(const uint32_t* order, int64_t n, uint32_t* bitmap_scratch, uint32_t* n_bad, void* stream);
 int pnp_move_plan_order_f32(const float* q_start, const float* target, int64_t n, uint32_t* order,
                             int32_t kinematics, void* stream);
 int pnp_move_plan_order_f64(const double* q_start, const double* target, int64_t n, uint32_t* order,
@@ -263,7 +280,8 @@ typedef struct PnpNormalizeParams {
  * compute_reward(next_obs[i].achieved_goal, new goal) with ee_pos = next_obs[i][0:3],
  * fingers_width = next_obs[i][6], ee_quat[n,4] and task_index[n] from the side arrays (bit-exact,
  * same arithmetic as pnp_reward_f32); is_success (nullable); rows optionally normalised (norm
- * nullable = copy through).  Outputs must not alias inputs.  counters as pnp_reward_*. */
+ * nullable = copy through).  future_idx[i] >= n keeps the stored goal like a negative index.  Outputs must not
+ * overlap the inputs or each other (checked by address range).  counters as pnp_reward_*. */
 int pnp_her_relabel_f32(const float* obs, const float* next_obs, const int32_t* future_idx, const float* ee_quat,
                         const int32_t* task_index, int64_t n, const PnpRewardParams* params,
                         const PnpNormalizeParams* norm, float* out_obs, float* out_next_obs, float* reward,
@@ -317,9 +335,23 @@ int pnp_ik_solve_packed_host_f32(PnpHostCtx* ctx, const float* targets, const fl
  * mailbox mapped into the device address space; one launch + one stream synchronisation.
  * out12 = q0..q6, pos_error | final_pos xyz, word (iterations | flags << 24): the two packed records of
  * pnp_ik_solve_packed_f32.  FP32; same arithmetic as the batch kernels (bit-identical results on the
- * specialised tree).  Not thread-safe per ctx (one mailbox). */
+ * specialised tree).  One mailbox per ctx: concurrent single-query calls on a ctx are serialised by a lock. */
 int pnp_ik_solve_one_host_f32(PnpHostCtx* ctx, const float* target3, const float* q_init7,
                               const PnpIkParams* params, float* out12);
+/* Compact-output variant of pnp_ik_solve_packed_host_f32 (see pnp_ik_solve_compact_f32): 32 B per query come back
+ * instead of 48. */
+int pnp_ik_solve_compact_host_f32(PnpHostCtx* ctx, const float* targets, const float* q_init,
+                                  int32_t q_init_stride, int64_t n, const PnpIkParams* params,
+                                  float* out_q8, unsigned long long* counters);
+/* ONE row, host in / host out, lowest latency - FrankaEnv.compute_reward(achieved_goal (3,), desired_goal (3,), info)
+ * as FrankaEnv.step calls it once per env.step (envs/panda_env.py:176-181) and test/reward_test.py:71-72 once per
+ * transition.  Same mapped-mailbox path as pnp_ik_solve_one_host_f32: one launch + one stream synchronisation, no
+ * cudaMemcpy, no counters.  FP64 storage, bit-exact (same arithmetic as pnp_reward_f64).  is_success and bits
+ * (placed | gripped << 1 | threshold_adjacent << 2) are nullable.  Single-query calls on one ctx are serialised by
+ * a lock. */
+int pnp_reward_one_host_f64(PnpHostCtx* ctx, const double* ag3, const double* dg3, const double* ee_pos3,
+                            const double* ee_quat4, double fingers_width, int32_t task_index,
+                            const PnpRewardParams* params, float* reward, float* is_success, uint32_t* bits);
 int pnp_reward_host_f32(PnpHostCtx* ctx, const float* ag, const float* dg, const float* ee_pos,
                         const float* ee_quat, const float* width, const int32_t* task_index,
                         int64_t n, const PnpRewardParams* params, float* reward, float* is_success,

@@ -15,10 +15,10 @@ from .tree import PnpTreeStruct
 LIB_NAME = "libpnp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-PNP_KIN_AUTO, PNP_KIN_GENERIC, PNP_KIN_SPECIALIZED, PNP_KIN_SPEC_LANE, PNP_KIN_SPEC_PAIR = 0, 1, 2, 3, 4
+PNP_KIN_AUTO, PNP_KIN_GENERIC, PNP_KIN_SPECIALIZED, PNP_KIN_SPEC_LANE, PNP_KIN_SPEC_PAIR, PNP_KIN_SPEC_PAIR_HYBRID = 0, 1, 2, 3, 4, 5
 PNP_IK_CONVERGED, PNP_IK_SUCCESS = 1, 2
 KINEMATICS = {"auto": PNP_KIN_AUTO, "generic": PNP_KIN_GENERIC, "specialized": PNP_KIN_SPECIALIZED,
-              "spec_lane": PNP_KIN_SPEC_LANE, "spec_pair": PNP_KIN_SPEC_PAIR}
+              "spec_lane": PNP_KIN_SPEC_LANE, "spec_pair": PNP_KIN_SPEC_PAIR, "spec_pair_hybrid": PNP_KIN_SPEC_PAIR_HYBRID}
 
 _ERRNAMES = {-1: "PNP_EINVAL", -2: "PNP_ENOTREE", -3: "PNP_ENODEVICE", -4: "PNP_ENOMEM"}
 
@@ -83,6 +83,7 @@ SIGNATURES = {
     "pnp_fk_jac_f64": (c_int, [_P, c_int64, _P, _P, _P, c_int32, _P]),
     "pnp_ik_solve_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_ik_solve_packed_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P]),
+    "pnp_ik_solve_compact_f32": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P]),
     "pnp_ik_solve_f64": (c_int, [_P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_ik_waypoints_f32": (c_int, [_P, _P, c_int64, c_int32, c_double, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),
     "pnp_ik_pose_solve_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), c_double, c_double,
@@ -93,6 +94,7 @@ SIGNATURES = {
     "pnp_move_ik_plan_f64": (c_int, [_P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_move_plan_order_f32": (c_int, [_P, _P, c_int64, _P, c_int32, _P]),
     "pnp_move_plan_order_f64": (c_int, [_P, _P, c_int64, _P, c_int32, _P]),
+    "pnp_move_plan_order_check": (c_int, [_P, c_int64, _P, _P, _P]),
     "pnp_move_ik_plan_ordered_f32": (c_int, [_P, _P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_move_ik_plan_ordered_f64": (c_int, [_P, _P, _P, c_int64, POINTER(PnpMoveParams), POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P, _P]),
     "pnp_reward_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P, _P]),
@@ -109,6 +111,8 @@ SIGNATURES = {
     "pnp_host_ctx_destroy": (c_int, [c_void_p]),
     "pnp_ik_solve_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P, _P, _P, _P]),
     "pnp_ik_solve_packed_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P, _P]),
+    "pnp_ik_solve_compact_host_f32": (c_int, [_P, _P, _P, c_int32, c_int64, POINTER(PnpIkParams), _P, _P]),
+    "pnp_reward_one_host_f64": (c_int, [_P, _P, _P, _P, _P, c_double, c_int32, POINTER(PnpRewardParams), _P, _P, _P]),
     "pnp_reward_host_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P]),
     "pnp_reward_host_f64": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(PnpRewardParams), _P, _P, _P]),
     "pnp_probe_fp32_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),

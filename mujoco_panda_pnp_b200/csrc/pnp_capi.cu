@@ -14,27 +14,56 @@
 
 #include "pnp_kernels.cuh"
 
+// what PNP_KIN_AUTO runs for big FP32 batches on the specialised tree: 1 = F2H (three-pair FMAs de-packed), 0 = F2
+#ifndef PNP_IK_PAIR_HYBRID_DEFAULT
+#define PNP_IK_PAIR_HYBRID_DEFAULT 0
+#endif
+
 namespace {
 
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
+
+// Launch scratch (refill ticket, plan-order histograms) is keyed by STREAM: launches on one stream are ordered, so a
+// stream's slot is free again by the time its next launch runs, whatever other streams are doing.  (Round 1 handed the
+// slots out round-robin per launch: launch k and launch k+64 on different streams could share a live ticket.)
+// The slots are allocated once in pnp_set_tree - never inside a launch, so capturing into a CUDA graph works - and a
+// stream gets one on first use.  A captured graph keeps the slot of its capture stream: do not replay it concurrently
+// with other work that was issued on that same stream object.  kStreamSlots distinct streams per device may have
+// library launches in flight at a time; beyond that the least recently assigned slot is handed out again.
+constexpr int kMaxDevices = 16;
+constexpr int kStreamSlots = 64;
 
 struct DeviceState {
   bool have_tree = false;
   bool specialized = false;
   PnpTree tree{};
   int sm_count = 0;
-  unsigned* tickets = nullptr;  // IK refill tickets, one slot per in-flight launch
-  unsigned* order_work = nullptr;  // plan-order histograms + cursors, one 2*PLAN_BUCKETS block per in-flight call
-  unsigned ticket_seq = 0;
-  int occ_ik[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned* tickets = nullptr;     // kStreamSlots refill tickets
+  unsigned* order_work = nullptr;  // kStreamSlots blocks of 2*PLAN_BUCKETS words: plan-order histograms + cursors
+  cudaStream_t slot_stream[kStreamSlots] = {};
+  bool slot_used[kStreamSlots] = {};
+  unsigned slot_clock = 0;
+  int occ_ik[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool obs_smem_set = false;
   bool fk_smem_set = false;
 };
-constexpr int kMaxDevices = 16;
-constexpr int kTicketSlots = 64;
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
+
+// the scratch slot of `st` on this device (see above)
+int stream_slot(DeviceState* s, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < kStreamSlots; ++i)
+    if (s->slot_used[i] && s->slot_stream[i] == st) return i;
+  int i = 0;
+  for (; i < kStreamSlots; ++i)
+    if (!s->slot_used[i]) break;
+  if (i == kStreamSlots) i = (int)(s->slot_clock++ % kStreamSlots);  // all taken: recycle, oldest assignment first
+  s->slot_used[i] = true;
+  s->slot_stream[i] = st;
+  return i;
+}
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -106,6 +135,7 @@ int pick_kin(const DeviceState* s, int kinematics, bool* use_spec) {
     case PNP_KIN_SPECIALIZED:
     case PNP_KIN_SPEC_LANE:
     case PNP_KIN_SPEC_PAIR:
+    case PNP_KIN_SPEC_PAIR_HYBRID:
       if (!s->specialized) return fail(PNP_EINVAL, "uploaded tree differs from the build-time specialised tree");
       *use_spec = true;
       return PNP_OK;
@@ -244,12 +274,17 @@ int get_obs_impl(const T* q_arm, const T* qvel_arm, const T* fingers, const T* o
   return PNP_OK;
 }
 
-template <typename T, typename Kin, bool kPacked>
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <typename T, typename Kin, int kOut>
 int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t st) {
-  const int slot = (sizeof(T) == 8 ? 4 : 0) + (Kin::kSpecialized ? 2 : 0) + (kPacked ? 1 : 0);
+  const int slot = (sizeof(T) == 8 ? 4 : 0) + (Kin::kSpecialized ? 2 : 0) + (kOut != pnp::IK_OUT_SEPARATE ? 1 : 0);
   if (s->occ_ik[slot] == 0) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_kernel<T, Kin, kPacked>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_kernel<T, Kin, kOut>,
                                                                   pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
@@ -264,20 +299,20 @@ int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t 
   chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : chunk);
   args.chunk = (unsigned)(chunk & ~31ll);
   args.solo_warp = small ? 1u : 0u;
-  pnp::ik_solve_kernel<T, Kin, kPacked><<<grid, block, 0, st>>>(args);
+  pnp::ik_solve_kernel<T, Kin, kOut><<<grid, block, 0, st>>>(args);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;
 }
 
-// Value-type kernels (pnp_vec.cuh): V = float, one query per lane; V = F2, two queries per lane.
-template <typename V, bool kPacked>
+// Value-type kernels (pnp_vec.cuh): V = float, one query per lane; V = F2 / F2H, two queries per lane.
+template <typename V, int kOut>
 int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStream_t st) {
   constexpr int S = pnp::Slots<V>::kN;
-  const int slot = 8 + (S - 1) * 2 + (kPacked ? 1 : 0);
+  const int slot = 8 + (std::is_same<V, pnp::F2H>::value ? 4 : (S - 1) * 2) + (kOut != pnp::IK_OUT_SEPARATE ? 1 : 0);
   if (s->occ_ik[slot] == 0) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kPacked, true>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kOut, true>,
                                                                   pnp::IK_BLOCK, 0);
     s->occ_ik[slot] = (e == cudaSuccess && occ > 0) ? occ : 1;
   }
@@ -285,7 +320,7 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   // only load the trig table (a lone warp needs ~5 us for its 40 KB)
   const int block = pnp::IK_BLOCK;
   const long long lanes_needed = ((long long)a.n + S - 1) / S;
-  static const int env_occ = [] { const char* e = getenv("PNP_IK_OCC"); return e ? atoi(e) : 0; }();
+  static const int env_occ = env_int("PNP_IK_OCC", 0);
   const int occ_use = env_occ > 0 && env_occ < s->occ_ik[slot] ? env_occ : s->occ_ik[slot];
   const int grid = small ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occ_use);
   pnp::IkArgs<float> args = a;
@@ -296,32 +331,53 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   args.chunk = (unsigned)(chunk & ~31ll);
   {
     // lanes with a finished slot that trigger a store + refill (PNP_IK_FLUSH_MIN overrides, for tuning)
-    static const int env_flush = [] { const char* e = getenv("PNP_IK_FLUSH_MIN"); return e ? atoi(e) : 0; }();
+    static const int env_flush = env_int("PNP_IK_FLUSH_MIN", 0);
     const bool oversubscribed = (long long)a.n >= (long long)s->sm_count * 8192;
     args.flush_min = env_flush > 0 ? (unsigned)env_flush : (S == 2 ? (small ? 1u : 10u) : (oversubscribed ? 4u : 1u));
+    // straggler hand-over at the end of the launch (pair kernels; PNP_IK_PARK=0 switches it off, for measurements)
+    static const int env_park = env_int("PNP_IK_PARK", 1);
+    args.park = (S == 2 && !small && env_park != 0) ? 1u : 0u;
   }
   if (a.q_init_stride == 0)
-    pnp::ik_solve_v_kernel<V, kPacked, true><<<grid, block, 0, st>>>(args);
+    pnp::ik_solve_v_kernel<V, kOut, true><<<grid, block, 0, st>>>(args);
   else
-    pnp::ik_solve_v_kernel<V, kPacked, false><<<grid, block, 0, st>>>(args);
+    pnp::ik_solve_v_kernel<V, kOut, false><<<grid, block, 0, st>>>(args);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return PNP_OK;
 }
 
-// FP32 on the specialised tree always runs the value-type kernels (same arithmetic in both, so a
-// batch gives bit-identical results whichever is picked).  AUTO / SPECIALIZED: two queries per lane
-// once the batch oversubscribes the machine (>= 4096 queries per SM); below that the batch is
-// latency bound and one query per lane finishes sooner.
-template <bool kPacked>
-int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
-  const bool big = (long long)a.n >= (long long)s->sm_count * 4096;
-  if (kinematics == PNP_KIN_SPEC_PAIR || (kinematics != PNP_KIN_SPEC_LANE && big))
-    return launch_ik_v<pnp::F2, kPacked>(s, a, (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2, st);
-  return launch_ik_v<float, kPacked>(s, a, small, st);
+// Small cold batches (at most one working warp per scheduler): the single-basic-block latency kernel, no ticket.
+template <int kOut>
+int launch_ik_small(const pnp::IkArgs<float>& a, cudaStream_t st) {
+  const int grid = (int)((a.n + 31u) / 32u);
+  if (a.q_init_stride == 0)
+    pnp::ik_solve_small_kernel<kOut, true><<<grid, pnp::IK_BLOCK, 0, st>>>(a);
+  else
+    pnp::ik_solve_small_kernel<kOut, false><<<grid, pnp::IK_BLOCK, 0, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
 }
 
-template <typename T, bool kPacked>
+// FP32 on the specialised tree always runs the value-type arithmetic (ik_eval_v / ik_step_v: a batch gives
+// bit-identical results whichever kernel is picked).  AUTO / SPECIALIZED:
+//   n <= 128 queries per SM          ik_solve_small_kernel (latency bound: the launch lasts as long as its slowest query)
+//   n >= 4096 queries per SM         two queries per lane (F2 all packed, or F2H: three-pair FMAs as scalar FFMAs)
+//   in between                       one query per lane with refill
+template <int kOut>
+int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
+  const bool big = (long long)a.n >= (long long)s->sm_count * 4096;
+  static const int env_hybrid = env_int("PNP_IK_PAIR_HYBRID", PNP_IK_PAIR_HYBRID_DEFAULT);
+  const bool pair_small = (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2;
+  if (kinematics == PNP_KIN_SPEC_PAIR_HYBRID) return launch_ik_v<pnp::F2H, kOut>(s, a, pair_small, st);
+  if (kinematics == PNP_KIN_SPEC_PAIR) return launch_ik_v<pnp::F2, kOut>(s, a, pair_small, st);
+  if (kinematics != PNP_KIN_SPEC_LANE && big)
+    return env_hybrid ? launch_ik_v<pnp::F2H, kOut>(s, a, pair_small, st) : launch_ik_v<pnp::F2, kOut>(s, a, pair_small, st);
+  return launch_ik_v<float, kOut>(s, a, small, st);
+}
+
+template <typename T, int kOut>
 int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int64_t n, const PnpIkParams* params,
                   T* q_out, T* final_pos, T* pos_err, int32_t* iters, uint8_t* flags, unsigned long long* counters,
                   void* stream) {
@@ -330,8 +386,10 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   if (n < 0 || (n > 0 && (!targets || !q_init || !q_out))) return fail(PNP_EINVAL, "ik_solve: null pointer or negative n");
   if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_solve: n must be < 2^31 per call (split the batch)");
   if (q_init_stride != 0 && q_init_stride != PNP_NJOINT) return fail(PNP_EINVAL, "q_init_stride must be 0 or 7");
-  if (kPacked && n > 0 && (!final_pos || !aligned16(q_out) || !aligned16(final_pos)))
+  if (kOut == pnp::IK_OUT_PACKED && n > 0 && (!final_pos || !aligned16(q_out) || !aligned16(final_pos)))
     return fail(PNP_EINVAL, "ik_solve_packed: out_q8 / out_aux must be non-null and 16-byte aligned");
+  if (kOut == pnp::IK_OUT_COMPACT && n > 0 && !aligned16(q_out))
+    return fail(PNP_EINVAL, "ik_solve_compact: out_q8 must be 16-byte aligned");
   DeviceState* s;
   if ((rc = current_state(&s))) return rc;
   bool spec;
@@ -339,26 +397,28 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   if (n == 0) return PNP_OK;
   cudaStream_t st = (cudaStream_t)stream;
 
-  unsigned* ticket;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
-  }
-  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-
   pnp::IkArgs<T> a;
   a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
-  a.counters = counters; a.ticket = ticket; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0;
+  a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.park = 0;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  if (spec) {
-    if constexpr (std::is_same<T, float>::value)
-      return launch_ik_spec_f32<kPacked>(s, a, params->kinematics, small, st);
-    else
-      return launch_ik<T, pnp::SpecKin, kPacked>(s, a, small, st);
+  if constexpr (std::is_same<T, float>::value) {
+    // the latency kernel needs no ticket: skip the memset node as well
+    static const int env_small = env_int("PNP_IK_SMALL", 1);
+    if (spec && small && env_small && (params->kinematics == PNP_KIN_AUTO || params->kinematics == PNP_KIN_SPECIALIZED))
+      return launch_ik_small<kOut>(a, st);
   }
-  return launch_ik<T, pnp::GenericKin, kPacked>(s, a, small, st);
+  a.ticket = s->tickets + stream_slot(s, st);
+  CUDA_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned), st));
+  if (spec) {
+    if constexpr (std::is_same<T, float>::value) {
+      return launch_ik_spec_f32<kOut>(s, a, params->kinematics, small, st);
+    } else {
+      return launch_ik<T, pnp::SpecKin, kOut>(s, a, small, st);
+    }
+  }
+  return launch_ik<T, pnp::GenericKin, kOut>(s, a, small, st);
 }
 
 // Smallest double s >= 0 with sqrt(s) >= t (sqrt is correctly rounded, hence monotone): the
@@ -465,11 +525,15 @@ int pnp_set_tree(const PnpTree* t) {
   pnp::TreeDev<double> td;
   fill_tree_dev(*t, &tf);
   fill_tree_dev(*t, &td);
+  // Replacing a tree that kernels on any stream (torch side streams, the host operators' non-blocking streams) may
+  // still be reading: cudaMemcpyToSymbol orders against none of them, so wait for the device first.  (The first
+  // upload and a re-upload of the same tree have nothing to wait for.)
+  if (s->have_tree && memcmp(&s->tree, t, sizeof *t) != 0) CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f32, &tf, sizeof tf));
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
   if (!s->tickets) {
-    CUDA_TRY(cudaMalloc(&s->tickets, kTicketSlots * sizeof(unsigned)));
-    CUDA_TRY(cudaMalloc(&s->order_work, (size_t)kTicketSlots * 2 * pnp::PLAN_BUCKETS * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&s->tickets, kStreamSlots * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&s->order_work, (size_t)kStreamSlots * 2 * pnp::PLAN_BUCKETS * sizeof(unsigned)));
     // sin(k * 2*pi/8192), k < 8192 + 2048, for the FP32 IK kernels' first-order table trig, evaluated in FP64
     static float tabv[pnp::kTrigVWords];
     for (int k = 0; k < pnp::kTrigVWords; ++k)
@@ -522,19 +586,24 @@ int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double
 int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err, int32_t* iters,
                      uint8_t* flags, unsigned long long* counters, void* stream) {
-  return ik_solve_impl<float, false>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
+  return ik_solve_impl<float, pnp::IK_OUT_SEPARATE>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
                                      flags, counters, stream);
 }
 int pnp_ik_solve_packed_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                             const PnpIkParams* params, float* out_q8, float* out_aux4,
                             unsigned long long* counters, void* stream) {
-  return ik_solve_impl<float, true>(targets, q_init, q_init_stride, n, params, out_q8, out_aux4, nullptr, nullptr,
+  return ik_solve_impl<float, pnp::IK_OUT_PACKED>(targets, q_init, q_init_stride, n, params, out_q8, out_aux4, nullptr, nullptr,
                                     nullptr, counters, stream);
+}
+int pnp_ik_solve_compact_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
+                             const PnpIkParams* params, float* out_q8, unsigned long long* counters, void* stream) {
+  return ik_solve_impl<float, pnp::IK_OUT_COMPACT>(targets, q_init, q_init_stride, n, params, out_q8, nullptr, nullptr,
+                                                   nullptr, nullptr, counters, stream);
 }
 int pnp_ik_solve_f64(const double* targets, const double* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, double* q_out, double* final_pos, double* pos_err, int32_t* iters,
                      uint8_t* flags, unsigned long long* counters, void* stream) {
-  return ik_solve_impl<double, false>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
+  return ik_solve_impl<double, pnp::IK_OUT_SEPARATE>(targets, q_init, q_init_stride, n, params, q_out, final_pos, pos_err, iters,
                                       flags, counters, stream);
 }
 
@@ -552,11 +621,7 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   if (n == 0) return PNP_OK;
   if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_waypoints: n must be < 2^31 per call");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned* ticket;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
-  }
+  unsigned* ticket = s->tickets + stream_slot(s, st);
   CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::WaypointArgs<float> a;
   a.q_start = q_start; a.goal = goal; a.n = (unsigned)n; a.n_steps = n_steps; a.ticket = ticket;
@@ -569,7 +634,7 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   // specialised tree: the value-type kernels (same arithmetic in both), one env per lane unless two are asked
   // for (with the fused accept / first-iteration pass the bookkeeping weighs more than the packed arithmetic
   // saves: 2^20 envs x 50, 0.81 ms against 0.87); other trees: the scalar-template kernel
-  const bool pair = spec && params->kinematics == PNP_KIN_SPEC_PAIR;
+  const bool pair = spec && (params->kinematics == PNP_KIN_SPEC_PAIR || params->kinematics == PNP_KIN_SPEC_PAIR_HYBRID);
   const int S = pair ? 2 : 1;
   int occ = 4;
   if (!small) {
@@ -623,11 +688,7 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
   if (n == 0) return PNP_OK;
   if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "ik_pose_solve: n must be < 2^31 per call");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned* ticket;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
-  }
+  unsigned* ticket = s->tickets + stream_slot(s, st);
   CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::PoseIkArgs<T> a;
   a.target_pos = tpos; a.target_quat = tquat; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
@@ -668,11 +729,7 @@ int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* orde
   if (n == 0) return PNP_OK;
   if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "move_plan_order: n must be < 2^31 per call");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned* work;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    work = s->order_work + (size_t)(s->ticket_seq++ % kTicketSlots) * 2 * pnp::PLAN_BUCKETS;
-  }
+  unsigned* work = s->order_work + (size_t)stream_slot(s, st) * 2 * pnp::PLAN_BUCKETS;
   CUDA_TRY(cudaMemsetAsync(work, 0, 2 * pnp::PLAN_BUCKETS * sizeof(unsigned), st));
   const int per_block = pnp::PLAN_ORDER_BLOCK * pnp::PLAN_ORDER_PER_THREAD;
   const int grid = (int)((n + per_block - 1) / per_block);
@@ -709,11 +766,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   if (n == 0) return PNP_OK;
   if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "move_ik_plan: n must be < 2^31 per call");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned* ticket;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    ticket = s->tickets + (s->ticket_seq++ % kTicketSlots);
-  }
+  unsigned* ticket = s->tickets + stream_slot(s, st);
   CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   pnp::MoveArgs<T> a;
   a.q_start = q_start; a.target = target; a.n = (unsigned)n; a.ticket = ticket;
@@ -730,7 +783,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   if constexpr (std::is_same<T, float>::value) {
     if (spec) {
       // specialised tree, FP32: the value-type kernels (same arithmetic in both, branch-free common path)
-      const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR;
+      const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR || params->kinematics == PNP_KIN_SPEC_PAIR_HYBRID;
       const int S = pair ? 2 : 1;
       int occv = 4;
       if (!small) {
@@ -805,6 +858,22 @@ int pnp_move_plan_order_f64(const double* q_start, const double* target, int64_t
   return plan_order_impl<double>(q_start, target, n, order, kinematics, stream);
 }
 
+int pnp_move_plan_order_check(const uint32_t* order, int64_t n, uint32_t* bitmap_scratch, uint32_t* n_bad, void* stream) {
+  if (n < 0 || (n > 0 && (!order || !bitmap_scratch)) || !n_bad) return fail(PNP_EINVAL, "move_plan_order_check: null pointer or negative n");
+  if (n >= (int64_t(1) << 31)) return fail(PNP_EINVAL, "move_plan_order_check: n must be < 2^31");
+  DeviceState* s;
+  int rc = current_state(&s);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(n_bad, 0, sizeof(uint32_t), st));
+  if (n == 0) return PNP_OK;
+  CUDA_TRY(cudaMemsetAsync(bitmap_scratch, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
+  pnp::plan_order_check_kernel<<<grid_for(n, 256, s->sm_count, 8), 256, 0, st>>>(order, (unsigned)n, bitmap_scratch, n_bad);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return PNP_OK;
+}
+
 int pnp_move_ik_plan_f32(const float* q_start, const float* target, int64_t n, const PnpMoveParams* mp,
                          const PnpIkParams* params, float* traj, int32_t* traj_len, float* q_final,
                          int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
@@ -873,8 +942,16 @@ int pnp_her_relabel_table_f32(const float* obs, const float* next_obs, const int
   if (params->n_tasks <= 0) return fail(PNP_EINVAL, "n_tasks must be > 0");
   if (n < 0 || (n > 0 && (!obs || !next_obs || !future_idx || !ee_quat || !task_index || !out_obs || !out_next_obs || !reward)))
     return fail(PNP_EINVAL, "her_relabel: null pointer or negative n");
-  if (n > 0 && (out_obs == obs || out_next_obs == next_obs || out_obs == next_obs || out_next_obs == obs))
-    return fail(PNP_EINVAL, "her_relabel: outputs must not alias inputs (future goals are gathered from next_obs)");
+  if (n > 0) {
+    const size_t bytes = (size_t)n * pnp::HER_ROW * sizeof(float);
+    auto overlap = [bytes](const float* x, const float* y) {
+      const uintptr_t a0 = (uintptr_t)x, b0 = (uintptr_t)y;
+      return a0 < b0 + bytes && b0 < a0 + bytes;
+    };
+    if (overlap(out_obs, obs) || overlap(out_obs, next_obs) || overlap(out_next_obs, obs) || overlap(out_next_obs, next_obs) ||
+        overlap(out_obs, out_next_obs))
+      return fail(PNP_EINVAL, "her_relabel: outputs must not overlap the inputs or each other (future goals are gathered from next_obs)");
+  }
   if (n > 0 && !aligned16(ee_quat)) return fail(PNP_EINVAL, "her_relabel: ee_quat must be 16-byte aligned");
   DeviceState* s;
   int rc = current_state(&s);

@@ -174,7 +174,13 @@ struct IkArgs {
   unsigned flush_min; // ik_solve_v_kernel: lanes with a finished slot that trigger a store + refill
   unsigned solo_warp; // ik_solve_v_kernel, small batches: the block has 4 warps to load the 40 KB trig table quickly,
                       // only warp 0 solves (one warp per block spreads a small batch over all SMs)
+  unsigned park;      // ik_solve_v_kernel: block-level straggler hand-over once the ticket pool is dry (see the kernel)
 };
+
+// output layouts of the FP32 IK kernels
+enum { IK_OUT_SEPARATE = 0,  // five arrays (pnp_ik_solve_f32)
+       IK_OUT_PACKED = 1,    // out_q8[n][8] = q0..q6, pos_error; out_aux[n][4] = final_pos xyz, iterations | flags << 24
+       IK_OUT_COMPACT = 2 }; // out_q8[n][8] = q0..q6, iterations | flags << 24   (32 B per query, nothing else)
 
 // convergence test (ik_solver.py:61-64).  FP64 follows the reference literally (sqrt, then
 // compare); FP32 compares squared norms and takes the sqrt only when a lane finishes.
@@ -183,7 +189,7 @@ __device__ __forceinline__ bool below_thresh(float n2, const IkConst<float>& k) 
 __device__ __forceinline__ double finish_sqrt(double n2) { return sqrt(n2); }
 __device__ __forceinline__ float finish_sqrt(float n2) { return n2 > 0.0f ? n2 * rsqrtf(n2) : 0.0f; }
 
-template <typename T, typename Kin, bool kPacked>
+template <typename T, typename Kin, int kOut>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) T s_q0[8];  // broadcast q_init: refills read it from shared memory
@@ -262,12 +268,16 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {
       // :88-92  final_pos = FK(q) = p; final_error = err; success = conv && err < 2*thresh
       const bool success = conv && (err < a.k.pos_thresh * T(2));
       const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
-      if (kPacked) {
+      if (kOut == IK_OUT_PACKED) {
         float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)idx * 2u;
         oq[0] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
         oq[1] = make_float4((float)q[4], (float)q[5], (float)q[6], (float)err);
         reinterpret_cast<float4*>(a.final_pos)[idx] =
             make_float4((float)p[0], (float)p[1], (float)p[2], __int_as_float((int)((unsigned)iterations | (fl << 24))));
+      } else if (kOut == IK_OUT_COMPACT) {
+        float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)idx * 2u;
+        oq[0] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        oq[1] = make_float4((float)q[4], (float)q[5], (float)q[6], __int_as_float((int)((unsigned)iterations | (fl << 24))));
       } else {
         T* qo = a.q_out + (size_t)idx * NJ;
 #pragma unroll
@@ -322,11 +332,11 @@ struct Slots<float> {
   static __device__ __forceinline__ float get(float v, int) { return v; }
   static __device__ __forceinline__ void set(float& v, int, float x) { v = x; }
 };
-template <>
-struct Slots<F2> {
+template <int M>
+struct Slots<F2T<M>> {
   static constexpr int kN = 2;
-  static __device__ __forceinline__ float get(const F2& v, int k) { return k == 0 ? v.v.x : v.v.y; }
-  static __device__ __forceinline__ void set(F2& v, int k, float x) { if (k == 0) v.v.x = x; else v.v.y = x; }
+  static __device__ __forceinline__ float get(const F2T<M>& v, int k) { return k == 0 ? v.v.x : v.v.y; }
+  static __device__ __forceinline__ void set(F2T<M>& v, int k, float x) { if (k == 0) v.v.x = x; else v.v.y = x; }
 };
 
 // Predicated global accesses for the store + refill block of ik_solve_v_kernel: as plain `if`s the
@@ -361,26 +371,43 @@ __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
 // parameter rather than a run-time branch because ptxas puts the (predicated-off) q_init loads on
 // the scoreboard of the target loads, and the first trig FFMA2 of the pass then waited a full
 // global-load latency for targets it does not need until mid-pass.
-template <typename V, bool kPacked, bool kBcast>
+//
+// Straggler hand-over (a.park).  0.2 % of cold queries run into max_iters = 100 while the mean is 16 passes, so when
+// the ticket pool runs dry nearly every warp of the grid is left holding one or two long-running slots, and a warp
+// with one live slot still pays a full pass: the launch ended with ~100 passes at 1/64 density on every scheduler
+// (0.13-0.15 ms of a 2.8 ms launch).  Once a warp has seen the pool dry and is down to <= IK_PARK_PER_WARP running
+// slots, it writes them (query index, iteration count, q, target) to a block-shared list and leaves; the LAST warp of
+// the block to get there keeps going and takes the whole list (<= 4 x 16 entries = its 64 slots).  The drain then runs
+// on one warp per block instead of four, at the latency of a lone warp per scheduler.  A query continues from exactly
+// the state it was parked in, so results do not depend on whether or where it was handed over.
+constexpr int IK_PARK_PER_WARP = 16;
+constexpr int IK_PARK_WORDS = 12;  // idx, it, q[7], target[3]
+
+template <typename V, int kOut, bool kBcast>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
+  constexpr int kParkCap = (IK_BLOCK / 32) * IK_PARK_PER_WARP;
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
   __shared__ __align__(16) float s_trig[kTrigVWords];
+  __shared__ __align__(16) float s_park[S == 2 ? kParkCap * IK_PARK_WORDS : 4];
+  __shared__ unsigned s_park_cnt, s_live_warps;
   load_trigv_table(s_trig);
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
+  if (threadIdx.x == 0) { s_park_cnt = 0; s_live_warps = IK_BLOCK / 32; }
   __syncthreads();
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
+  const bool can_park = S == 2 && a.park && !a.solo_warp;
   enum { IDLE = 0, RUN = 1, FIN_CONV = 2, FIN_NOCONV = 3 };
 
   V q[NJ], tgt[3], slim(0.0f);
   int it[S], st[S];
   unsigned idx[S];
-  bool exhausted = false;
+  bool exhausted = false, sink = false;
   unsigned c_n = 0, c_conv = 0;
   unsigned long long c_iter = 0;
 #pragma unroll
@@ -390,6 +417,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; st[k] = IDLE; }
   unsigned pool_next = 0, pool_end = 0;  // warp-local pool of reserved query indices
   bool flush = true;  // first pass: nothing to store, every slot to fill
+  bool pool_dry = false;  // warp-uniform: some lane of this warp has drawn an index >= n
 
   while (true) {
     if (flush) {  // warp-uniform
@@ -441,6 +469,63 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         } else {
           pool_next += count;
         }
+        pool_dry = pool_dry || __any_sync(FULL, ran_out);
+      }
+      if (can_park && pool_dry && !sink) {  // warp-uniform
+        // ---- straggler hand-over: few running slots left and nothing more to take ------------------
+        unsigned run_m[S], n_run = 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          run_m[k] = __ballot_sync(FULL, st[k] == RUN);
+          n_run += (unsigned)__popc(run_m[k]);
+        }
+        if (n_run <= (unsigned)IK_PARK_PER_WARP) {
+          unsigned base = 0;
+          if (n_run) {
+            if (lane == 0) base = atomicAdd(&s_park_cnt, n_run);
+            base = __shfl_sync(FULL, base, 0);
+          }
+          unsigned before = 0;
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            if (st[k] == RUN) {
+              float* e = s_park + (base + before + (unsigned)__popc(run_m[k] & lanemask_lt)) * IK_PARK_WORDS;
+              e[0] = __uint_as_float(idx[k]);
+              e[1] = __int_as_float(it[k]);
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) e[2 + i] = Slots<V>::get(q[i], k);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) e[9 + i] = Slots<V>::get(tgt[i], k);
+              st[k] = IDLE;
+            }
+            before += (unsigned)__popc(run_m[k]);
+          }
+          __threadfence_block();  // the entries are written before this warp is counted out
+          unsigned left = 0;
+          if (lane == 0) left = atomicSub(&s_live_warps, 1u);
+          left = __shfl_sync(FULL, left, 0);
+          if (left != 1u) break;  // another warp of the block is still at work: it will take the list
+          // last warp of the block: every other warp has written its entries (their fence precedes their
+          // decrement, which precedes ours) - take them all
+          sink = true;
+          __threadfence_block();
+          const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&s_park_cnt);
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            const unsigned j = (unsigned)k * 32u + lane;
+            if (j < cnt) {
+              const float* e = s_park + j * IK_PARK_WORDS;
+              idx[k] = __float_as_uint(e[0]);
+              it[k] = __float_as_int(e[1]);
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) Slots<V>::set(q[i], k, e[2 + i]);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) Slots<V>::set(tgt[i], k, e[9 + i]);
+              st[k] = RUN;
+              Slots<V>::set(slim, k, a.k.step_limit);
+            }
+          }
+        }
       }
       bool any_run = false;
 #pragma unroll
@@ -468,7 +553,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
     ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
+    // (pool dry: no refill to amortise, and the hand-over above looks at the running count after every finish)
+    flush = n_fin >= (pool_dry && can_park ? 1 : flush_min) || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
     if (flush) {  // warp-uniform
       // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,
       //      so this pass's values are the query's final ones.  One exception: a query that finished on
@@ -492,12 +578,16 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 #pragma unroll
           for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
         }
-        if (kPacked) {
+        const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
+        if (kOut == IK_OUT_PACKED) {
           float* oq = a.q_out + (size_t)id * 8u;
           stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
           stg128_if(f, oq + 4, qf[4], qf[5], qf[6], err);
-          stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k),
-                    __int_as_float((int)((unsigned)iterations | (fl << 24))));
+          stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k), word);
+        } else if (kOut == IK_OUT_COMPACT) {
+          float* oq = a.q_out + (size_t)id * 8u;
+          stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
+          stg128_if(f, oq + 4, qf[4], qf[5], qf[6], word);
         } else if (f) {
           float* qo = a.q_out + (size_t)id * NJ;
 #pragma unroll
@@ -527,6 +617,88 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, w_conv);  // success == converged
       atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, w_iter);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small cold batches, latency bound (BASELINE cfg2: 4096 targets).  A launch of n <= ~one warp per scheduler lasts as
+// long as its slowest query - 100 passes for a target that runs into max_iters - so what matters is the latency of
+// ONE pass of a lone warp, not throughput.  One query per lane, one working warp per block (the batch spreads over all
+// SMs), three helper warps that only load the trig table; no ticket, no refill, no per-slot state machine: the loop
+// body is a single basic block (evaluate, test, vote, step) that ptxas can schedule for latency.  Same arithmetic as
+// ik_solve_v_kernel<float> (ik_eval_v / ik_step_v): bit-identical results.  A finished lane is frozen (step limit 0).
+// ---------------------------------------------------------------------------------------------
+template <int kOut, bool kBcast>
+__global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<float> a) {
+  __shared__ __align__(16) float s_trig[kTrigVWords];
+  load_trigv_table(s_trig);
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const TrigV trig{s_trig};
+  const unsigned lane = threadIdx.x;
+  const unsigned id = blockIdx.x * 32u + lane;
+  const bool valid = id < a.n;
+  const unsigned ld = valid ? id : 0u;
+  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
+  float q[NJ], tgt[3], pf[3] = {0.0f, 0.0f, 0.0f}, n2f = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tgt[i] = a.targets[(size_t)ld * 3u + i];
+  const float* qi = kBcast ? a.q_init : a.q_init + (size_t)ld * NJ;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+  bool done = !valid, conv = false;
+  int iterations = 0;
+  for (int it = 0;; ++it) {
+    float p[3], e[3], n2, J[21];
+    ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
+    const bool last = it >= a.k.max_iters;                     // loop ran out (ik_solver.py:57)
+    const bool fin = !done && (last || n2 < thresh2);          // :61-64
+    if (fin) {
+      conv = !last;
+      iterations = conv ? it + 1 : it;                         // :66 / :85
+      pf[0] = p[0]; pf[1] = p[1]; pf[2] = p[2]; n2f = n2;      // final_pos / final_error (:88-89)
+    }
+    done = done || fin;
+    if (__all_sync(FULL, done)) break;
+    ik_step_v<float>(q, J, e, a.k.damping, done ? 0.0f : a.k.step_limit);  // frozen once finished
+  }
+  if (a.counters) {  // whole warp (lanes past the end of the batch add zeros)
+    const unsigned long long w_n = warp_sum((unsigned long long)(valid ? 1u : 0u)),
+                             w_conv = warp_sum((unsigned long long)((valid && conv) ? 1u : 0u)),
+                             w_iter = warp_sum((unsigned long long)(valid ? iterations : 0));
+    if (lane == 0) {
+      atomicAdd(a.counters + PNP_IK_CNT_N, w_n);
+      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, w_conv);
+      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, w_conv);  // success == converged
+      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, w_iter);
+    }
+  }
+  if (!valid) return;
+  if (iterations == (conv ? 1 : 0)) {  // finished on the first pass: q_init comes back untouched (see ik_solve_v_kernel)
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+  }
+  const float err = finish_sqrt(n2f);
+  const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
+  const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+  const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
+  if (kOut == IK_OUT_PACKED) {
+    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
+    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
+    oq[1] = make_float4(q[4], q[5], q[6], err);
+    reinterpret_cast<float4*>(a.final_pos)[id] = make_float4(pf[0], pf[1], pf[2], word);
+  } else if (kOut == IK_OUT_COMPACT) {
+    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
+    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
+    oq[1] = make_float4(q[4], q[5], q[6], word);
+  } else {
+    float* qo = a.q_out + (size_t)id * NJ;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) qo[i] = q[i];
+    if (a.final_pos) { a.final_pos[(size_t)id * 3u] = pf[0]; a.final_pos[(size_t)id * 3u + 1] = pf[1]; a.final_pos[(size_t)id * 3u + 2] = pf[2]; }
+    if (a.pos_err) a.pos_err[id] = err;
+    if (a.iters) a.iters[id] = iterations;
+    if (a.flags) a.flags[id] = (uint8_t)fl;
   }
 }
 
@@ -1334,6 +1506,22 @@ __global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_scatter_kernel(co
   }
 }
 
+// Is a caller-made `order` a permutation of [0, n)?  One pass: every entry sets its bit in a zeroed bitmap; an entry
+// outside the batch or a bit already set counts as bad.  (The planner itself skips out-of-range entries; a repeated
+// entry plans one env twice and leaves another one unplanned - this is how a caller finds out.)
+__global__ void __launch_bounds__(256) plan_order_check_kernel(const unsigned* __restrict__ order, unsigned n,
+                                                                unsigned* __restrict__ bitmap, unsigned* __restrict__ n_bad) {
+  unsigned bad = 0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned e = order[i];
+    if (e >= n) { ++bad; continue; }
+    const unsigned bit = 1u << (e & 31u);
+    if (atomicOr(&bitmap[e >> 5], bit) & bit) ++bad;
+  }
+  bad = (unsigned)warp_sum((unsigned long long)bad);
+  if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(n_bad, bad);
+}
+
 // The planner's scalar bookkeeping in the two precisions: FP64 follows the reference's operations
 // literally (sqrt, a*b/c, (a/c)*b); FP32 - held to the 1e-4 m tolerance, not to bit parity - uses one
 // MUFU each (x*rsqrt(x), a*b*rcp(c)): the bookkeeping runs on every pass of the flattened loop, and
@@ -1404,14 +1592,17 @@ __global__ void __launch_bounds__(IK_BLOCK) move_ik_plan_kernel(const MoveArgs<T
         const unsigned rank = (unsigned)__popc(need & lanemask_lt);
         const unsigned idx = rank < avail ? pool_next + rank : fresh + (rank - avail);
         if (idx < a.n) {
-          e = a.order ? a.order[idx] : idx;
+          const unsigned eo = a.order ? a.order[idx] : idx;
+          if (eo < a.n) {  // an out-of-range entry of a caller-made order is skipped: nothing is read or written for it
+            e = eo;
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) q[i] = qs[i] = a.q_start[(size_t)e * NJ + i];
+            for (int i = 0; i < NJ; ++i) q[i] = qs[i] = a.q_start[(size_t)e * NJ + i];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) goal[i] = a.target[(size_t)e * 3 + i];
-          traj = a.traj + (size_t)e * a.traj_cap * 3;
-          len = 0; solves = 0; st = 0; point_count = 0; cf = 0; outer = 0; astep = T(0);
-          state = INIT;
+            for (int i = 0; i < 3; ++i) goal[i] = a.target[(size_t)e * 3 + i];
+            traj = a.traj + (size_t)e * a.traj_cap * 3;
+            len = 0; solves = 0; st = 0; point_count = 0; cf = 0; outer = 0; astep = T(0);
+            state = INIT;
+          }
         } else {
           exhausted = true;
         }
@@ -1736,6 +1927,25 @@ __global__ void __launch_bounds__(256) reward_kernel(const RewardArgs<TIn> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// One row, lowest latency: FrankaEnv.step evaluates compute_reward once per env.step (envs/panda_env.py:176-181) and
+// test/reward_test.py:71-72 calls it one transition at a time.  `in` / `out` point into the pinned, mapped host mailbox
+// of the single-query path (see ik_solve_one_kernel): one launch + one stream synchronisation, no cudaMemcpy, no
+// counters memset.  FP64 storage (what the reference hands over), the same reward_row as the streaming kernel.
+//   in [15] = achieved_goal3, desired_goal3, ee_pos3, ee_quat4 (wxyz), fingers_width, task_index (as a double)
+//   out[3]  = reward, is_success, bits(placed | gripped << 1 | threshold_adjacent << 2)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) reward_one_kernel(const double* __restrict__ in, const RewardConst k,
+                                                        float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  float succ;
+  unsigned pl, gr, ad;
+  const float r = reward_row<double>(in, in + 3, in + 6, in + 9, in[13], (int)in[14], k, &succ, pl, gr, ad);
+  out[0] = r;
+  out[1] = succ;
+  out[2] = __uint_as_float(pl | (gr << 1) | (ad << 2));
+}
+
+// ---------------------------------------------------------------------------------------------
 // The planner over the value types of pnp_vec.cuh (specialised tree, FP32): V = float plans one env per
 // lane, V = F2 two (packed FFMA2/FMUL2/FADD2) - same operations, bit-identical results.  Same state
 // machine and reference line numbers as move_ik_plan_kernel above, restructured so that the COMMON
@@ -1830,17 +2040,19 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
           if (id < a.n) {
             const unsigned e = a.order ? a.order[id] : id;
-            env[k] = e;
+            if (e < a.n) {  // an out-of-range entry of a caller-made order is skipped: nothing is read or written for it
+              env[k] = e;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) {
-              const float v = a.q_start[(size_t)e * NJ + i];
-              Slots<V>::set(qs[i], k, v);
-              qa[(k * NJ + i) * IK_BLOCK] = v;
+              for (int i = 0; i < NJ; ++i) {
+                const float v = a.q_start[(size_t)e * NJ + i];
+                Slots<V>::set(qs[i], k, v);
+                qa[(k * NJ + i) * IK_BLOCK] = v;
+              }
+#pragma unroll
+              for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)e * 3 + i]);
+              len[k] = 0; solves[k] = 0; st[k] = 0; point_count[k] = 0; cf[k] = 0; outer[k] = 0; astep[k] = 0.0f; it[k] = 0;
+              state[k] = INIT;
             }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)e * 3 + i]);
-            len[k] = 0; solves[k] = 0; st[k] = 0; point_count[k] = 0; cf[k] = 0; outer[k] = 0; astep[k] = 0.0f; it[k] = 0;
-            state[k] = INIT;
           } else {
             ran_out = true;
           }
@@ -2115,7 +2327,7 @@ __device__ __forceinline__ void her_row(const HerArgs& a, long long row, float* 
                                         unsigned& ad) {
   const int fi = a.future_idx[row];
   float g[3] = {x[22], x[23], x[24]};
-  if (fi >= 0) {
+  if (fi >= 0 && (long long)fi < a.n_total) {  // an index past the end keeps the stored goal, like a negative one
     const float* src = a.future_ag ? a.future_ag + (long long)fi * 3
                                    : a.next_obs + (long long)fi * HER_ROW + 19;   // future achieved_goal (original rows)
     g[0] = src[0]; g[1] = src[1]; g[2] = src[2];

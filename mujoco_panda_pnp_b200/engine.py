@@ -95,6 +95,25 @@ def _check_cuda(name: str, t: torch.Tensor, dtype, shape_tail) -> torch.Tensor:
     return t.contiguous()
 
 
+def _check_out(name: str, t, shape, dtype, device) -> torch.Tensor:
+    """A caller-supplied CUDA output buffer goes to the library as a bare pointer: refuse anything that is not exactly
+    the buffer the kernel will write (shape, dtype, device, contiguous)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {device}, got "
+                         f"{t.dtype} {tuple(t.shape)} on {t.device}{'' if t.is_contiguous() else ' (not contiguous)'}")
+    return t
+
+
+def _check_out_np(name: str, a, shape, dtype) -> np.ndarray:
+    """Same for a host output buffer of the host-buffer operators (written by cudaMemcpyAsync)."""
+    if not isinstance(a, np.ndarray) or a.shape != tuple(shape) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"] \
+            or not a.flags["WRITEABLE"]:
+        raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dtype)} array of shape {tuple(shape)}")
+    return a
+
+
 # ---------------------------------------------------------------------------------------------
 # FK + Jacobian
 # ---------------------------------------------------------------------------------------------
@@ -180,12 +199,13 @@ def unpack_ik(out_q8, out_aux4):
 
 def ik_solve(targets: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams, counters: Optional[torch.Tensor] = None,
              packed: Optional[bool] = None, out_q8: Optional[torch.Tensor] = None,
-             out_aux4: Optional[torch.Tensor] = None) -> BatchIKResult:
+             out_aux4: Optional[torch.Tensor] = None, compact: bool = False) -> BatchIKResult:
     """Device path: targets[N,3], q_init[N,7] or [7] (cuda, same float dtype).
 
     float32 uses the packed-output kernel (pnp_ik_solve_packed_f32) by default: the result fields
     are views into two [N,8] / [N,4] buffers.  ``packed=False`` selects the separate-array entry
-    point (pnp_ik_solve_f32); float64 always uses separate arrays."""
+    point (pnp_ik_solve_f32); float64 always uses separate arrays.  ``compact=True`` (float32) writes
+    one 32-byte record per query - q, iterations, converged, success; ``final_pos`` / ``pos_error`` are None."""
     lib = _lib.load()
     dt = targets.dtype
     if dt not in (torch.float32, torch.float64):
@@ -205,14 +225,25 @@ def ik_solve(targets: torch.Tensor, q_init: torch.Tensor, params: PnpIkParams, c
     dev = targets.device
     if counters is not None and (counters.dtype != torch.int64 or counters.numel() < 4 or not counters.is_cuda):
         raise ValueError("counters must be a CUDA int64 tensor with >= 4 elements")
+    if compact:
+        if dt != torch.float32 or packed is False:
+            raise ValueError("compact outputs exist for float32 only (and exclude packed=False)")
+        packed = True
     if packed is None:
         packed = dt == torch.float32
     if packed and dt != torch.float32:
         raise ValueError("packed outputs exist for float32 only")
     with torch.cuda.device(dev):
         if packed:
-            q8 = out_q8 if out_q8 is not None else torch.empty((n, 8), dtype=dt, device=dev)
-            aux = out_aux4 if out_aux4 is not None else torch.empty((n, 4), dtype=dt, device=dev)
+            q8 = _check_out("out_q8", out_q8, (n, 8), dt, dev) if out_q8 is not None else torch.empty((n, 8), dtype=dt, device=dev)
+            if compact:
+                _lib.check(
+                    lib.pnp_ik_solve_compact_f32(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q8),
+                                                 _ptr(counters), _stream()),
+                    "pnp_ik_solve_compact",
+                )
+                return BatchIKResult(q=q8[:, :7], word=q8[:, 7].view(torch.int32), counters=counters)
+            aux = _check_out("out_aux4", out_aux4, (n, 4), dt, dev) if out_aux4 is not None else torch.empty((n, 4), dtype=dt, device=dev)
             _lib.check(
                 lib.pnp_ik_solve_packed_f32(_ptr(targets), _ptr(q_init), stride, n, ctypes.byref(params), _ptr(q8),
                                             _ptr(aux), _ptr(counters), _stream()),
@@ -325,13 +356,29 @@ def move_plan_order(q_start: torch.Tensor, target: torch.Tensor, kinematics="aut
     return order
 
 
+def move_plan_order_check(order: torch.Tensor) -> int:
+    """Number of entries of ``order`` (int32[N], CUDA) that are outside [0, N) or repeat an earlier entry; 0 means
+    a permutation (pnp_move_plan_order_check).  Synchronises to read the count."""
+    lib = _lib.load()
+    order = _check_cuda("order", order, torch.int32, ())
+    n = order.shape[0]
+    dev = order.device
+    bitmap = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=dev)
+    bad = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pnp_move_plan_order_check(_ptr(order), n, _ptr(bitmap), _ptr(bad), _stream()), "pnp_move_plan_order_check")
+    return int(bad.item())
+
+
 def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParams, pos_thresh: float = 0.01,
                  max_traj_points: int = 200, step_size: float = 0.01, max_outer: int = 0, traj_cap: int = 256,
-                 counters: Optional[torch.Tensor] = None, order="auto", out: Optional[dict] = None):
+                 counters: Optional[torch.Tensor] = None, order="auto", out: Optional[dict] = None,
+                 validate_order: bool = True):
     """Batched MoveIKSkill.reset planner (skills/move.py:76-191): CUDA tensors f32 or f64.
 
     ``order``: "auto" (longest plans first from N = 2^16 up, see move_plan_order), None (index order) or a
-    tensor from move_plan_order; it changes the schedule, never the result.  ``out``: the dict of a previous
+    tensor from move_plan_order; it changes the schedule, never the result (a caller-made tensor is checked to be a
+    permutation unless ``validate_order=False``).  ``out``: the dict of a previous
     call with the same N / traj_cap / dtype, whose buffers are then reused (trajectory rows beyond traj_len
     keep their old contents); fresh trajectory storage is zero-filled.
 
@@ -369,6 +416,10 @@ def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParam
         order = _check_cuda("order", order, torch.int32, ())
         if order.shape[0] != n:
             raise ValueError("order disagrees with q_start on N")
+        if validate_order:  # one pass over a bitmap; costs a device->host read of one word
+            bad = move_plan_order_check(order)
+            if bad:
+                raise ValueError(f"order is not a permutation of [0, {n}): {bad} entries are out of range or repeated")
     fn = lib.pnp_move_ik_plan_ordered_f32 if dt == torch.float32 else lib.pnp_move_ik_plan_ordered_f64
     with torch.cuda.device(dev):
         _lib.check(
@@ -402,8 +453,8 @@ def reward(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, 
         if t.shape[0] != n:
             raise ValueError(f"{name} disagrees with achieved_goal on N")
     dev = ag.device
-    rew = out if out is not None else torch.empty((n,), dtype=torch.float32, device=dev)
-    succ = out_success if out_success is not None else (
+    rew = _check_out("out", out, (n,), torch.float32, dev) if out is not None else torch.empty((n,), dtype=torch.float32, device=dev)
+    succ = _check_out("out_success", out_success, (n,), torch.float32, dev) if out_success is not None else (
         torch.empty((n,), dtype=torch.float32, device=dev) if want_success else None)
     fn = lib.pnp_reward_f32 if dt == torch.float32 else lib.pnp_reward_f64
     with torch.cuda.device(dev):
@@ -476,7 +527,7 @@ def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewar
     """HER relabel + reward + optional VecNormalize over N stored transitions (CUDA float32).
 
     obs / next_obs: [N,25] rows (observation19 | achieved_goal3 | desired_goal3); future_idx int32[N]
-    (row whose next achieved_goal becomes the goal, < 0 keeps the stored one); ee_quat[N,4];
+    (row whose next achieved_goal becomes the goal; < 0 or >= N keeps the stored one); ee_quat[N,4];
     task_index int32[N].  ``future_ag`` [N,3] (optional): the next achieved goals as a separate table
     (SB3's ``next_observations["achieved_goal"]``); the goal gather then reads this L2-sized table instead
     of the 100-byte rows.  Returns (out_obs[N,25], out_next_obs[N,25], reward[N], is_success[N] | None)."""
@@ -494,9 +545,9 @@ def her_relabel(obs, next_obs, future_idx, ee_quat, task_index, params: PnpRewar
         if t is not None and t.shape[0] != n:
             raise ValueError(f"{name} disagrees with obs on N")
     dev = obs.device
-    o = out_obs if out_obs is not None else torch.empty_like(obs)
-    x = out_next_obs if out_next_obs is not None else torch.empty_like(next_obs)
-    r = out_reward if out_reward is not None else torch.empty((n,), dtype=torch.float32, device=dev)
+    o = _check_out("out_obs", out_obs, (n, 25), torch.float32, dev) if out_obs is not None else torch.empty_like(obs)
+    x = _check_out("out_next_obs", out_next_obs, (n, 25), torch.float32, dev) if out_next_obs is not None else torch.empty_like(next_obs)
+    r = _check_out("out_reward", out_reward, (n,), torch.float32, dev) if out_reward is not None else torch.empty((n,), dtype=torch.float32, device=dev)
     sc = torch.empty((n,), dtype=torch.float32, device=dev) if want_success else None
     with torch.cuda.device(dev):
         _lib.check(
@@ -550,13 +601,15 @@ def _as_host(name: str, a, dtype, shape_tail) -> np.ndarray:
 
 
 def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out: Optional[dict] = None,
-                  packed: bool = True) -> dict:
+                  packed: bool = True, compact: bool = False) -> dict:
     """Host path: NumPy / CPU-tensor inputs (float32), NumPy outputs.
 
     packed=True (default) goes through pnp_ik_solve_packed_host_f32: the device writes two packed
     records per query and the returned q / final_pos / pos_error / iterations are views into the
     host copies ``out["q8"]`` [N,8] and ``out["aux4"]`` [N,4] (preallocate them pinned for full
-    copy/compute overlap).  packed=False uses the separate-array operator."""
+    copy/compute overlap).  compact=True (pnp_ik_solve_compact_host_f32) brings back ``out["q8"]`` only -
+    q, iterations, converged, success in 32 bytes per query; final_pos / pos_error are not computed.
+    packed=False uses the separate-array operator."""
     lib = _lib.load()
     targets = _as_host("targets", targets, np.float32, (3,))
     n = targets.shape[0]
@@ -570,10 +623,24 @@ def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out
     else:
         raise ValueError(f"q_init must have shape (7,) or ({n}, 7), got {q_init.shape}")
     out = out or {}
+
+    def buf(key, shape, dtype):
+        return _check_out_np(f"out[{key!r}]", out[key], shape, dtype) if out.get(key) is not None else np.empty(shape, dtype)
+
     counters = np.zeros(4, dtype=np.uint64)
+    if compact:
+        q8 = buf("q8", (n, 8), np.float32)
+        _lib.check(
+            lib.pnp_ik_solve_compact_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
+                                              ctypes.byref(params), _np_ptr(q8), _np_ptr(counters)),
+            "pnp_ik_solve_compact_host",
+        )
+        word = q8[:, 7].view(np.int32)
+        return dict(q=q8[:, :7], q8=q8, iterations=word & 0xFFFFFF, converged=(word & (1 << 24)) != 0,
+                    success=(word & (2 << 24)) != 0, counters=counters)
     if packed:
-        q8 = out.get("q8") if out.get("q8") is not None else np.empty((n, 8), np.float32)
-        aux = out.get("aux4") if out.get("aux4") is not None else np.empty((n, 4), np.float32)
+        q8 = buf("q8", (n, 8), np.float32)
+        aux = buf("aux4", (n, 4), np.float32)
         _lib.check(
             lib.pnp_ik_solve_packed_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
                                              ctypes.byref(params), _np_ptr(q8), _np_ptr(aux), _np_ptr(counters)),
@@ -581,11 +648,11 @@ def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out
         )
         q, err, fpos, _ = unpack_ik(q8, aux)
         return HostIKResult(q=q, final_pos=fpos, pos_error=err, q8=q8, aux4=aux, counters=counters)
-    q = out.get("q") if out.get("q") is not None else np.empty((n, 7), np.float32)
-    fpos = out.get("final_pos") if out.get("final_pos") is not None else np.empty((n, 3), np.float32)
-    err = out.get("pos_error") if out.get("pos_error") is not None else np.empty((n,), np.float32)
-    iters = out.get("iterations") if out.get("iterations") is not None else np.empty((n,), np.int32)
-    flags = out.get("flags") if out.get("flags") is not None else np.empty((n,), np.uint8)
+    q = buf("q", (n, 7), np.float32)
+    fpos = buf("final_pos", (n, 3), np.float32)
+    err = buf("pos_error", (n,), np.float32)
+    iters = buf("iterations", (n,), np.int32)
+    flags = buf("flags", (n,), np.uint8)
     _lib.check(
         lib.pnp_ik_solve_host_f32(host_ctx(chunk_rows), _np_ptr(targets), _np_ptr(q_init), stride, n,
                                   ctypes.byref(params), _np_ptr(q), _np_ptr(fpos), _np_ptr(err), _np_ptr(iters),
@@ -608,6 +675,26 @@ def ik_solve_one_host(target3: np.ndarray, q_init7: np.ndarray, params: PnpIkPar
     return out
 
 
+_one_reward_out = None
+
+
+def reward_one_host(ag3: np.ndarray, dg3: np.ndarray, ee_pos3: np.ndarray, ee_quat4: np.ndarray, fingers_width: float,
+                    task_index: int, params: PnpRewardParams):
+    """One row through the mapped-mailbox path (pnp_reward_one_host_f64): contiguous float64 arrays in,
+    (reward np.float32, is_success float, bits int) out - bits = placed | gripped << 1 | threshold_adjacent << 2."""
+    global _one_reward_out
+    lib = _lib.load()
+    if _one_reward_out is None:
+        _one_reward_out = (ctypes.c_float(), ctypes.c_float(), ctypes.c_uint32())
+    r, sc, bits = _one_reward_out
+    rc = lib.pnp_reward_one_host_f64(host_ctx(0), ag3.ctypes.data, dg3.ctypes.data, ee_pos3.ctypes.data,
+                                     ee_quat4.ctypes.data, float(fingers_width), int(task_index), ctypes.byref(params),
+                                     ctypes.byref(r), ctypes.byref(sc), ctypes.byref(bits))
+    if rc:
+        _lib.check(rc, "pnp_reward_one_host")
+    return np.float32(r.value), sc.value, bits.value
+
+
 def reward_host(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardParams, want_success=True,
                 chunk_rows: int = 0, out: Optional[np.ndarray] = None, out_success: Optional[np.ndarray] = None):
     """Host path: NumPy rows (float32 or float64 storage) -> reward float32[N], success, counters."""
@@ -625,8 +712,9 @@ def reward_host(ag, dg, ee_pos, ee_quat, width, task_index, params: PnpRewardPar
                     ("task_index", task_index)):
         if t.shape[0] != n:
             raise ValueError(f"{name} disagrees with achieved_goal on N")
-    rew = out if out is not None else np.empty((n,), np.float32)
-    succ = out_success if out_success is not None else (np.empty((n,), np.float32) if want_success else None)
+    rew = _check_out_np("out", out, (n,), np.float32) if out is not None else np.empty((n,), np.float32)
+    succ = _check_out_np("out_success", out_success, (n,), np.float32) if out_success is not None else (
+        np.empty((n,), np.float32) if want_success else None)
     counters = np.zeros(4, dtype=np.uint64)
     fn = lib.pnp_reward_host_f32 if dt == np.float32 else lib.pnp_reward_host_f64
     _lib.check(

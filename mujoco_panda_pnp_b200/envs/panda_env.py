@@ -81,10 +81,39 @@ class FrankaRewardModel:
 
     # ---- helpers -------------------------------------------------------------------------
     def _params(self):
-        return engine.reward_params(
-            self.reward_type, len(self.task_sequence), self.initial_object_height, self.distance_threshold,
-            self.high_pick_z,
-        )
+        key = (self.reward_type, len(self.task_sequence), self.initial_object_height, self.distance_threshold,
+               self.high_pick_z)
+        cached = getattr(self, "_params_cache", None)
+        if cached is None or cached[0] != key:  # the attributes are public and may be reassigned between calls
+            cached = self._params_cache = (key, engine.reward_params(*key))
+        return cached[1]
+
+    def _compute_reward_one(self, achieved_goal, desired_goal, info):
+        """Scalar call (goals (3,), the shape FrankaEnv.step and test/reward_test.py use): one kernel launch through
+        the library's mapped mailbox (pnp_reward_one_host_f64), FP64, bit-exact.  Returns np.float32."""
+        st = getattr(self, "_one_stage", None)
+        if st is None:
+            st = self._one_stage = (np.empty(3), np.empty(3), np.empty(3), np.empty(4))
+        ag, dg, ee, eq = st
+        ag[:] = achieved_goal
+        dg[:] = desired_goal
+        if info:
+            ee[:] = info["ee_pos"] if "ee_pos" in info else self.get_ee_position()
+            eq[:] = info["ee_quat"] if "ee_quat" in info else self.get_ee_orientation()
+            width = info["fingers_width"] if "fingers_width" in info else self.get_fingers_width()
+            task = info["task_index"] if "task_index" in info else self.current_task_index
+        else:
+            ee[:] = self.get_ee_position()
+            eq[:] = self.get_ee_orientation()
+            width, task = self.get_fingers_width(), self.current_task_index
+        params = self._params()
+        if self.device is not None and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                r, succ, bits = engine.reward_one_host(ag, dg, ee, eq, width, task, params)
+        else:
+            r, succ, bits = engine.reward_one_host(ag, dg, ee, eq, width, task, params)
+        self.last_counters = np.array([1, bits & 1, (bits >> 1) & 1, (bits >> 2) & 1], dtype=np.uint64)
+        return r
 
     def _state_from_info(self, info, n: Optional[int]):
         """Collect ee_pos / ee_quat / fingers_width / task_index for n rows (None = scalar)."""
@@ -158,16 +187,15 @@ class FrankaRewardModel:
         if len(shape) == 1:
             if shape != (3,):
                 raise ValueError("goals must have shape (3,) or (N, 3)")
-            st = self._state_from_info(info, None)
-            row = lambda x, k: np.asarray(x, dtype=np.float64).reshape(1, k)  # noqa: E731
-            rew, _ = self._run(
-                row(achieved_goal, 3), row(desired_goal, 3),
-                dict(ee_pos=row(st["ee_pos"], 3), ee_quat=row(st["ee_quat"], 4),
-                     fingers_width=np.asarray(st["fingers_width"], dtype=np.float64).reshape(1),
-                     task_index=np.asarray(st["task_index"], dtype=np.int32).reshape(1)),
-                want_success=False,
-            )
-            return np.float32(rew[0])
+            if info is not None and not isinstance(info, Mapping):
+                raise ValueError("a scalar compute_reward takes a dict `info` (or None)")
+            if not torch.cuda.is_available():
+                raise engine._lib.PnpLibraryError("no CUDA device: compute_reward has no CPU path")
+            if isinstance(achieved_goal, torch.Tensor):
+                achieved_goal = achieved_goal.detach().cpu().numpy()
+            if isinstance(desired_goal, torch.Tensor):
+                desired_goal = desired_goal.detach().cpu().numpy()
+            return self._compute_reward_one(achieved_goal, desired_goal, info)
         if len(shape) != 2 or shape[1] != 3:
             raise ValueError("goals must have shape (3,) or (N, 3)")
         st = self._state_from_info(info, shape[0])

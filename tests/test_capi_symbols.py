@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert set(declared_functions()) <= exported
     for name in declared_functions():
         assert hasattr(cuda_lib, name)
-    assert cuda_lib.pnp_abi_version() == 1
+    assert cuda_lib.pnp_abi_version() == 2
 
 
 def test_struct_layouts_match_header(cuda_lib):
@@ -50,9 +50,10 @@ def test_header_constants_match_binding():
     text = open(HEADER).read()
     defs = {m.group(1): int(m.group(2).rstrip("u")) for m in re.finditer(r"#define\s+(PNP_[A-Z0-9_]+)\s+(-?\d+u?)\b", text)}
     for name in ("PNP_KIN_AUTO", "PNP_KIN_GENERIC", "PNP_KIN_SPECIALIZED", "PNP_KIN_SPEC_LANE", "PNP_KIN_SPEC_PAIR",
-                 "PNP_IK_CONVERGED", "PNP_IK_SUCCESS"):
+                 "PNP_KIN_SPEC_PAIR_HYBRID", "PNP_IK_CONVERGED", "PNP_IK_SUCCESS"):
         assert defs[name] == getattr(_lib, name), name
-    assert _lib.KINEMATICS == {"auto": 0, "generic": 1, "specialized": 2, "spec_lane": 3, "spec_pair": 4}
+    assert _lib.KINEMATICS == {"auto": 0, "generic": 1, "specialized": 2, "spec_lane": 3, "spec_pair": 4,
+                               "spec_pair_hybrid": 5}
     assert [defs[f"PNP_IK_CNT_{k}"] for k in ("N", "CONVERGED", "SUCCESS", "ITERATIONS")] == [0, 1, 2, 3]
 
 
