@@ -8,15 +8,21 @@ Headline line (one JSON object on stdout, rank 0):
   metric  panda_ik_converged_solves_per_s          (BASELINE.json: "Panda IK solves/s ...")
   step    one pass of the IK hot path over the rank's batch: 2^24 cold reachable targets per
           GPU from the neutral pose, reference defaults (BASELINE cfg5 sweep point; the cfg2
-          batch of 4096 is a latency case and is reported under "cfg2").  Weak scaling.
+          batch of 4096 is a latency case and is reported under "latency").  Weak scaling.
   value   converged solves of all ranks / max-over-ranks device time, inputs resident in HBM
   e2e     same metric through the host-buffer C-ABI operator (pnp_ik_solve_packed_host_f32): pinned host
-          inputs -> H2D -> kernel -> D2H of every IKResult field, all inside the timed region
+          inputs -> H2D -> kernel -> D2H of every IKResult field, all inside the timed region;
+          e2e.link = the same bytes moved by bare cudaMemcpyAsync in both directions at once, no kernels
+          (what the box's PCIe / host side delivers to this many ranks at the same time);
+          e2e_compact = the 32-byte-record operator (q + iterations + flags only)
   roofline     IK kernel vs the FP32 CUDA-core peak (measured live by pnp_probe_fp32_peak;
                MEASURED_PEAKS.json has no FP32 entry) - the schema's "hbm"/"tensor" do not apply
   reward       the second half of the metric (HER reward evals/s, cfg3: 16 777 216 rows, FP32
                storage, 64 B/row) with its own value / e2e / HBM roofline / cpu_baseline
+  latency      cfg1 (one solve() host to host), cfg2 (4096 cold targets, one launch), one scalar
+               compute_reward() - each beside the C port and the NumPy port of the same call
   cpu_baseline the C oracle port on all host cores over a bounded sample of the same workload
+  headline     both halves of BASELINE.json's metric once more, last on the line
 """
 
 from __future__ import annotations
@@ -46,6 +52,18 @@ NEUTRAL = np.array([0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79])
 
 def host_cores() -> int:
     return len(os.sched_getaffinity(0))
+
+
+def bench_config(world: int, log2_n_ik: int = LOG2_N_IK, log2_n_reward: int = LOG2_N_REWARD) -> dict:
+    """What is measured - the same dict in our arm and in the reference arm."""
+    return {
+        "workload": f"cfg5 cold IK, 2^{log2_n_ik} reachable targets (FK of q* ~ U(joint range)) per GPU from the neutral "
+                    "pose, max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1",
+        "second_half": f"cfg3 dense reward, 2^{log2_n_reward} HER-relabelled rows per GPU, FP32 storage",
+        "l2_hygiene": f"inputs+outputs per step {(1 << log2_n_ik) * 60 / 1e6:.0f} MB (IK) / {(1 << log2_n_reward) * 64 / 1e6:.0f} MB "
+                      "(reward) > 126 MB L2, no flush needed",
+        "parallelism": f"batch-index shards x{world}, NCCL all_reduce of 4 counters",
+    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -222,6 +240,55 @@ def cpu_ik_baseline(budget_s: float = 12.0) -> dict:
     return out
 
 
+def cpu_latency_baselines(targets4096: np.ndarray) -> dict:
+    """The CPU side of the three latency configs: the C port and the NumPy port of the same call, timed here."""
+    from oracle import c_oracle, ik_oracle, mj_oracle, reward_oracle
+
+    c_oracle, chain, model = cpu_ik_setup()
+    cores = host_cores()
+    out = {}
+    grasp = [np.array(t) for t in [(1.415, 0, 0.73), (1.415, 0, 1.03), (1.415, 0, 0.43)]]
+    for t_ in grasp:
+        c_oracle.ik_solve(chain, t_[None], NEUTRAL, nthreads=1)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        for t_ in grasp:
+            c_oracle.ik_solve(chain, t_[None], NEUTRAL, nthreads=1)
+    c_us = (time.perf_counter() - t0) / 600 * 1e6
+    ctl = ik_oracle.JacobianIKController(model, mj_oracle.MjData(model))
+    t0 = time.perf_counter()
+    for t_ in grasp:
+        ctl.solve(t_, NEUTRAL)
+    np_us = (time.perf_counter() - t0) / 3 * 1e6
+    out["cfg1"] = {"c_port_us_per_solve": c_us, "numpy_port_us_per_solve": np_us, "cores": 1,
+                   "note": "same 3 grasp poses; C port = one ctypes call per solve, NumPy port = oracle/ik_oracle.py "
+                           "(the reference's control flow over the restated engine, no mj_forward collision stages)"}
+    c_oracle.ik_solve(chain, targets4096, NEUTRAL, nthreads=cores)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        c_oracle.ik_solve(chain, targets4096, NEUTRAL, nthreads=cores)
+        ts.append(time.perf_counter() - t0)
+    out["cfg2"] = {"c_port_us_per_batch": min(ts) * 1e6, "cores": cores,
+                   "numpy_port_us_per_batch_est": np_us * 4096, "note": "NumPy port: per-solve time x 4096, one core"}
+    h = cpu_reward_rows(64)
+    c_oracle.reward(*[x[:1] for x in h], nthreads=1)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        for i in range(64):
+            c_oracle.reward(*[x[i:i + 1] for x in h], nthreads=1)
+    rc_us = (time.perf_counter() - t0) / (50 * 64) * 1e6
+    t0 = time.perf_counter()
+    for _ in range(20):
+        for i in range(64):
+            reward_oracle.compute_reward(h[0][i], h[1][i], h[2][i], h[3][i], h[4][i], h[5][i])
+    rn_us = (time.perf_counter() - t0) / (20 * 64) * 1e6
+    out["reward_scalar"] = {"c_port_us_per_call": rc_us, "numpy_port_us_per_call": rn_us, "cores": 1,
+                            "note": "NumPy port = oracle/reward_oracle.compute_reward, the reference's own statements "
+                                    "(panda_env.py:205-245) with the simulator getters replaced by arguments"}
+    return out
+
+
 def cpu_reward_rows(n, seed=0):
     import torch
 
@@ -256,15 +323,25 @@ def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import torch
+
+    from mujoco_panda_pnp_b200 import synthetic
+
     c_oracle, chain, model = cpu_ik_setup()
     cores = host_cores()
     calib = cpu_ik_targets(c_oracle, chain, model, 8192)
     t0 = time.perf_counter()
     c_oracle.ik_solve(chain, calib, NEUTRAL, nthreads=cores)
     rate = len(calib) / (time.perf_counter() - t0)
-    budget = min(3.0, 150.0 / max(1, args.steps + args.warmup))  # whole run within a few minutes
-    n = int(min(max(rate * budget, 4096), 1 << 22))
-    targets = cpu_ik_targets(c_oracle, chain, model, n)
+    # Each step = the SAME workload as our arm: 2^24 cold targets of the same generator family (q* ~ U(joint range),
+    # target = FK(q*), seed 1234).  Only if the whole K + W run would not end within ~10 minutes on this box's cores is
+    # a step cut down to a bounded sample of that batch (said in cpu_baseline.sample; the metric is a rate).
+    n_full = 1 << args.log2_n_ik
+    budget_s = 600.0 / max(1, args.steps + args.warmup)
+    n = n_full if n_full / rate <= budget_s else int(max(rate * budget_s, 4096))
+    qstar = synthetic.random_joint_configs(n, model.jnt_range[:7, 0], model.jnt_range[:7, 1], seed=1234, dtype=torch.float64).numpy()
+    targets = c_oracle.fk_jac(chain, qstar, nthreads=cores)[0]
+    del qstar
     for _ in range(args.warmup):
         c_oracle.ik_solve(chain, targets, NEUTRAL, nthreads=cores)
     conv = 0
@@ -275,19 +352,19 @@ def run_reference(args) -> int:
     dt = time.perf_counter() - t0
     value = conv / dt
     rw = cpu_reward_baseline(budget_s=5.0)
-    sample = (f"each step = {n} cold reachable targets from neutral (bounded sample of the 2^{LOG2_N_IK}-per-GPU "
-              f"workload), {cores} threads")
+    sample = (f"each step = {'the full batch of ' if n == n_full else 'a bounded sample of '}{n} cold reachable targets from "
+              f"neutral (workload: 2^{args.log2_n_ik} per GPU), {cores} threads, FP64 C restatement of ik_solver.py:50-101")
     line = {
         "impl": "reference", "metric": "panda_ik_converged_solves_per_s", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg5 cold IK, 2^{LOG2_N_IK} reachable targets per GPU from the neutral pose, "
-                               "max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1", "cpu_sample": sample},
+        "config": bench_config(args.gpus, args.log2_n_ik, args.log2_n_reward),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reward": {"metric": "her_reward_evals_per_s", "value": rw["value"], "unit": "rows/s", "cpu_baseline": rw},
         "note": "reference arm = oracle port (C, FP64, all host threads): mujoco is not installable in this image, "
                 "see DESIGN.md; it omits mj_forward's collision/constraint work and is faster than the real reference",
+        "headline": {"ik_solves_per_s": value, "reward_rows_per_s": rw["value"], "cores": cores},
     }
     emit(line)
     return 0
@@ -420,6 +497,46 @@ def run_ours(args) -> int:
     ik_h2d = n_ik * 12 + 28
     ik_d2h = n_ik * (32 + 16) + 32  # packed records: q0..q6,pos_error | final_pos xyz, iterations|flags
 
+    # the 32-byte-record operator: q + iterations + flags only (final_pos / pos_error not brought back)
+    for _ in range(2):
+        engine.ik_solve_host(h_targets, h_neutral, params, out=h_out, compact=True)
+    D.barrier()
+    t0 = time.perf_counter()
+    conv_c = 0
+    for _ in range(Ke):
+        r = engine.ik_solve_host(h_targets, h_neutral, params, out=h_out, compact=True)
+        conv_c += int(r["counters"][1])
+    ik_e2e_c_s = D.reduce_max(time.perf_counter() - t0, dev)
+    ik_e2e_c = int(D.reduce_counters(torch.tensor([conv_c, 0, 0, 0], dtype=torch.int64, device=dev))[0]) / ik_e2e_c_s
+    # what the link delivers: the same bytes per step as bare copies in both directions at once, no kernels, all ranks
+    # at the same time (pinned host memory, one cudaMemcpyAsync per direction on its own stream)
+    d_up = torch.empty(n_ik * 3, device=dev)
+    d_dn = torch.empty(n_ik * 12, device=dev)
+    h_up = h_targets.reshape(-1)
+    h_dn = torch.empty(n_ik * 12).pin_memory()
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def raw_copies():
+        with torch.cuda.stream(s_up):
+            d_up.copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_dn.copy_(d_dn, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+
+    raw_copies()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        raw_copies()
+    link_s = D.reduce_max(time.perf_counter() - t0, dev) / Ke
+    link = {"h2d_plus_d2h_gbs_all_ranks": (n_ik * 60.0) * world / link_s / 1e9,
+            "d2h_gbs_all_ranks": (n_ik * 48.0) * world / link_s / 1e9,
+            "ceiling_solves_per_s": float(c[1]) / float(c[0]) * n_ik * world / link_s,
+            "how": "bare pinned cudaMemcpyAsync of one step's bytes (12 B/query up, 48 B/query down) on two streams, "
+                   "all ranks at once, max over ranks: the e2e value cannot exceed ceiling_solves_per_s on this box"}
+    del d_up, d_dn, h_dn
+
     h_rows = [rows[k].cpu().pin_memory() for k in REWARD_KEYS]
     h_rw = torch.empty(n_rw, dtype=torch.float32).pin_memory().numpy()
     for _ in range(2):
@@ -439,8 +556,8 @@ def run_ours(args) -> int:
         for _ in range(3):
             f()
         _, ts = cuda_time_steps(f, 20, torch)
-        side["cfg2"] = {"workload": "4096 cold targets, 1 launch", "ms_per_launch": statistics.median(ts),
-                        "solves_per_s": 4096 / (statistics.median(ts) * 1e-3)}
+        side["cfg2"] = {"workload": "4096 cold targets, 1 launch (ik_solve_small_kernel)", "ms_per_launch": statistics.median(ts),
+                        "us_per_launch": statistics.median(ts) * 1e3, "solves_per_s": 4096 / (statistics.median(ts) * 1e-3)}
         n_env = 1 << 20
         w = synthetic.waypoint_envs(n_env, seed=0, device=dev)
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -469,6 +586,21 @@ def run_ours(args) -> int:
         side["cfg1"] = {"workload": "single-query solve() to the 3 shelf grasp poses from neutral (test/ik_test.py path)",
                         "us_per_solve_host_to_host": (time.perf_counter() - t0) / (3 * reps) * 1e6,
                         "iterations": its[:3]}
+        # one scalar compute_reward(achieved_goal (3,), desired_goal (3,), info) host to host: what FrankaEnv.step pays
+        # once per env.step (envs/panda_env.py:176-181), through the mapped mailbox
+        from mujoco_panda_pnp_b200.envs import FrankaShelfPNPReward
+
+        renv = FrankaShelfPNPReward("dense")
+        hr = [rows[k][:64].double().cpu().numpy() if rows[k].dtype != torch.int32 else rows[k][:64].cpu().numpy() for k in REWARD_KEYS]
+        infos = [dict(ee_pos=hr[2][i], ee_quat=hr[3][i], fingers_width=float(hr[4][i]), task_index=int(hr[5][i])) for i in range(64)]
+        for i in range(64):
+            renv.compute_reward(hr[0][i], hr[1][i], infos[i])
+        t0 = time.perf_counter()
+        for _ in range(20):
+            for i in range(64):
+                renv.compute_reward(hr[0][i], hr[1][i], infos[i])
+        side["reward_scalar"] = {"workload": "one compute_reward() with (3,) goals, host in -> np.float32 out (pnp_reward_one_host_f64)",
+                                 "us_per_call_host_to_host": (time.perf_counter() - t0) / (20 * 64) * 1e6}
         # whole MoveIKSkill.reset planner, 2^20 envs in one launch (plans are 40-200 solves long and a lane
         # owns one env at a time: below ~2^20 envs the launch is dominated by load imbalance, 2^18 runs at 0.7 of this rate)
         n_pl = 1 << 20
@@ -575,53 +707,68 @@ def run_ours(args) -> int:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_ik = cpu_ik_baseline()
         cpu_rw = cpu_reward_baseline()
+        lat = cpu_latency_baselines(targets[:4096].double().cpu().numpy())
+        for key in ("cfg1", "cfg2", "reward_scalar"):
+            if key in side:
+                side[key]["cpu"] = lat[key]
     D.barrier()
 
     if rank == 0:
+        latency = {k: side.pop(k) for k in ("cfg1", "cfg2", "reward_scalar") if k in side}
+        ik_roofline = {
+            "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": ik_tflops / fp32_peak, "frac_of_nominal_74.4": ik_tflops / 74.4,
+            "traffic": ncu_traffic("ik_solve_v_kernel" if specialized else "ik_solve_kernel", n_ik),
+            "traffic_note": "DRAM bytes/launch from the ncu capture (48 B/query; algorithmic 60 B, part of the output is still in L2 at kernel end)",
+            "kernel": ("ik_solve_v_kernel<F2|F2H,packed,bcast> (two queries per lane on FFMA2/FMUL2/FADD2)" if specialized
+                       else "ik_solve_kernel<float,GenericKin,packed>"),
+            "kernel_ms": ik_kernel_ms,
+            "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json; nominal 148 x 128 x 2 x 1.965 GHz = 74.4)",
+            "algorithmic": f"{IK_FLOP_PER_ITER:.0f} FLOP x iterations + {IK_FLOP_PER_SOLVE:.0f} per solve (SURVEY 8d)",
+        }
+        rw_roofline = {"bound": "hbm", "achieved": rw_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": rw_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("reward_kernel", n_rw),
+                       "kernel": "reward_kernel<float,true>", "kernel_ms": rw_kernel_ms, "peak_source": peaks["source"],
+                       "algorithmic": "64 B/row (60 in + 4 out)"}
+        rw_e2e_d = {"value": rw_e2e, "unit": "rows/s", "h2d_bytes_per_step": n_rw * 60, "d2h_bytes_per_step": n_rw * 4,
+                    "api": "pnp_reward_host_f32",
+                    "note": "host-resident rows are PCIe bound (64 B/row over a ~57 GB/s link): about the speed of the CPU "
+                            "port; the GPU reward pays when the rows are already resident (value, her_relabel)"}
+        e2e = {"value": ik_e2e, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": ik_d2h,
+               "steps": Ke, "api": "pnp_ik_solve_packed_host_f32 (pinned host buffers, 3-stream chunk pipeline)", "link": link}
+        e2e_compact = {"value": ik_e2e_c, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": n_ik * 32 + 32,
+                       "steps": Ke, "api": "pnp_ik_solve_compact_host_f32 (q, iterations, converged, success; no final_pos / pos_error)"}
         line = {
             "metric": "panda_ik_converged_solves_per_s", "value": ik_value, "unit": "solves/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ik_ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"cfg5 cold IK, 2^{args.log2_n_ik} reachable targets per GPU from the neutral pose, "
-                            "max_iters=100 pos_thresh=1e-3 damping=1e-2 step_limit=0.1",
-                "l2_hygiene": f"inputs+outputs per step {n_ik * 60 / 1e6:.0f} MB (IK) / {n_rw * 64 / 1e6:.0f} MB (reward) "
-                              "> 126 MB L2, no flush needed",
-                "kinematics": "specialized" if specialized else "generic",
-                "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
-                "parallelism": f"batch-index shards x{world}, NCCL all_reduce of 4 counters",
-                "numa_bound_cpus": numa,
-            },
-            "e2e": {"value": ik_e2e, "unit": "solves/s", "h2d_bytes_per_step": ik_h2d, "d2h_bytes_per_step": ik_d2h,
-                    "steps": Ke, "api": "pnp_ik_solve_packed_host_f32 (pinned host buffers, 3-stream chunk pipeline)"},
+            "config": bench_config(world, args.log2_n_ik, args.log2_n_reward),
+            "workload_stats": {"kinematics": "specialized" if specialized else "generic",
+                               "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
+                               "numa_bound_cpus": numa, "threshold_adjacent_reward_rows": int(rw_counters[3].item())},
+            "e2e": e2e,
+            "e2e_compact": e2e_compact,
             "gpu_launches": int(launches_ik),
             "clocks": clocks,
-            "roofline": {
-                "bound": "fp32", "achieved": ik_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ik_tflops / fp32_peak, "traffic": ncu_traffic("ik_solve_v_kernel" if specialized else "ik_solve_kernel", n_ik),
-                "traffic_note": "DRAM bytes/launch from the ncu capture (48 B/query; algorithmic 60 B, part of the output is still in L2 at kernel end)",
-                "kernel": ("ik_solve_v_kernel<F2,packed,bcast> (two queries per lane on FFMA2/FMUL2/FADD2)" if specialized
-                           else "ik_solve_kernel<float,GenericKin,packed>"),
-                "kernel_ms": ik_kernel_ms,
-                "peak_source": "pnp_probe_fp32_peak, measured in this run (no FP32 entry in MEASURED_PEAKS.json)",
-                "algorithmic": f"{IK_FLOP_PER_ITER:.0f} FLOP x iterations + {IK_FLOP_PER_SOLVE:.0f} per solve (SURVEY 8d)",
-            },
+            "roofline": ik_roofline,
             "cpu_baseline": cpu_ik,
+            **side,
+            "latency": latency,
             "reward": {
                 "metric": "her_reward_evals_per_s", "value": rw_value, "unit": "rows/s",
                 "workload": f"cfg3 dense reward, 2^{args.log2_n_reward} HER-relabelled rows per GPU, FP32 storage",
-                "ms_per_step": rw_ms_total / K,
-                "e2e": {"value": rw_e2e, "unit": "rows/s", "h2d_bytes_per_step": n_rw * 60, "d2h_bytes_per_step": n_rw * 4,
-                        "api": "pnp_reward_host_f32"},
-                "roofline": {"bound": "hbm", "achieved": rw_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": rw_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("reward_kernel", n_rw),
-                             "kernel": "reward_kernel<float,true>",
-                             "kernel_ms": rw_kernel_ms, "peak_source": peaks["source"],
-                             "algorithmic": "64 B/row (60 in + 4 out)"},
-                "cpu_baseline": cpu_rw,
-                "threshold_adjacent_rows": int(rw_counters[3].item()),
+                "ms_per_step": rw_ms_total / K, "e2e": rw_e2e_d, "roofline": rw_roofline, "cpu_baseline": cpu_rw,
             },
-            **side,
+            # both halves of BASELINE.json's metric once more, LAST on the line (the driver keeps the tail)
+            "headline": {
+                "ik": {"solves_per_s": ik_value, "roofline_frac": ik_tflops / fp32_peak, "e2e_solves_per_s": ik_e2e,
+                       "e2e_compact_solves_per_s": ik_e2e_c, "e2e_link_ceiling_solves_per_s": link["ceiling_solves_per_s"],
+                       "cpu_port_solves_per_s": cpu_ik["value"] if cpu_ik else None, "cpu_cores": cpu_ik["cores"] if cpu_ik else None},
+                "reward": {"rows_per_s": rw_value, "roofline_frac": rw_gbs / peaks["hbm_gbs"], "GBps": rw_gbs,
+                           "e2e_rows_per_s": rw_e2e, "cpu_port_rows_per_s": cpu_rw["value"] if cpu_rw else None},
+                "latency_us": {k: (v.get("us_per_solve_host_to_host") or v.get("us_per_launch") or v.get("us_per_call_host_to_host"))
+                               for k, v in latency.items()},
+            },
         }
         emit(line)
     if world > 1:

@@ -950,7 +950,7 @@ int pnp_her_relabel_table_f32(const float* obs, const float* next_obs, const int
     };
     if (overlap(out_obs, obs) || overlap(out_obs, next_obs) || overlap(out_next_obs, obs) || overlap(out_next_obs, next_obs) ||
         overlap(out_obs, out_next_obs))
-      return fail(PNP_EINVAL, "her_relabel: outputs must not overlap the inputs or each other (future goals are gathered from next_obs)");
+      return fail(PNP_EINVAL, "her_relabel: outputs must not alias or overlap the inputs or each other (future goals are gathered from next_obs)");
   }
   if (n > 0 && !aligned16(ee_quat)) return fail(PNP_EINVAL, "her_relabel: ee_quat must be 16-byte aligned");
   DeviceState* s;

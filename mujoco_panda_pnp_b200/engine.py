@@ -9,6 +9,7 @@ tensors and go through the library's own H2D -> kernel -> D2H pipeline (``pnp_*_
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -675,18 +676,18 @@ def ik_solve_one_host(target3: np.ndarray, q_init7: np.ndarray, params: PnpIkPar
     return out
 
 
-_one_reward_out = None
+_tls = threading.local()
 
 
 def reward_one_host(ag3: np.ndarray, dg3: np.ndarray, ee_pos3: np.ndarray, ee_quat4: np.ndarray, fingers_width: float,
                     task_index: int, params: PnpRewardParams):
     """One row through the mapped-mailbox path (pnp_reward_one_host_f64): contiguous float64 arrays in,
     (reward np.float32, is_success float, bits int) out - bits = placed | gripped << 1 | threshold_adjacent << 2."""
-    global _one_reward_out
     lib = _lib.load()
-    if _one_reward_out is None:
-        _one_reward_out = (ctypes.c_float(), ctypes.c_float(), ctypes.c_uint32())
-    r, sc, bits = _one_reward_out
+    outs = getattr(_tls, "reward_out", None)
+    if outs is None:  # per thread: the C call runs without the GIL
+        outs = _tls.reward_out = (ctypes.c_float(), ctypes.c_float(), ctypes.c_uint32())
+    r, sc, bits = outs
     rc = lib.pnp_reward_one_host_f64(host_ctx(0), ag3.ctypes.data, dg3.ctypes.data, ee_pos3.ctypes.data,
                                      ee_quat4.ctypes.data, float(fingers_width), int(task_index), ctypes.byref(params),
                                      ctypes.byref(r), ctypes.byref(sc), ctypes.byref(bits))

@@ -90,6 +90,15 @@ def test_controller_is_a_drop_in(kin_model):
         ctl.solve(np.zeros(2), NEUTRAL)
 
 
+ROT_TOL_RAD = 1e-3  # north_star: ... and to 1e-3 rad
+
+
+def _quat_angle(a, b):
+    """Angle (rad) of the rotation between unit quaternions a and b, row-wise."""
+    d = np.abs(np.sum(a * b, axis=1))
+    return 2.0 * np.arccos(np.clip(d, 0.0, 1.0))
+
+
 def _compare_with_oracle(res, ref, targets, oracle_chain, pos_thresh, flip_budget):
     q = res.q.double().cpu().numpy()
     conv = res.converged.cpu().numpy()
@@ -99,10 +108,20 @@ def _compare_with_oracle(res, ref, targets, oracle_chain, pos_thresh, flip_budge
     conv_flips = int((conv != ref["converged"]).sum())
     assert flips <= flip_budget, (flips, flip_budget)
     assert conv_flips <= max(1, flip_budget // 4)
-    same = conv & ref["converged"] & (iters == ref["iterations"])
-    # reference FK of the GPU's joint solution vs the reference's own final EE position
-    ee = c_oracle.fk_jac(oracle_chain, q, nthreads=8)[0]
+    both = conv & ref["converged"]
+    same = both & (iters == ref["iterations"])
+    # reference FK (position AND orientation) of the GPU's joint solution vs the reference's own final EE pose
+    ee, ee_quat, _ = c_oracle.fk_jac(oracle_chain, q, nthreads=8)
+    ref_quat = c_oracle.fk_jac(oracle_chain, ref["q"], nthreads=8)[1]
     assert np.linalg.norm(ee[same] - ref["final_pos"][same], axis=1).max() < EE_TOL_M
+    rot = _quat_angle(ee_quat, ref_quat)
+    assert rot[same].max() < ROT_TOL_RAD, rot[same].max()
+    # queries whose iteration count flipped (one side crossed pos_thresh a step earlier): both poses lie in the
+    # pos_thresh ball around the target, one DLS step (<= ~pos_thresh of EE travel) apart
+    flipped = both & ~same
+    if flipped.any():
+        assert np.linalg.norm(ee[flipped] - ref["final_pos"][flipped], axis=1).max() <= 2 * pos_thresh
+        assert rot[flipped].max() < 1e-2, rot[flipped].max()
     # every converged GPU solution really is within pos_thresh of its target under reference FK
     assert np.linalg.norm(ee[conv] - targets[conv], axis=1).max() < pos_thresh + 1e-5
     # limits respected
@@ -242,10 +261,12 @@ def test_pair_kernel_is_bit_identical_to_lane_kernel(tree, oracle_chain):
                 cl = torch.zeros(4, dtype=torch.int64, device="cuda")
                 cp = torch.zeros(4, dtype=torch.int64, device="cuda")
                 a = engine.ik_solve(tg, qi, engine.ik_params(max_iters=60, kinematics="spec_lane"), packed=packed, counters=cl)
-                b = engine.ik_solve(tg, qi, engine.ik_params(max_iters=60, kinematics="spec_pair"), packed=packed, counters=cp)
-                for f in ("q", "final_pos", "pos_error", "iterations", "converged", "success"):
-                    assert torch.equal(getattr(a, f), getattr(b, f)), (n, f, packed)
-                assert torch.equal(cl, cp) and int(cl[0]) == n
+                for kin in ("spec_pair", "spec_pair_hybrid"):  # all packed / three-pair FMAs as scalar FFMAs
+                    cp.zero_()
+                    b = engine.ik_solve(tg, qi, engine.ik_params(max_iters=60, kinematics=kin), packed=packed, counters=cp)
+                    for f in ("q", "final_pos", "pos_error", "iterations", "converged", "success"):
+                        assert torch.equal(getattr(a, f), getattr(b, f)), (n, f, packed, kin)
+                    assert torch.equal(cl, cp) and int(cl[0]) == n
         first = engine.ik_solve(t_out, q_out, engine.ik_params(kinematics="spec_pair"))
         sel = torch.arange(0, n, 53, device="cuda")
         assert bool((first.iterations[sel] == 1).all()) and torch.equal(first.q[sel], q_out[sel])
@@ -407,6 +428,10 @@ def test_cfg5_full_size_batch_properties(tree):
     a2 = engine.ik_solve(targets, neutral, engine.ik_params(kinematics="spec_pair"))
     assert torch.equal(a.q, a2.q) and torch.equal(a.iterations, a2.iterations)
     del a2
+    h = engine.ik_solve(targets, neutral, engine.ik_params(kinematics="spec_pair_hybrid"))
+    for f in ("q", "final_pos", "pos_error", "iterations", "converged"):
+        assert torch.equal(getattr(a, f), getattr(h, f)), ("hybrid", f)
+    del h
     fk = engine.fk_jac(a.q, want_quat=False, want_jac=False)[0]
     assert float((fk - a.final_pos).abs().max()) < 2e-6
     err = (fk - targets).norm(dim=1)
