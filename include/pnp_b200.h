@@ -90,9 +90,6 @@ typedef struct PnpIkParams {
                                   waypoint and planner kernels and for small IK batches) */
 #define PNP_KIN_SPEC_PAIR 4    /* two queries / envs per lane on packed FFMA2/FMUL2/FADD2 (what AUTO picks for
                                   FP32 IK batches of >= 4096 queries per SM on the specialised tree) */
-#define PNP_KIN_SPEC_PAIR_HYBRID 5 /* pnp_ik_solve_*_f32 only: two queries per lane, FMAs whose three operands are three
-                                  distinct register pairs issued as two scalar FFMAs (an FFMA2 reading three fresh pairs
-                                  costs 3 clocks, two FFMAs 2.2), everything else packed; elsewhere = PNP_KIN_SPEC_PAIR */
 
 /* flags[] bits written by the IK kernels (IKResult.converged / .success, ik_solver.py:92-100) */
 #define PNP_IK_CONVERGED 1u

@@ -15,10 +15,10 @@ from .tree import PnpTreeStruct
 LIB_NAME = "libpnp_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-PNP_KIN_AUTO, PNP_KIN_GENERIC, PNP_KIN_SPECIALIZED, PNP_KIN_SPEC_LANE, PNP_KIN_SPEC_PAIR, PNP_KIN_SPEC_PAIR_HYBRID = 0, 1, 2, 3, 4, 5
+PNP_KIN_AUTO, PNP_KIN_GENERIC, PNP_KIN_SPECIALIZED, PNP_KIN_SPEC_LANE, PNP_KIN_SPEC_PAIR = 0, 1, 2, 3, 4
 PNP_IK_CONVERGED, PNP_IK_SUCCESS = 1, 2
 KINEMATICS = {"auto": PNP_KIN_AUTO, "generic": PNP_KIN_GENERIC, "specialized": PNP_KIN_SPECIALIZED,
-              "spec_lane": PNP_KIN_SPEC_LANE, "spec_pair": PNP_KIN_SPEC_PAIR, "spec_pair_hybrid": PNP_KIN_SPEC_PAIR_HYBRID}
+              "spec_lane": PNP_KIN_SPEC_LANE, "spec_pair": PNP_KIN_SPEC_PAIR}
 
 _ERRNAMES = {-1: "PNP_EINVAL", -2: "PNP_ENOTREE", -3: "PNP_ENODEVICE", -4: "PNP_ENOMEM"}
 

@@ -14,11 +14,6 @@
 
 #include "pnp_kernels.cuh"
 
-// what PNP_KIN_AUTO runs for big FP32 batches on the specialised tree: 1 = F2H (three-pair FMAs de-packed), 0 = F2
-#ifndef PNP_IK_PAIR_HYBRID_DEFAULT
-#define PNP_IK_PAIR_HYBRID_DEFAULT 0
-#endif
-
 namespace {
 
 thread_local std::string g_err;
@@ -135,7 +130,6 @@ int pick_kin(const DeviceState* s, int kinematics, bool* use_spec) {
     case PNP_KIN_SPECIALIZED:
     case PNP_KIN_SPEC_LANE:
     case PNP_KIN_SPEC_PAIR:
-    case PNP_KIN_SPEC_PAIR_HYBRID:
       if (!s->specialized) return fail(PNP_EINVAL, "uploaded tree differs from the build-time specialised tree");
       *use_spec = true;
       return PNP_OK;
@@ -305,11 +299,11 @@ int launch_ik(DeviceState* s, const pnp::IkArgs<T>& a, bool small, cudaStream_t 
   return PNP_OK;
 }
 
-// Value-type kernels (pnp_vec.cuh): V = float, one query per lane; V = F2 / F2H, two queries per lane.
+// Value-type kernels (pnp_vec.cuh): V = float, one query per lane; V = F2, two queries per lane.
 template <typename V, int kOut>
 int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStream_t st) {
   constexpr int S = pnp::Slots<V>::kN;
-  const int slot = 8 + (std::is_same<V, pnp::F2H>::value ? 4 : (S - 1) * 2) + (kOut != pnp::IK_OUT_SEPARATE ? 1 : 0);
+  const int slot = 8 + (S - 1) * 2 + (kOut != pnp::IK_OUT_SEPARATE ? 1 : 0);
   if (s->occ_ik[slot] == 0) {
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_solve_v_kernel<V, kOut, true>,
@@ -363,17 +357,13 @@ int launch_ik_small(const pnp::IkArgs<float>& a, cudaStream_t st) {
 // FP32 on the specialised tree always runs the value-type arithmetic (ik_eval_v / ik_step_v: a batch gives
 // bit-identical results whichever kernel is picked).  AUTO / SPECIALIZED:
 //   n <= 128 queries per SM          ik_solve_small_kernel (latency bound: the launch lasts as long as its slowest query)
-//   n >= 4096 queries per SM         two queries per lane (F2 all packed, or F2H: three-pair FMAs as scalar FFMAs)
+//   n >= 4096 queries per SM         two queries per lane (packed FFMA2/FMUL2/FADD2)
 //   in between                       one query per lane with refill
 template <int kOut>
 int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
   const bool big = (long long)a.n >= (long long)s->sm_count * 4096;
-  static const int env_hybrid = env_int("PNP_IK_PAIR_HYBRID", PNP_IK_PAIR_HYBRID_DEFAULT);
-  const bool pair_small = (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2;
-  if (kinematics == PNP_KIN_SPEC_PAIR_HYBRID) return launch_ik_v<pnp::F2H, kOut>(s, a, pair_small, st);
-  if (kinematics == PNP_KIN_SPEC_PAIR) return launch_ik_v<pnp::F2, kOut>(s, a, pair_small, st);
-  if (kinematics != PNP_KIN_SPEC_LANE && big)
-    return env_hybrid ? launch_ik_v<pnp::F2H, kOut>(s, a, pair_small, st) : launch_ik_v<pnp::F2, kOut>(s, a, pair_small, st);
+  if (kinematics == PNP_KIN_SPEC_PAIR || (kinematics != PNP_KIN_SPEC_LANE && big))
+    return launch_ik_v<pnp::F2, kOut>(s, a, (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2, st);
   return launch_ik_v<float, kOut>(s, a, small, st);
 }
 
@@ -634,7 +624,7 @@ int pnp_ik_waypoints_f32(const float* q_start, const float* goal, int64_t n, int
   // specialised tree: the value-type kernels (same arithmetic in both), one env per lane unless two are asked
   // for (with the fused accept / first-iteration pass the bookkeeping weighs more than the packed arithmetic
   // saves: 2^20 envs x 50, 0.81 ms against 0.87); other trees: the scalar-template kernel
-  const bool pair = spec && (params->kinematics == PNP_KIN_SPEC_PAIR || params->kinematics == PNP_KIN_SPEC_PAIR_HYBRID);
+  const bool pair = spec && params->kinematics == PNP_KIN_SPEC_PAIR;
   const int S = pair ? 2 : 1;
   int occ = 4;
   if (!small) {
@@ -783,7 +773,7 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   if constexpr (std::is_same<T, float>::value) {
     if (spec) {
       // specialised tree, FP32: the value-type kernels (same arithmetic in both, branch-free common path)
-      const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR || params->kinematics == PNP_KIN_SPEC_PAIR_HYBRID;
+      const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR;
       const int S = pair ? 2 : 1;
       int occv = 4;
       if (!small) {

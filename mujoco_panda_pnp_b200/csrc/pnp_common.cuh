@@ -61,7 +61,7 @@ __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sinco
 // ---------------------------------------------------------------------------------------------
 constexpr int kTrigVN = 8192;
 constexpr int kTrigVWords = kTrigVN + kTrigVN / 4;  // + a quarter turn for the cosine
-__device__ float g_trigv_tab[kTrigVWords];          // sin(k * 2*pi/8192), filled by pnp_set_tree
+__device__ __align__(16) float g_trigv_tab[kTrigVWords];  // sin(k * 2*pi/8192), filled by pnp_set_tree
 
 template <typename T>
 struct Trig;
@@ -89,11 +89,15 @@ struct Trig<double> {
   __device__ __forceinline__ void operator()(double x, double* s, double* c) const { sincos(x, s, c); }
 };
 
-// Cooperative load of the trig table into shared memory (call by every thread of the block).
+// Cooperative load of the trig table into shared memory (call by every thread of the block, __syncthreads() after).
+// cp.async (LDGSTS): all of a thread's 16-byte copies are in flight at once and bypass the register file.  The plain
+// LDG/STS loop ran in batches of four loads and took 5.5 us of a 32 us cfg2 launch (ncu: the STS waiting on its LDG
+// held 17 % of the kernel's warp samples); a single-query solve paid the same 5 us.
 __device__ __forceinline__ void load_trigv_table(float* s_tab) {
-  const float4* src = reinterpret_cast<const float4*>(g_trigv_tab);
-  float4* dst = reinterpret_cast<float4*>(s_tab);
-  for (int i = threadIdx.x; i < kTrigVWords / 4; i += blockDim.x) dst[i] = src[i];
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(s_tab);
+  for (int i = threadIdx.x; i < kTrigVWords / 4; i += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(g_trigv_tab + 4 * i) : "memory");
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // one MUFU.RCP (callers pass pivots of J J^T + damping I in [damping, ~10] or distances > 1e-3: no
@@ -340,29 +344,22 @@ __device__ __forceinline__ void ik_eval_and_step(const T (&q)[NJ], const T (&tgt
 // Specialised tree only (the generated "_v" kinematics).
 // ---------------------------------------------------------------------------------------------
 using pnp_spec::F2;
-using pnp_spec::F2H;
-using pnp_spec::F2T;
 using pnp_spec::pnp_add;
 using pnp_spec::pnp_fma;
-using pnp_spec::pnp_fma3;
 using pnp_spec::pnp_mul;
 using pnp_spec::pnp_neg;
 
 __device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
-template <int M>
-__device__ __forceinline__ F2T<M> v_sub(F2T<M> a, F2T<M> b) { return pnp_spec::pnp_sub(a, b); }
+__device__ __forceinline__ F2 v_sub(F2 a, F2 b) { return pnp_spec::pnp_sub(a, b); }
 __device__ __forceinline__ float v_rcp(float x) { return rcp_approx(x); }
-template <int M>
-__device__ __forceinline__ F2T<M> v_rcp(F2T<M> x) { return F2T<M>(rcp_approx(x.v.x), rcp_approx(x.v.y)); }
+__device__ __forceinline__ F2 v_rcp(F2 x) { return F2(rcp_approx(x.v.x), rcp_approx(x.v.y)); }
 __device__ __forceinline__ float v_clamp_sym(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
-template <int M>
-__device__ __forceinline__ F2T<M> v_clamp_sym(F2T<M> x, F2T<M> lim) {
-  return F2T<M>(fminf(fmaxf(x.v.x, -lim.v.x), lim.v.x), fminf(fmaxf(x.v.y, -lim.v.y), lim.v.y));
+__device__ __forceinline__ F2 v_clamp_sym(F2 x, F2 lim) {
+  return F2(fminf(fmaxf(x.v.x, -lim.v.x), lim.v.x), fminf(fmaxf(x.v.y, -lim.v.y), lim.v.y));
 }
 __device__ __forceinline__ float v_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-template <int M>
-__device__ __forceinline__ F2T<M> v_clamp(F2T<M> x, float lo, float hi) {
-  return F2T<M>(fminf(fmaxf(x.v.x, lo), hi), fminf(fmaxf(x.v.y, lo), hi));
+__device__ __forceinline__ F2 v_clamp(F2 x, float lo, float hi) {
+  return F2(fminf(fmaxf(x.v.x, lo), hi), fminf(fmaxf(x.v.y, lo), hi));
 }
 
 // Table trig of the value-type kernels: Trig<float>'s arithmetic for V = float and, packed, for V = F2 (the two
@@ -379,17 +376,16 @@ struct TrigV {
     *s = fmaf(ec, r, es);
     *c = fmaf(-es, r, ec);
   }
-  template <int M>
-  __device__ __forceinline__ void operator()(F2T<M> x, F2T<M>* s, F2T<M>* c) const {
-    using P = F2T<M>;
+  __device__ __forceinline__ void operator()(F2 x, F2* s, F2* c) const {
+    using P = F2;
     const P t = pnp_fma(x, P(1303.7972412109375f), P(12582912.0f));
     const int ja = __float_as_int(t.v.x) & (kTrigVN - 1), jb = __float_as_int(t.v.y) & (kTrigVN - 1);
     const P k = pnp_add(t, P(-12582912.0f));
     P r = pnp_fma(k, P(-7.669904152862728e-4f), x);
     r = pnp_fma(k, P(2.1343451311883754e-11f), r);
     const P es(tab[ja], tab[jb]), ec(tab[ja + kTrigVN / 4], tab[jb + kTrigVN / 4]);
-    *s = pnp_fma3(ec, r, es);
-    *c = pnp_fma3(pnp_neg(es), r, ec);
+    *s = pnp_fma(ec, r, es);
+    *c = pnp_fma(pnp_neg(es), r, ec);
   }
 };
 
@@ -420,18 +416,18 @@ __device__ __forceinline__ void ik_step_v(V (&q)[NJ], const V (&J)[21], const V 
   const V a00 = pnp_add(A[0], lam), a11 = pnp_add(A[3], lam), a22 = pnp_add(A[5], lam);
   const V i0 = v_rcp(a00);
   const V l10 = pnp_mul(A[1], i0), l20 = pnp_mul(A[2], i0);
-  const V d1 = pnp_fma3(pnp_neg(l10), A[1], a11);
-  const V u12 = pnp_fma3(pnp_neg(l10), A[2], A[4]);
+  const V d1 = pnp_fma(pnp_neg(l10), A[1], a11);
+  const V u12 = pnp_fma(pnp_neg(l10), A[2], A[4]);
   const V i1 = v_rcp(d1);
   const V l21 = pnp_mul(u12, i1);
-  const V d2 = pnp_fma3(pnp_neg(l21), u12, pnp_fma3(pnp_neg(l20), A[2], a22));
+  const V d2 = pnp_fma(pnp_neg(l21), u12, pnp_fma(pnp_neg(l20), A[2], a22));
   const V i2 = v_rcp(d2);
-  const V z1 = pnp_fma3(pnp_neg(l10), e[0], e[1]);
-  const V z2 = pnp_fma3(pnp_neg(l21), z1, pnp_fma3(pnp_neg(l20), e[0], e[2]));
+  const V z1 = pnp_fma(pnp_neg(l10), e[0], e[1]);
+  const V z2 = pnp_fma(pnp_neg(l21), z1, pnp_fma(pnp_neg(l20), e[0], e[2]));
   V y[3];
   y[2] = pnp_mul(z2, i2);
-  y[1] = pnp_fma3(pnp_neg(l21), y[2], pnp_mul(z1, i1));
-  y[0] = pnp_fma3(pnp_neg(l20), y[2], pnp_fma3(pnp_neg(l10), y[1], pnp_mul(e[0], i0)));
+  y[1] = pnp_fma(pnp_neg(l21), y[2], pnp_mul(z1, i1));
+  y[0] = pnp_fma(pnp_neg(l20), y[2], pnp_fma(pnp_neg(l10), y[1], pnp_mul(e[0], i0)));
   V dq[NJ];
   pnp_spec::spec_jty_v<V>(J, y, dq);
 #pragma unroll

@@ -176,7 +176,10 @@ class HostIKResult(dict):
     converged, success) are decoded from the packed word only when first asked for."""
 
     def __missing__(self, key):
-        word = dict.__getitem__(self, "aux4")[:, 3].view(np.int32)
+        if dict.__contains__(self, "aux4"):
+            word = dict.__getitem__(self, "aux4")[:, 3].view(np.int32)
+        else:  # compact records: the word is the 8th column of q8
+            word = dict.__getitem__(self, "q8")[:, 7].view(np.int32)
         if key == "iterations":
             val = word & 0xFFFFFF
         elif key == "flags":
@@ -636,9 +639,7 @@ def ik_solve_host(targets, q_init, params: PnpIkParams, chunk_rows: int = 0, out
                                               ctypes.byref(params), _np_ptr(q8), _np_ptr(counters)),
             "pnp_ik_solve_compact_host",
         )
-        word = q8[:, 7].view(np.int32)
-        return dict(q=q8[:, :7], q8=q8, iterations=word & 0xFFFFFF, converged=(word & (1 << 24)) != 0,
-                    success=(word & (2 << 24)) != 0, counters=counters)
+        return HostIKResult(q=q8[:, :7], q8=q8, counters=counters)  # iterations / converged / success decoded on demand
     if packed:
         q8 = buf("q8", (n, 8), np.float32)
         aux = buf("aux4", (n, 4), np.float32)

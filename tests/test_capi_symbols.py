@@ -50,10 +50,9 @@ def test_header_constants_match_binding():
     text = open(HEADER).read()
     defs = {m.group(1): int(m.group(2).rstrip("u")) for m in re.finditer(r"#define\s+(PNP_[A-Z0-9_]+)\s+(-?\d+u?)\b", text)}
     for name in ("PNP_KIN_AUTO", "PNP_KIN_GENERIC", "PNP_KIN_SPECIALIZED", "PNP_KIN_SPEC_LANE", "PNP_KIN_SPEC_PAIR",
-                 "PNP_KIN_SPEC_PAIR_HYBRID", "PNP_IK_CONVERGED", "PNP_IK_SUCCESS"):
+                 "PNP_IK_CONVERGED", "PNP_IK_SUCCESS"):
         assert defs[name] == getattr(_lib, name), name
-    assert _lib.KINEMATICS == {"auto": 0, "generic": 1, "specialized": 2, "spec_lane": 3, "spec_pair": 4,
-                               "spec_pair_hybrid": 5}
+    assert _lib.KINEMATICS == {"auto": 0, "generic": 1, "specialized": 2, "spec_lane": 3, "spec_pair": 4}
     assert [defs[f"PNP_IK_CNT_{k}"] for k in ("N", "CONVERGED", "SUCCESS", "ITERATIONS")] == [0, 1, 2, 3]
 
 

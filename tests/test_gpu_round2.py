@@ -79,7 +79,7 @@ def test_cfg2_latency_kernel_vs_oracle(tree, oracle_chain):
     assert int((res.converged.cpu().numpy() != ref["converged"]).sum()) <= 2
 
 
-@pytest.mark.parametrize("kin", ["spec_pair", "spec_pair_hybrid", "spec_lane", "generic"])
+@pytest.mark.parametrize("kin", ["spec_pair", "spec_lane", "generic"])
 def test_compact_records(tree, kin):
     """pnp_ik_solve_compact_f32: q0..q6 | iterations | flags << 24 in one 32-byte record, equal to the packed result."""
     n = 300_001 if kin != "generic" else 20_011
@@ -96,12 +96,14 @@ def test_compact_records(tree, kin):
         assert torch.equal(getattr(a, f), getattr(b, f)), f
     assert torch.equal(ca, cb)
     # host operator: 32 bytes per query come back
-    th = targets[:70_001].cpu().numpy()
+    m = min(n, 70_001)
+    th = targets[:m].cpu().numpy()
     h = engine.ik_solve_host(th, NEUTRAL.astype(np.float32), p, chunk_rows=9_999, compact=True)
-    np.testing.assert_array_equal(h["q"], a.q[:70_001].cpu().numpy())
-    np.testing.assert_array_equal(h["iterations"], a.iterations[:70_001].cpu().numpy())
-    np.testing.assert_array_equal(h["converged"], a.converged[:70_001].cpu().numpy())
-    assert h["counters"][0] == 70_001 and h["counters"][1] == int(a.converged[:70_001].sum())
+    np.testing.assert_array_equal(h["q"], a.q[:m].cpu().numpy())
+    np.testing.assert_array_equal(h["iterations"], a.iterations[:m].cpu().numpy())
+    np.testing.assert_array_equal(h["converged"], a.converged[:m].cpu().numpy())
+    np.testing.assert_array_equal(h["success"], a.success[:m].cpu().numpy())
+    assert h["counters"][0] == m and h["counters"][1] == int(a.converged[:m].sum())
 
 
 def test_straggler_handover_with_many_long_queries(tree):
@@ -113,7 +115,7 @@ def test_straggler_handover_with_many_long_queries(tree):
         targets = _targets(tree, n, seed=n % 1000)
         targets[::stride] = torch.tensor([2.5, 0.0, 0.5], device="cuda")
         ref = engine.ik_solve(targets, _neutral(), engine.ik_params(kinematics="spec_lane"))
-        for kin in ("spec_pair", "spec_pair_hybrid"):
+        for kin in ("spec_pair",):
             cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
             q8 = torch.full((n, 8), float("nan"), device="cuda")
             aux = torch.full((n, 4), float("nan"), device="cuda")
@@ -151,7 +153,7 @@ def test_scalar_compute_reward_mailbox_is_bit_exact_and_thread_safe(cuda_lib, go
     """compute_reward with (3,) goals = one launch through the mapped mailbox (pnp_reward_one_host_f64): bit-exact on
     the reference's own rows for both reward types; four threads hammering the single-query IK and reward paths of the
     shared host context get the serial answers (the mailbox is locked per call)."""
-    g = golden_reward
+    g = {k: golden_reward[k] for k in golden_reward.files}  # NpzFile reads lazily and is not thread-safe
     for rt, key in (("dense", "reward_dense"), ("sparse", "reward_sparse")):
         env = FrankaShelfPNPReward(rt)
         for i in range(256):

@@ -192,11 +192,7 @@ class Compiler:
             else:
                 neg = a.sign * b.sign < 0
                 prod = f"{'-' if neg else ''}{a.node.name} * {b.node.name}"
-                # three DISTINCT runtime operands -> pnp_fma3 (the hybrid pair type issues those as two scalar
-                # FFMAs: an FFMA2 reading three fresh register pairs costs 3 clocks, see pnp_vec.cuh)
-                distinct3 = (not c.is_const) and len({a.node.name, b.node.name, c.node.name}) == 3
-                fn = "pnp_fma3" if distinct3 else "pnp_fma"
-                vx = f"{fn}({'pnp_neg(' + a.node.name + ')' if neg else a.node.name}, {b.node.name}, {self.vref(c)})"
+                vx = f"pnp_fma({'pnp_neg(' + a.node.name + ')' if neg else a.node.name}, {b.node.name}, {self.vref(c)})"
             return f"{prod} + {self.ref(c, leading=False)}", "fma", self._deps(a, b, c), vx
 
         return self._canon(fp, emit)
@@ -376,8 +372,7 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
             if jp_zero[r, j] or jp_zero[s_, j]:
                 continue
             a_, b_ = f"J[{r * 7 + j}]", f"J[{s_ * 7 + j}]"
-            fma_fn = "pnp_fma3" if r != s_ else "pnp_fma"  # off-diagonal: three distinct operands
-            jjt.append(f"  {'T ' if not started[k] else ''}a{k} = " + (f"{fma_fn}({a_}, {b_}, a{k});" if started[k] else f"pnp_mul({a_}, {b_});"))
+            jjt.append(f"  {'T ' if not started[k] else ''}a{k} = " + (f"pnp_fma({a_}, {b_}, a{k});" if started[k] else f"pnp_mul({a_}, {b_});"))
             started[k] = True
     for k in range(6):
         jjt.append(f"  A[{k}] = {'a%d' % k if started[k] else 'T(0.0)'};")
@@ -396,7 +391,7 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         for j in range(7):
             if jp_zero[r, j]:
                 continue
-            jty.append(f"  {'T ' if not started[j] else ''}d{j} = " + (f"pnp_fma3(J[{r * 7 + j}], y[{r}], d{j});" if started[j] else f"pnp_mul(J[{r * 7 + j}], y[{r}]);"))
+            jty.append(f"  {'T ' if not started[j] else ''}d{j} = " + (f"pnp_fma(J[{r * 7 + j}], y[{r}], d{j});" if started[j] else f"pnp_mul(J[{r * 7 + j}], y[{r}]);"))
             started[j] = True
     for j in range(7):
         jty.append(f"  dq[{j}] = {'d%d' % j if started[j] else 'T(0.0)'};")
