@@ -174,7 +174,6 @@ struct IkArgs {
   unsigned flush_min; // ik_solve_v_kernel: lanes with a finished slot that trigger a store + refill
   unsigned solo_warp; // ik_solve_v_kernel, small batches: the block has 4 warps to load the 40 KB trig table quickly,
                       // only warp 0 solves (one warp per block spreads a small batch over all SMs)
-  unsigned park;      // ik_solve_v_kernel: block-level straggler hand-over once the ticket pool is dry (see the kernel)
 };
 
 // output layouts of the FP32 IK kernels
@@ -339,9 +338,6 @@ struct Slots<F2> {
   static __device__ __forceinline__ void set(F2& v, int k, float x) { if (k == 0) v.v.x = x; else v.v.y = x; }
 };
 
-__device__ __forceinline__ float2 pair_bits(float v) { return make_float2(v, 0.0f); }
-__device__ __forceinline__ float2 pair_bits(const F2& v) { return v.v; }
-
 // Predicated global accesses for the store + refill block of ik_solve_v_kernel: as plain `if`s the
 // four per-slot blocks (store slot 0/1, refill slot 0/1) were four divergent branches executed one after
 // the other by a handful of lanes (24 % of all warp samples for 15 % of the instructions); predicated,
@@ -356,16 +352,6 @@ __device__ __forceinline__ void ldg3_if(bool pred, const float* ptr, float& x, f
       "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.f32 %0, [%4];\n\t@p ld.global.nc.f32 %1, [%4+4];\n\t"
       "@p ld.global.nc.f32 %2, [%4+8];\n\t}"
       : "+f"(x), "+f"(y), "+f"(z) : "r"((unsigned)pred), "l"(ptr));
-}
-__device__ __forceinline__ void lds3_if(bool pred, const float* ptr, float& x, float& y, float& z) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.f32 %0, [%4];\n\t@p ld.shared.f32 %1, [%4+4];\n\t"
-      "@p ld.shared.f32 %2, [%4+8];\n\t}"
-      : "+f"(x), "+f"(y), "+f"(z) : "r"((unsigned)pred), "r"((unsigned)__cvta_generic_to_shared(ptr)));
-}
-__device__ __forceinline__ void lds1_if(bool pred, const float* ptr, float& x) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.shared.f32 %0, [%2];\n\t}"
-               : "+f"(x) : "r"((unsigned)pred), "r"((unsigned)__cvta_generic_to_shared(ptr)));
 }
 __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
@@ -385,43 +371,35 @@ __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
 // the scoreboard of the target loads, and the first trig FFMA2 of the pass then waited a full
 // global-load latency for targets it does not need until mid-pass.
 //
-// Straggler hand-over (a.park).  0.2 % of cold queries run into max_iters = 100 while the mean is 16 passes, so when
-// the ticket pool runs dry nearly every warp of the grid is left holding one or two long-running slots, and a warp
-// with one live slot still pays a full pass: the launch ended with ~100 passes at 1/64 density on every scheduler
-// (0.13-0.15 ms of a 2.8 ms launch).  Once a warp has seen the pool dry and is down to <= IK_PARK_PER_WARP running
-// slots, it writes them (query index, iteration count, q, target) to a block-shared list and leaves; the LAST warp of
-// the block to get there keeps going and takes the whole list (<= 4 x 16 entries = its 64 slots).  The drain then runs
-// on one warp per block instead of four, at the latency of a lone warp per scheduler.  A query continues from exactly
-// the state it was parked in, so results do not depend on whether or where it was handed over.
-constexpr int IK_PARK_PER_WARP = 16;
-constexpr int IK_PARK_PAIRS = NJ;  // q[7], one register pair each (the target is re-read from global memory)
-
+// Measured and dropped (round 2): a block-level straggler hand-over.  0.2 % of cold queries run into max_iters = 100
+// while the mean is 16 passes, so when the ticket pool runs dry most warps are left holding one or two long-running
+// slots.  Once a warp had seen the pool dry and was down to <= 16 running slots it dumped them to a block-shared list
+// and left; the last warp of the block took the whole list, so that the drain ran on one warp per block.  Bit-identical
+// results, but 2.94 ms against 2.91 ms for 2^24 queries with the code compiled in and switched off (and 2.82 ms
+// without it): a lone two-queries-per-lane warp needs ~1000 clocks per pass, about what four straggler warps sharing a
+// scheduler need per round, and the extra predicated loads of a refill that can also read the list cost more than the
+// shorter tail returned.  (Touching the HALVES of the register pairs inside a divergent block also made ptxas split
+// the pairs and re-pack them with 35 moves in the hot loop - whole-pair 64-bit dumps avoided that.)
 template <typename V, int kOut, bool kBcast>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
-  constexpr int kParkCap = (IK_BLOCK / 32) * IK_PARK_PER_WARP;
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
   __shared__ __align__(16) float s_trig[kTrigVWords];
-  __shared__ __align__(16) float s_state[S == 2 ? IK_BLOCK * 2 * IK_PARK_PAIRS : 4];  // per thread: q[7] of both slots, as pairs
-  __shared__ unsigned s_list[S == 2 ? kParkCap * 3 : 4];                               // parked: query index, iterations, owner
-  __shared__ unsigned s_park_cnt, s_live_warps;
   load_trigv_table(s_trig);
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
-  if (threadIdx.x == 0) { s_park_cnt = 0; s_live_warps = IK_BLOCK / 32; }
   __syncthreads();
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
-  const bool can_park = S == 2 && a.park && !a.solo_warp;
   enum { IDLE = 0, RUN = 1, FIN_CONV = 2, FIN_NOCONV = 3 };
 
   V q[NJ], tgt[3], slim(0.0f);
   int it[S], st[S];
   unsigned idx[S];
-  bool exhausted = false, sink = false;
+  bool exhausted = false;
   unsigned c_n = 0, c_conv = 0;
   unsigned long long c_iter = 0;
 #pragma unroll
@@ -430,71 +408,21 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 #pragma unroll
   for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; st[k] = IDLE; }
   unsigned pool_next = 0, pool_end = 0;  // warp-local pool of reserved query indices
-  unsigned park_next = 0, park_end = 0;  // sink warp: its position in / the length of the block's list of parked queries
   bool flush = true;  // first pass: nothing to store, every slot to fill
-  bool pool_dry = false;  // warp-uniform: some lane of this warp has drawn an index >= n
 
   while (true) {
     if (flush) {  // warp-uniform
-#ifndef PNP_IK_NO_PARK
-      if (can_park && pool_dry && !sink) {  // warp-uniform
-        // ---- straggler hand-over: few running slots left and nothing more to take.  The slots are only READ here
-        //      (and marked idle); the last warp picks the list up through the ordinary refill code below, so q / tgt
-        //      keep a single point of definition (a separate load path cost 35 register moves per pass).
-        unsigned run_m[S], n_run = 0;
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-          run_m[k] = __ballot_sync(FULL, st[k] == RUN);
-          n_run += (unsigned)__popc(run_m[k]);
-        }
-        if (n_run <= (unsigned)IK_PARK_PER_WARP) {
-          unsigned base = 0;
-          if (n_run) {
-            if (lane == 0) base = atomicAdd(&s_park_cnt, n_run);
-            base = __shfl_sync(FULL, base, 0);
-          }
-          // every lane dumps BOTH its slots as whole register pairs (64-bit stores, no access to the halves: ptxas
-          // otherwise splits the pairs and re-packs them in the hot loop); the list names the running ones
-          float2* area = reinterpret_cast<float2*>(s_state) + (size_t)threadIdx.x * IK_PARK_PAIRS;
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) area[i] = pair_bits(q[i]);
-          unsigned before = 0;
-#pragma unroll
-          for (int k = 0; k < S; ++k) {
-            if (st[k] == RUN) {
-              unsigned* e = s_list + (base + before + (unsigned)__popc(run_m[k] & lanemask_lt)) * 3u;
-              e[0] = idx[k];
-              e[1] = (unsigned)it[k];
-              e[2] = threadIdx.x * 2u + (unsigned)k;  // whose slot it was
-              st[k] = IDLE;
-            }
-            before += (unsigned)__popc(run_m[k]);
-          }
-          __threadfence_block();  // the entries are written before this warp is counted out
-          unsigned left = 0;
-          if (lane == 0) left = atomicSub(&s_live_warps, 1u);
-          left = __shfl_sync(FULL, left, 0);
-          if (left != 1u) break;  // another warp of the block is still at work: it will take the list
-          // last warp of the block: every other warp has written its entries (their fence precedes their
-          // decrement, which precedes ours); from now on the refill below draws from the list
-          sink = true;
-          __threadfence_block();
-          park_end = *reinterpret_cast<volatile unsigned*>(&s_park_cnt);
-        }
-      }
-#endif
-      // ---- refill idle slots (slot-major ranks: all idle slot-0 lanes first, then slot 1): from the warp's pool of
-      //      reserved query indices, or - the sink warp of a block - from the block's list of parked queries ---------
+      // ---- refill idle slots (slot-major ranks: all idle slot-0 lanes first, then slot 1) -----------
       unsigned need[S], count = 0;
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        need[k] = __ballot_sync(FULL, st[k] == IDLE && (sink || !exhausted));
+        need[k] = __ballot_sync(FULL, st[k] == IDLE && !exhausted);
         count += (unsigned)__popc(need[k]);
       }
-      if (count && !(sink && park_next >= park_end)) {
-        const unsigned avail = sink ? park_end - park_next : pool_end - pool_next;
+      if (count) {
+        const unsigned avail = pool_end - pool_next;
         unsigned fresh = 0;
-        if (!sink && count > avail) {  // warp-uniform
+        if (count > avail) {  // warp-uniform
           if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
           fresh = __shfl_sync(FULL, fresh, 0);
         }
@@ -502,58 +430,41 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         bool ran_out = false;
 #pragma unroll
         for (int k = 0; k < S; ++k) {  // predicated, no per-slot branch
-          const bool want = st[k] == IDLE && (sink || !exhausted);
+          const bool want = st[k] == IDLE && !exhausted;
           const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
-          // sink: position in the parked list; otherwise the query index itself
-          const unsigned id = sink ? park_next + rank : (rank < avail ? pool_next + rank : fresh + (rank - avail));
-          const bool ok = want && id < (sink ? park_end : a.n);
+          const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
+          const bool ok = want && id < a.n;
           ran_out = ran_out || (want && !ok);
-          const bool okg = ok && !sink, oks = ok && sink;
-          const unsigned* ent = s_list + (oks ? id : 0u) * 3u;
-          const unsigned who = oks ? ent[2] : 0u;  // (thread << 1) | slot of the lane that parked it
-          const float* src = s_state + (size_t)(who >> 1) * (2 * IK_PARK_PAIRS) + (who & 1u);  // that slot's half of each pair
-          const unsigned qid = oks ? ent[0] : id;  // the query this slot takes
           float t0 = Slots<V>::get(tgt[0], k), t1 = Slots<V>::get(tgt[1], k), t2 = Slots<V>::get(tgt[2], k);
-          ldg3_if(ok, a.targets + (size_t)qid * 3u, t0, t1, t2);
+          ldg3_if(ok, a.targets + (size_t)id * 3u, t0, t1, t2);
           Slots<V>::set(tgt[0], k, t0);
           Slots<V>::set(tgt[1], k, t1);
           Slots<V>::set(tgt[2], k, t2);
 #pragma unroll
           for (int i = 0; i < NJ; ++i) {
             float qi = Slots<V>::get(q[i], k);
-            if (kBcast) qi = okg ? s_q0[i] : qi;
-            else ldg1_if(okg, a.q_init + (size_t)id * NJ + i, qi);
-            lds1_if(oks, src + 2 * i, qi);
+            if (kBcast) qi = ok ? s_q0[i] : qi;
+            else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
             Slots<V>::set(q[i], k, qi);
           }
-          idx[k] = ok ? qid : idx[k];
-          it[k] = ok ? (sink ? (int)ent[1] : 0) : it[k];
+          idx[k] = ok ? id : idx[k];
+          it[k] = ok ? 0 : it[k];
           st[k] = ok ? (int)RUN : st[k];
           Slots<V>::set(slim, k, ok ? a.k.step_limit : Slots<V>::get(slim, k));
           before += (unsigned)__popc(need[k]);
         }
-        if (sink) {
-          park_next += count;
+        exhausted = exhausted || ran_out;
+        if (count > avail) {
+          pool_next = fresh + (count - avail);
+          pool_end = fresh + a.chunk;
         } else {
-          exhausted = exhausted || ran_out;
-          if (count > avail) {
-            pool_next = fresh + (count - avail);
-            pool_end = fresh + a.chunk;
-          } else {
-            pool_next += count;
-          }
-          pool_dry = pool_dry || __any_sync(FULL, ran_out);
+          pool_next += count;
         }
       }
       bool any_run = false;
 #pragma unroll
       for (int k = 0; k < S; ++k) any_run = any_run || st[k] == RUN;
-      if (!__any_sync(FULL, any_run)) {
-        // a warp that never got to hand anything over (it was already empty when the pool ran dry) still has to be
-        // counted out - and, if it is the block's last, to take the list
-        if (can_park && !sink && pool_dry) continue;
-        break;  // everything stored, nothing left to take
-      }
+      if (!__any_sync(FULL, any_run)) break;  // everything stored, nothing left to take
     }
 
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
@@ -576,8 +487,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
     ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    // (pool dry: no refill to amortise, and the hand-over above looks at the running count after every finish)
-    flush = n_fin >= (pool_dry && can_park ? 1 : flush_min) || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
+    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
     if (flush) {  // warp-uniform
       // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,
       //      so this pass's values are the query's final ones.  One exception: a query that finished on

@@ -1,5 +1,4 @@
-"""GPU: the round-2 additions - compact IK records, the small-batch latency kernel, the straggler hand-over of
-the pair kernels, per-stream launch scratch, the single-row reward mailbox, plan-order validation and the
+"""GPU: the round-2 additions - compact IK records, the small-batch latency kernel, per-stream launch scratch, the single-row reward mailbox, plan-order validation and the
 checks on caller-supplied output buffers.  Everything goes through the C ABI (ctypes)."""
 import threading
 
@@ -106,11 +105,11 @@ def test_compact_records(tree, kin):
     assert h["counters"][0] == m and h["counters"][1] == int(a.converged[:m].sum())
 
 
-def test_straggler_handover_with_many_long_queries(tree):
-    """The pair kernels hand their last running slots over to one warp per block once the ticket pool is dry.  A batch
-    whose long-running queries are (a) rare, (b) one in seven, (c) all of them, and one that is too small to fill the
-    grid: results equal the one-query-per-lane kernel bit for bit, counters equal the per-query outputs, nothing is
-    lost or solved twice (n == counters[0], every record written)."""
+def test_pair_kernel_with_many_long_queries(tree):
+    """Batches whose long-running queries (unreachable targets: 100 passes) are (a) rare, (b) one in seven, (c) all of
+    them, and one that is too small to fill the grid: the two-queries-per-lane kernel equals the one-query-per-lane
+    kernel bit for bit, counters equal the per-query outputs, nothing is lost or solved twice (n == counters[0], every
+    record written)."""
     for n, stride in (((1 << 21) + 5, 997), ((1 << 21) + 5, 7), (700_000, 1), (40_000, 3)):
         targets = _targets(tree, n, seed=n % 1000)
         targets[::stride] = torch.tensor([2.5, 0.0, 0.5], device="cuda")

@@ -243,3 +243,55 @@ def test_move_planner_never_terminates_on_unreachable_targets_without_a_bound(or
     smaller steps and never advances point_count; only an explicit bound stops the loop."""
     r = c_oracle.move_plan(oracle_chain, NEUTRAL[None], np.array([[2.0, 0.0, 0.5]]), max_outer=400, traj_cap=64)
     assert r["status"][0] & 2 and r["status"][0] & 4 and r["traj_len"][0] > 200
+
+
+def test_pose_ik_statement_agrees_with_an_independent_formulation(oracle_model):
+    """oracle/pose_ik_oracle.py states the pose-mode extension (there is no reference code for it).  A
+    second, independently written formulation must walk the same iterates: the orientation error as SciPy's rotation
+    vector of R_target R_site^T (instead of mju_mat2Quat + mju_mulQuat + mju_quat2Vel) and the damped step as the
+    least-squares solution of the stacked system [J; sqrt(damping) I] dq = [e; 0] (numpy.linalg.lstsq, instead of
+    J^T solve(J J^T + damping I, e)) - two-source evidence for the semantics the GPU kernel is tested against."""
+    from scipy.spatial.transform import Rotation
+
+    from oracle import pose_ik_oracle
+
+    model = oracle_model
+    sid = model.site("ee_center_site").id
+    lower, upper = model.jnt_range[:7, 0], model.jnt_range[:7, 1]
+    rng = np.random.default_rng(11)
+    d1, d2 = mj_oracle.MjData(model), mj_oracle.MjData(model)
+    n_conv = 0
+    for case in range(12):
+        q_goal = np.clip(NEUTRAL + rng.uniform(-0.5, 0.5, 7), lower, upper)
+        p_t, _, quat_t, _ = ik_oracle.fk_site(model, d1, q_goal)
+        want = pose_ik_oracle.solve_pose(model, d1, p_t, quat_t, NEUTRAL, damping=1e-2, rot_weight=0.7)
+        # ---- independent loop ----------------------------------------------------------------------------
+        r_t = Rotation.from_quat([quat_t[1], quat_t[2], quat_t[3], quat_t[0]])  # SciPy is xyzw
+        q = NEUTRAL.copy()
+        converged, iterations = False, 0
+        for i in range(100 + 1):
+            d2.qpos[:7] = q
+            mj_oracle.mj_forward(model, d2)
+            p = d2.site_xpos[sid].copy()
+            r_c = Rotation.from_matrix(np.asarray(d2.site_xmat[sid]).reshape(3, 3))
+            rv = (r_t * r_c.inv()).as_rotvec()  # world-frame rotation vector, angle in [0, pi]
+            e_pos = p_t - p
+            if i == 100:
+                iterations = 100
+                break
+            if np.linalg.norm(e_pos) < 1e-3 and np.linalg.norm(rv) < 1e-2:
+                converged, iterations = True, i + 1
+                break
+            jp, jr = np.zeros((3, model.nv)), np.zeros((3, model.nv))
+            mj_oracle.mj_jacSite(model, d2, jp, jr, sid)
+            J = np.vstack([jp[:, :7], 0.7 * jr[:, :7]])
+            e = np.concatenate([e_pos, 0.7 * rv])
+            A = np.vstack([J, np.sqrt(1e-2) * np.eye(7)])
+            b = np.concatenate([e, np.zeros(7)])
+            dq = np.linalg.lstsq(A, b, rcond=None)[0]
+            q = np.clip(q + np.clip(dq, -0.1, 0.1), lower, upper)
+        assert converged == want["converged"] and iterations == want["iterations"], case
+        np.testing.assert_allclose(q, want["q"], atol=1e-8)
+        np.testing.assert_allclose(p, want["final_pos"], atol=1e-9)
+        n_conv += converged
+    assert n_conv >= 10

@@ -1,6 +1,6 @@
 """A/B timing of the FP32 IK kernels (development tool, run on the GPU box):
 pair (F2) vs lane at 2^24 / 2^22 cold targets, the cfg2 batch through the latency kernel vs the
-refill kernel, and the single-call latencies.  PNP_IK_PARK / PNP_IK_FLUSH_MIN / PNP_IK_OCC are read once per process:
+refill kernel, and the single-call latencies.  PNP_IK_FLUSH_MIN / PNP_IK_OCC are read once per process:
 run the script once per setting.  Prints one JSON object."""
 import json
 import os
@@ -39,7 +39,7 @@ def main():
     engine.set_tree(tree)
     dev = torch.device("cuda")
     neutral = torch.tensor(NEUTRAL, dtype=torch.float32, device=dev)
-    out = {"env": {k: os.environ.get(k) for k in ("PNP_IK_PARK", "PNP_IK_FLUSH_MIN", "PNP_IK_OCC", "PNP_IK_SMALL")}}
+    out = {"env": {k: os.environ.get(k) for k in ("PNP_IK_FLUSH_MIN", "PNP_IK_OCC", "PNP_IK_SMALL")}}
     peak = max(engine.probe_fp32_peak()[0] for _ in range(2))
     out["fp32_peak_tflops"] = peak
     for log2n in ((24,) if quick else (24, 22, 26)):

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""BASELINE cfg5: IK scaling sweep, N in {2^20 .. 2^28} cold reachable targets per GPU, with the
-NCCL reduction of the success / iteration counters.  Run plain (1 GPU) or under torchrun.
+"""BASELINE cfg5: IK scaling sweep, N in {2^20 .. 2^28} cold reachable targets, with the NCCL reduction of the
+success / iteration counters.  Run plain (1 GPU) or under torchrun.  Default: N targets PER GPU (weak scaling);
+--total: N targets in all, rank r solves its contiguous shard of N / world (the 5 x 4 table of BASELINE cfg5).
 
-    python tools/sweep_cfg5.py [--max-log2 28] > profiles/sweep_cfg5_r1.json
+    python tools/sweep_cfg5.py [--max-log2 28] [--total] > profiles/sweep_cfg5_rN.json
 """
 import argparse
 import ctypes
@@ -25,6 +26,7 @@ def main():
     ap.add_argument("--min-log2", type=int, default=20)
     ap.add_argument("--max-log2", type=int, default=28)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--total", action="store_true", help="N is the total over all GPUs (strong scaling)")
     args = ap.parse_args()
     rank, local_rank, world = D.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
@@ -37,7 +39,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     rows = []
     for log2n in range(args.min_log2, args.max_log2 + 1, 2):
-        n = 1 << log2n
+        n = (1 << log2n) // world if args.total else 1 << log2n
         # generate targets in slices so the float64 generator temporaries stay small
         targets = torch.empty((n, 3), dtype=torch.float32, device=dev)
         step = 1 << 24
@@ -68,7 +70,7 @@ def main():
             ts.append(e0.elapsed_time(e1))
         ms = D.reduce_max(float(np.median(ts)), dev)
         c = D.reduce_counters(cnt).cpu().numpy()
-        rows.append({"log2_n_per_gpu": log2n, "n_gpus": world, "ms": ms, "converged_solves_per_s": float(c[1]) / (ms * 1e-3),
+        rows.append({"log2_n_total" if args.total else "log2_n_per_gpu": log2n, "n_per_gpu": n, "n_gpus": world, "ms": ms, "converged_solves_per_s": float(c[1]) / (ms * 1e-3),
                      "success_rate": float(c[2]) / float(c[0]), "mean_iterations": float(c[3]) / float(c[0]),
                      "alg_tflops_per_gpu": (500.0 * float(c[3]) + 216.0 * float(c[0])) / world / (ms * 1e-3) / 1e12})
         del targets, q8, aux
