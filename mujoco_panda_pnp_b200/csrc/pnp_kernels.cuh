@@ -174,6 +174,7 @@ struct IkArgs {
   unsigned flush_min; // ik_solve_v_kernel: lanes with a finished slot that trigger a store + refill
   unsigned solo_warp; // ik_solve_v_kernel, small batches: the block has 4 warps to load the 40 KB trig table quickly,
                       // only warp 0 solves (one warp per block spreads a small batch over all SMs)
+  unsigned tail;      // ik_solve_v_kernel<F2>: finish the block's last stragglers in the one-query-per-lane latency loop
 };
 
 // output layouts of the FP32 IK kernels
@@ -358,6 +359,64 @@ __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
                : "+f"(x) : "r"((unsigned)pred), "l"(ptr));
 }
 
+// ---------------------------------------------------------------------------------------------
+// One query per lane, from a given state to the end: the loop of the small-batch latency kernel, also run by the tail
+// phase of the pair kernel.  No refill, no per-slot state machine - the loop body is a single basic block (evaluate,
+// test, vote, step).  Same arithmetic as ik_solve_v_kernel (ik_eval_v / ik_step_v).  A finished lane is frozen (step
+// limit 0).  `it` is the lane's pass counter on entry (0 for a fresh query).  All 32 lanes must call.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lane_solve(const IkConst<float>& k, const TrigV& trig, bool valid, int it, float (&q)[NJ],
+                                           const float (&tgt)[3], float (&pf)[3], float& n2f, int& iterations, bool& conv) {
+  const float thresh2 = k.pos_thresh * k.pos_thresh;
+  bool done = !valid;
+  conv = false;
+  iterations = 0;
+  pf[0] = pf[1] = pf[2] = 0.0f;
+  n2f = 0.0f;
+  for (;; ++it) {
+    float p[3], e[3], n2, J[21];
+    ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
+    const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
+    const bool fin = !done && (last || n2 < thresh2);          // :61-64
+    if (fin) {
+      conv = !last;
+      iterations = conv ? it + 1 : it;                         // :66 / :85
+      pf[0] = p[0]; pf[1] = p[1]; pf[2] = p[2]; n2f = n2;      // final_pos / final_error (:88-89)
+    }
+    done = done || fin;
+    if (__all_sync(FULL, done)) break;
+    ik_step_v<float>(q, J, e, k.damping, done ? 0.0f : k.step_limit);  // frozen once finished
+  }
+}
+
+// the result record(s) of one query in the layout kOut (see IK_OUT_*)
+template <int kOut>
+__device__ __forceinline__ void store_lane_result(const IkArgs<float>& a, unsigned id, const float (&q)[NJ], const float (&pf)[3],
+                                                  float n2f, int iterations, bool conv) {
+  const float err = finish_sqrt(n2f);
+  const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
+  const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
+  const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
+  if (kOut == IK_OUT_PACKED) {
+    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
+    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
+    oq[1] = make_float4(q[4], q[5], q[6], err);
+    reinterpret_cast<float4*>(a.final_pos)[id] = make_float4(pf[0], pf[1], pf[2], word);
+  } else if (kOut == IK_OUT_COMPACT) {
+    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
+    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
+    oq[1] = make_float4(q[4], q[5], q[6], word);
+  } else {
+    float* qo = a.q_out + (size_t)id * NJ;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) qo[i] = q[i];
+    if (a.final_pos) { a.final_pos[(size_t)id * 3u] = pf[0]; a.final_pos[(size_t)id * 3u + 1] = pf[1]; a.final_pos[(size_t)id * 3u + 2] = pf[2]; }
+    if (a.pos_err) a.pos_err[id] = err;
+    if (a.iters) a.iters[id] = iterations;
+    if (a.flags) a.flags[id] = (uint8_t)fl;
+  }
+}
+
 // Deferred flush: a finished slot is FROZEN (its step limit becomes 0, so qn == q and the next passes
 // recompute the same p / n2) instead of being stored and refilled at once; the divergent store +
 // refill code runs only when at least `flush_min` lanes hold a finished slot, when nothing is
@@ -371,29 +430,43 @@ __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
 // the scoreboard of the target loads, and the first trig FFMA2 of the pass then waited a full
 // global-load latency for targets it does not need until mid-pass.
 //
-// Measured and dropped (round 2): a block-level straggler hand-over.  0.2 % of cold queries run into max_iters = 100
-// while the mean is 16 passes, so when the ticket pool runs dry most warps are left holding one or two long-running
-// slots.  Once a warp had seen the pool dry and was down to <= 16 running slots it dumped them to a block-shared list
-// and left; the last warp of the block took the whole list, so that the drain ran on one warp per block.  Bit-identical
-// results, but 2.94 ms against 2.91 ms for 2^24 queries with the code compiled in and switched off (and 2.82 ms
-// without it): a lone two-queries-per-lane warp needs ~1000 clocks per pass, about what four straggler warps sharing a
-// scheduler need per round, and the extra predicated loads of a refill that can also read the list cost more than the
-// shorter tail returned.  (Touching the HALVES of the register pairs inside a divergent block also made ptxas split
-// the pairs and re-pack them with 35 moves in the hot loop - whole-pair 64-bit dumps avoided that.)
+// Tail phase (a.tail, pair kernel).  0.2 % of cold queries run into max_iters = 100 while the mean is 16 passes, so when
+// the ticket pool runs dry most warps are left holding one or two long-running slots, and a warp with one live slot
+// still pays a full two-queries-per-lane pass: the launch time fits a + b n with a = 0.123 ms at max_iters = 100,
+// 0.050 ms at 30 and 0.013 ms for targets that take 3 passes (tools/dev/dev_ik_fixed_cost.py) - ~1.1 us per pass of the
+// longest query, on every scheduler.  Once a warp has seen the pool dry and is down to <= 8 running slots it parks
+// them (query index, pass counter, q) in shared memory and leaves; the LAST warp of the block to get there finishes
+// the block's stragglers after the loop, one per lane, in lane_solve().  A query continues from exactly the state it
+// was parked in: results do not depend on whether or where it was handed over.
+// (First attempt, dropped: the last warp took the list back into its 64 slots through the refill code.  No gain -
+// a lone two-queries-per-lane warp needs ~1000 clocks per pass, and a refill that can also read the list put 40
+// predicated instructions more into every flush.)
+constexpr int IK_TAIL_PER_WARP = 8;                          // a warp parks once it is down to this many running slots
+constexpr int IK_TAIL_MAX = (IK_BLOCK / 32) * IK_TAIL_PER_WARP;  // = 32: the block's stragglers fit one warp, one per lane
+__device__ __forceinline__ float2 pair_of(float v) { return make_float2(v, 0.0f); }
+__device__ __forceinline__ float2 pair_of(const F2& v) { return v.v; }
+
 template <typename V, int kOut, bool kBcast>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
   __shared__ __align__(16) float s_trig[kTrigVWords];
+  __shared__ float2 s_dump[S == 2 ? IK_BLOCK * NJ : 1];            // tail: every thread's q register pairs
+  __shared__ unsigned s_list[S == 2 ? IK_TAIL_MAX * 3 : 1];        // tail: query index, pass counter, owner of each parked slot
+  __shared__ unsigned s_list_n, s_live_warps;
   load_trigv_table(s_trig);
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
+  if (threadIdx.x == 0) { s_list_n = 0; s_live_warps = IK_BLOCK / 32; }
   __syncthreads();
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
   const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
+  const bool tail = S == 2 && a.tail && !a.solo_warp;  // see the tail phase below the loop
+  bool pool_dry = false;   // warp-uniform: a lane of this warp has drawn an index past the end of the batch
+  bool last_warp = false;  // this warp was the last of its block to leave the loop
   enum { IDLE = 0, RUN = 1, FIN_CONV = 2, FIN_NOCONV = 3 };
 
   V q[NJ], tgt[3], slim(0.0f);
@@ -460,6 +533,43 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         } else {
           pool_next += count;
         }
+        if (S == 2) pool_dry = pool_dry || __any_sync(FULL, ran_out);
+      }
+      if (S == 2 && tail && pool_dry) {  // warp-uniform
+        // ---- nothing left to take: once this warp is down to a few running slots it parks them and leaves ----------
+        unsigned run_m[S], n_run = 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          run_m[k] = __ballot_sync(FULL, st[k] == RUN);
+          n_run += (unsigned)__popc(run_m[k]);
+        }
+        if (n_run <= (unsigned)IK_TAIL_PER_WARP) {
+          unsigned base = 0;
+          if (n_run) {
+            if (lane == 0) base = atomicAdd(&s_list_n, n_run);
+            base = __shfl_sync(FULL, base, 0);
+            // every lane dumps BOTH its slots as whole register pairs: 64-bit stores that never touch a half (reading
+            // the halves inside this divergent block made ptxas split the pairs and re-pack them in the hot loop)
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) s_dump[threadIdx.x * NJ + i] = pair_of(q[i]);
+            unsigned before = 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+              if (st[k] == RUN) {
+                unsigned* e = s_list + (base + before + (unsigned)__popc(run_m[k] & lanemask_lt)) * 3u;
+                e[0] = idx[k];
+                e[1] = (unsigned)it[k];
+                e[2] = threadIdx.x * 2u + (unsigned)k;
+              }
+              before += (unsigned)__popc(run_m[k]);
+            }
+          }
+          __threadfence_block();  // list and dump are written before this warp is counted out
+          unsigned left = 0;
+          if (lane == 0) left = atomicSub(&s_live_warps, 1u);
+          last_warp = __shfl_sync(FULL, left, 0) == 1u;
+          break;
+        }
       }
       bool any_run = false;
 #pragma unroll
@@ -487,7 +597,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
     ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
+    // (pool dry: no refill left to amortise; the parking test above wants to see the running count after every finish)
+    flush = n_fin >= ((S == 2 && tail && pool_dry) ? 1 : flush_min) || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
     if (flush) {  // warp-uniform
       // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,
       //      so this pass's values are the query's final ones.  One exception: a query that finished on
@@ -541,6 +652,39 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
   }
 
+  if (S == 2 && last_warp) {
+    // ---- tail phase.  Every other warp of the block has parked its last running slots and gone (their fence precedes
+    //      their decrement, which precedes ours).  The stragglers of the whole block - a handful of queries on their
+    //      way to max_iters - finish here, one per lane, in the latency loop of the small-batch kernel: ~500 clocks
+    //      per pass for a lone warp, where four straggler warps sharing a scheduler needed ~2000 per round. -----------
+    __threadfence_block();
+    const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&s_list_n);  // <= 4 warps x IK_TAIL_PER_WARP = 32
+    if (cnt) {
+      const bool valid = lane < cnt;
+      const unsigned* e = s_list + (valid ? lane : 0u) * 3u;
+      const unsigned id = e[0], who = e[2];
+      const int it0 = (int)e[1];
+      const float* src = reinterpret_cast<const float*>(s_dump + (size_t)(who >> 1) * NJ) + (who & 1u);
+      float ql[NJ], q0[NJ], tl[3], pf[3], n2f;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) ql[i] = q0[i] = src[2 * i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tl[i] = a.targets[(size_t)id * 3u + i];
+      bool conv;
+      int iterations;
+      lane_solve(a.k, trig, valid, it0, ql, tl, pf, n2f, iterations, conv);
+      if (valid) {
+        if (iterations == (conv ? 1 : 0)) {  // parked before its first pass and finished on it: q_init untouched
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) ql[i] = q0[i];
+        }
+        store_lane_result<kOut>(a, id, ql, pf, n2f, iterations, conv);
+        c_n += 1u;
+        c_conv += conv ? 1u : 0u;
+        c_iter += (unsigned)iterations;
+      }
+    }
+  }
   if (a.counters) {
     const unsigned long long w_n = warp_sum((unsigned long long)c_n), w_conv = warp_sum((unsigned long long)c_conv),
                              w_iter = warp_sum(c_iter);
@@ -557,9 +701,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 // Small cold batches, latency bound (BASELINE cfg2: 4096 targets).  A launch of n <= ~one warp per scheduler lasts as
 // long as its slowest query - 100 passes for a target that runs into max_iters - so what matters is the latency of
 // ONE pass of a lone warp, not throughput.  One query per lane, one working warp per block (the batch spreads over all
-// SMs), three helper warps that only load the trig table; no ticket, no refill, no per-slot state machine: the loop
-// body is a single basic block (evaluate, test, vote, step) that ptxas can schedule for latency.  Same arithmetic as
-// ik_solve_v_kernel<float> (ik_eval_v / ik_step_v): bit-identical results.  A finished lane is frozen (step limit 0).
+// SMs), three helper warps that only load the trig table; no ticket, no refill: lane_solve() above.  Bit-identical to
+// ik_solve_v_kernel<float>.
 // ---------------------------------------------------------------------------------------------
 template <int kOut, bool kBcast>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<float> a) {
@@ -572,29 +715,15 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<f
   const unsigned id = blockIdx.x * 32u + lane;
   const bool valid = id < a.n;
   const unsigned ld = valid ? id : 0u;
-  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
-  float q[NJ], tgt[3], pf[3] = {0.0f, 0.0f, 0.0f}, n2f = 0.0f;
+  float q[NJ], tgt[3], pf[3], n2f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) tgt[i] = a.targets[(size_t)ld * 3u + i];
   const float* qi = kBcast ? a.q_init : a.q_init + (size_t)ld * NJ;
 #pragma unroll
   for (int i = 0; i < NJ; ++i) q[i] = qi[i];
-  bool done = !valid, conv = false;
-  int iterations = 0;
-  for (int it = 0;; ++it) {
-    float p[3], e[3], n2, J[21];
-    ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
-    const bool last = it >= a.k.max_iters;                     // loop ran out (ik_solver.py:57)
-    const bool fin = !done && (last || n2 < thresh2);          // :61-64
-    if (fin) {
-      conv = !last;
-      iterations = conv ? it + 1 : it;                         // :66 / :85
-      pf[0] = p[0]; pf[1] = p[1]; pf[2] = p[2]; n2f = n2;      // final_pos / final_error (:88-89)
-    }
-    done = done || fin;
-    if (__all_sync(FULL, done)) break;
-    ik_step_v<float>(q, J, e, a.k.damping, done ? 0.0f : a.k.step_limit);  // frozen once finished
-  }
+  bool conv;
+  int iterations;
+  lane_solve(a.k, trig, valid, 0, q, tgt, pf, n2f, iterations, conv);
   if (a.counters) {  // whole warp (lanes past the end of the batch add zeros)
     const unsigned long long w_n = warp_sum((unsigned long long)(valid ? 1u : 0u)),
                              w_conv = warp_sum((unsigned long long)((valid && conv) ? 1u : 0u)),
@@ -611,28 +740,7 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<f
 #pragma unroll
     for (int i = 0; i < NJ; ++i) q[i] = qi[i];
   }
-  const float err = finish_sqrt(n2f);
-  const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
-  const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
-  const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
-  if (kOut == IK_OUT_PACKED) {
-    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
-    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
-    oq[1] = make_float4(q[4], q[5], q[6], err);
-    reinterpret_cast<float4*>(a.final_pos)[id] = make_float4(pf[0], pf[1], pf[2], word);
-  } else if (kOut == IK_OUT_COMPACT) {
-    float4* oq = reinterpret_cast<float4*>(a.q_out) + (size_t)id * 2u;
-    oq[0] = make_float4(q[0], q[1], q[2], q[3]);
-    oq[1] = make_float4(q[4], q[5], q[6], word);
-  } else {
-    float* qo = a.q_out + (size_t)id * NJ;
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) qo[i] = q[i];
-    if (a.final_pos) { a.final_pos[(size_t)id * 3u] = pf[0]; a.final_pos[(size_t)id * 3u + 1] = pf[1]; a.final_pos[(size_t)id * 3u + 2] = pf[2]; }
-    if (a.pos_err) a.pos_err[id] = err;
-    if (a.iters) a.iters[id] = iterations;
-    if (a.flags) a.flags[id] = (uint8_t)fl;
-  }
+  store_lane_result<kOut>(a, id, q, pf, n2f, iterations, conv);
 }
 
 // ---------------------------------------------------------------------------------------------
