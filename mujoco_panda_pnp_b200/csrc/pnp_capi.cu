@@ -331,6 +331,9 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     // tail phase of the pair kernel (PNP_IK_TAIL=0 switches it off, for measurements)
     static const int env_tail = env_int("PNP_IK_TAIL", 1);
     args.tail = (S == 2 && !small && env_tail != 0) ? 1u : 0u;
+    // guided ticket chunks: a reservation = (queries left) / (2 x warps) (PNP_IK_GUIDED=0: fixed chunks)
+    static const int env_guided = env_int("PNP_IK_GUIDED", 1);
+    args.guided = (!small && env_guided != 0) ? (unsigned)(warps * 2) : 0u;
   }
   if (a.q_init_stride == 0)
     pnp::ik_solve_v_kernel<V, kOut, true><<<grid, block, 0, st>>>(args);
@@ -391,7 +394,7 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.targets = targets; a.q_init = q_init; a.q_init_stride = q_init_stride; a.n = (unsigned)n;
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
-  a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.tail = 0;
+  a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.tail = 0; a.guided = 0;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   if constexpr (std::is_same<T, float>::value) {
     // the latency kernel needs no ticket: skip the memset node as well

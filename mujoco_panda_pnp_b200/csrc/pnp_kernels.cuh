@@ -175,6 +175,7 @@ struct IkArgs {
   unsigned solo_warp; // ik_solve_v_kernel, small batches: the block has 4 warps to load the 40 KB trig table quickly,
                       // only warp 0 solves (one warp per block spreads a small batch over all SMs)
   unsigned tail;      // ik_solve_v_kernel<F2>: finish the block's last stragglers in the one-query-per-lane latency loop
+  unsigned guided;    // ik_solve_v_kernel: 0 = fixed ticket chunks; else a reservation is (queries left) / guided, within [32 S, chunk]
 };
 
 // output layouts of the FP32 IK kernels
@@ -354,6 +355,10 @@ __device__ __forceinline__ void ldg3_if(bool pred, const float* ptr, float& x, f
       "@p ld.global.nc.f32 %2, [%4+8];\n\t}"
       : "+f"(x), "+f"(y), "+f"(z) : "r"((unsigned)pred), "l"(ptr));
 }
+__device__ __forceinline__ void lds1_if(bool pred, const float* ptr, float& x) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.shared.f32 %0, [%2];\n\t}"
+               : "+f"(x) : "r"((unsigned)pred), "r"((unsigned)__cvta_generic_to_shared(ptr)));
+}
 __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
                : "+f"(x) : "r"((unsigned)pred), "l"(ptr));
@@ -481,6 +486,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 #pragma unroll
   for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; st[k] = IDLE; }
   unsigned pool_next = 0, pool_end = 0;  // warp-local pool of reserved query indices
+  unsigned my_chunk = a.chunk;           // queries this warp reserves with its next ticket atomic
   bool flush = true;  // first pass: nothing to store, every slot to fill
 
   while (true) {
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         const unsigned avail = pool_end - pool_next;
         unsigned fresh = 0;
         if (count > avail) {  // warp-uniform
-          if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
+          if (lane == 0) fresh = atomicAdd(a.ticket, my_chunk);
           fresh = __shfl_sync(FULL, fresh, 0);
         }
         unsigned before = 0;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
 #pragma unroll
           for (int i = 0; i < NJ; ++i) {
             float qi = Slots<V>::get(q[i], k);
-            if (kBcast) qi = ok ? s_q0[i] : qi;
+            if (kBcast) lds1_if(ok, s_q0 + i, qi);   // predicated load: one instruction instead of LDS + select
             else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
             Slots<V>::set(q[i], k, qi);
           }
@@ -529,7 +535,14 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         exhausted = exhausted || ran_out;
         if (count > avail) {
           pool_next = fresh + (count - avail);
-          pool_end = fresh + a.chunk;
+          pool_end = fresh + my_chunk;
+          if (a.guided) {
+            // guided self-scheduling: the next reservation shrinks with what is left, so that no warp is still working
+            // through a full chunk of 256 when the others have run dry
+            const unsigned left = pool_end < a.n ? a.n - pool_end : 0u;
+            const unsigned want = (left / a.guided) & ~31u;
+            my_chunk = want < 32u * S ? 32u * S : (want > a.chunk ? a.chunk : want);
+          }
         } else {
           pool_next += count;
         }
@@ -597,8 +610,14 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
     ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    // (pool dry: no refill left to amortise; the parking test above wants to see the running count after every finish)
-    flush = n_fin >= ((S == 2 && tail && pool_dry) ? 1 : flush_min) || !__any_sync(FULL, any_run) || __any_sync(FULL, imm);
+    const bool any_imm = __any_sync(FULL, imm);
+    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || any_imm;
+    if (S == 2 && tail && pool_dry && !flush) {  // warp-uniform; pool dry: flush (store, then park) once few slots still run
+      unsigned n_run = 0;
+#pragma unroll
+      for (int k = 0; k < S; ++k) n_run += (unsigned)__popc(__ballot_sync(FULL, st[k] == RUN));
+      flush = n_run <= (unsigned)IK_TAIL_PER_WARP;
+    }
     if (flush) {  // warp-uniform
       // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,
       //      so this pass's values are the query's final ones.  One exception: a query that finished on
@@ -617,7 +636,9 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         float qf[NJ];
 #pragma unroll
         for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
-        if (f && iterations == (conv ? 1 : 0)) {  // finished on the first pass (non-converged: max_iters == 0); rare
+        // finished on the first pass (non-converged: max_iters == 0): rare, and only ever in the flush that such a finish
+        // forces itself (imm) - a warp-uniform branch keeps the 7 predicated-off loads out of every other flush
+        if (any_imm && f && iterations == (conv ? 1 : 0)) {
           const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
 #pragma unroll
           for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
