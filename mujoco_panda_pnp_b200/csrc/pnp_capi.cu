@@ -691,30 +691,6 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
   a.iters = iters; a.flags = flags; a.counters = counters; a.ticket = ticket;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
-  if constexpr (std::is_same<T, float>::value) {
-    // FP32 on the specialised tree: the value-type kernels - two pose queries per lane on packed arithmetic from
-    // 2048 queries per SM up (PNP_KIN_SPEC_PAIR forces it, PNP_KIN_SPEC_LANE / PNP_POSE_V=0 keep the scalar kernel)
-    static const int env_v = env_int("PNP_POSE_V", 1);
-    const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR ||
-                      (params->kinematics != PNP_KIN_SPEC_LANE && (long long)n >= (long long)s->sm_count * 2048);
-    if (spec && env_v && pair) {
-      int occv = 2;
-      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::ik_pose_solve_v_kernel<pnp::F2, true>, pnp::IK_BLOCK, 0);
-      if (e != cudaSuccess || occv < 1) occv = 2;
-      const long long lanes_needed = (n + 1) / 2;
-      const bool small_v = lanes_needed <= (long long)s->sm_count * pnp::IK_BLOCK;
-      const int gridv = small_v ? (int)((lanes_needed + 31) / 32) : grid_for(lanes_needed, block, s->sm_count, occv);
-      long long chunkv = n / ((long long)gridv * (small_v ? 1 : block / 32) * 16);
-      chunkv = chunkv < 64 ? 64 : (chunkv > 256 ? 256 : chunkv);
-      a.chunk = (unsigned)(chunkv & ~31ll);
-      a.solo_warp = small_v ? 1u : 0u;
-      if (q_init_stride == 0) pnp::ik_pose_solve_v_kernel<pnp::F2, true><<<gridv, block, 0, st>>>(a);
-      else pnp::ik_pose_solve_v_kernel<pnp::F2, false><<<gridv, block, 0, st>>>(a);
-      ++g_launches;
-      CUDA_TRY(cudaGetLastError());
-      return PNP_OK;
-    }
-  }
   int occ = 4;
   if (!small) {
     cudaError_t e = spec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pnp::ik_pose_solve_kernel<T, pnp::SpecKin>, pnp::IK_BLOCK, 0)

@@ -1457,269 +1457,6 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_pose_solve_kernel(const PoseIkArg
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Pose-mode IK over the value types of pnp_vec.cuh (specialised tree, FP32): V = F2 solves TWO pose queries per lane
-// with FK + 6x7 Jacobian (spec_fk_full_v), the error quaternion, J J^T (spec_jjt6_v), the 6x6 LDL^T and J^T y
-// (spec_jty6_v) on packed FFMA2/FMUL2/FADD2; mju_mat2Quat's case selection, atan2 and the clamps run per slot.
-// Same semantics as ik_pose_solve_kernel (test before update, frozen finished slots, refill from a chunked ticket,
-// deferred flush as in ik_solve_v_kernel).  V = float is the one-query-per-lane instantiation of the same code.
-// ---------------------------------------------------------------------------------------------
-template <typename V>
-__device__ __forceinline__ void ldlt6_solve_v(V (&A)[21], V (&b)[6]) {
-  // A: lower triangle of an SPD matrix, row-major (A[r (r + 1) / 2 + c], c <= r); on return b = A^-1 b
-  auto at = [](int r, int c) { return r * (r + 1) / 2 + c; };
-  V dg[6], dinv[6], w[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    V d = A[at(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; ++k) {
-      w[k] = pnp_mul(A[at(j, k)], dg[k]);              // L_jk D_k
-      d = pnp_fma(pnp_neg(A[at(j, k)]), w[k], d);
-    }
-    dg[j] = d;
-    dinv[j] = v_rcp(d);
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      V v = A[at(i, j)];
-#pragma unroll
-      for (int k = 0; k < j; ++k) v = pnp_fma(pnp_neg(A[at(i, k)]), w[k], v);
-      A[at(i, j)] = pnp_mul(v, dinv[j]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int k = 0; k < i; ++k) b[i] = pnp_fma(pnp_neg(A[at(i, k)]), b[k], b[i]);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) b[i] = pnp_mul(b[i], dinv[i]);
-#pragma unroll
-  for (int i = 5; i >= 0; --i)
-#pragma unroll
-    for (int k = i + 1; k < 6; ++k) b[i] = pnp_fma(pnp_neg(A[at(k, i)]), b[k], b[i]);
-}
-
-template <typename V, bool kBcast>
-__global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? 2 : 1) ik_pose_solve_v_kernel(const PoseIkArgs<float> a) {
-  constexpr int S = Slots<V>::kN;
-  const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float s_q0[8];
-  __shared__ __align__(16) float s_trig[kTrigVWords];
-  load_trigv_table(s_trig);
-  if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
-  __syncthreads();
-  if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
-  const TrigV trig{s_trig};
-  const unsigned lanemask_lt = (1u << lane) - 1u;
-  const float pt2 = a.k.pos_thresh * a.k.pos_thresh, rt2 = a.rot_thresh * a.rot_thresh;
-  const int flush_min = S == 2 ? 6 : 1;
-  enum { IDLE = 0, RUN = 1, FIN_CONV = 2, FIN_NOCONV = 3 };
-
-  V q[NJ], tp[3], tq[4], slim(0.0f);
-  int it[S], st[S];
-  unsigned idx[S];
-  bool exhausted = false;
-  unsigned c_n = 0, c_conv = 0;
-  unsigned long long c_iter = 0;
-#pragma unroll
-  for (int i = 0; i < NJ; ++i) q[i] = V(0.0f);
-  tp[0] = tp[1] = tp[2] = V(0.0f);
-  tq[0] = V(1.0f); tq[1] = tq[2] = tq[3] = V(0.0f);
-#pragma unroll
-  for (int k = 0; k < S; ++k) { it[k] = 0; idx[k] = 0; st[k] = IDLE; }
-  unsigned pool_next = 0, pool_end = 0;
-  bool flush = true;
-
-  while (true) {
-    if (flush) {  // warp-uniform
-      // ---- refill idle slots (slot-major ranks) ---------------------------------------------------------
-      unsigned need[S], count = 0;
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        need[k] = __ballot_sync(FULL, st[k] == IDLE && !exhausted);
-        count += (unsigned)__popc(need[k]);
-      }
-      if (count) {
-        const unsigned avail = pool_end - pool_next;
-        unsigned fresh = 0;
-        if (count > avail) {
-          if (lane == 0) fresh = atomicAdd(a.ticket, a.chunk);
-          fresh = __shfl_sync(FULL, fresh, 0);
-        }
-        unsigned before = 0;
-        bool ran_out = false;
-#pragma unroll
-        for (int k = 0; k < S; ++k) {  // predicated, no per-slot branch
-          const bool want = st[k] == IDLE && !exhausted;
-          const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
-          const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
-          const bool ok = want && id < a.n;
-          ran_out = ran_out || (want && !ok);
-          float t0 = Slots<V>::get(tp[0], k), t1 = Slots<V>::get(tp[1], k), t2 = Slots<V>::get(tp[2], k);
-          ldg3_if(ok, a.target_pos + (size_t)id * 3u, t0, t1, t2);
-          Slots<V>::set(tp[0], k, t0); Slots<V>::set(tp[1], k, t1); Slots<V>::set(tp[2], k, t2);
-          float u0 = Slots<V>::get(tq[0], k), u1 = Slots<V>::get(tq[1], k), u2 = Slots<V>::get(tq[2], k), u3 = Slots<V>::get(tq[3], k);
-          ldg3_if(ok, a.target_quat + (size_t)id * 4u, u0, u1, u2);
-          ldg1_if(ok, a.target_quat + (size_t)id * 4u + 3, u3);
-          const float inv = rsqrtf(fmaxf((u0 * u0 + u1 * u1) + (u2 * u2 + u3 * u3), 1e-30f));  // normalised on load
-          Slots<V>::set(tq[0], k, ok ? u0 * inv : u0); Slots<V>::set(tq[1], k, ok ? u1 * inv : u1);
-          Slots<V>::set(tq[2], k, ok ? u2 * inv : u2); Slots<V>::set(tq[3], k, ok ? u3 * inv : u3);
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) {
-            float qi = Slots<V>::get(q[i], k);
-            if (kBcast) lds1_if(ok, s_q0 + i, qi);
-            else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
-            Slots<V>::set(q[i], k, qi);
-          }
-          idx[k] = ok ? id : idx[k];
-          it[k] = ok ? 0 : it[k];
-          st[k] = ok ? (int)RUN : st[k];
-          Slots<V>::set(slim, k, ok ? a.k.step_limit : Slots<V>::get(slim, k));
-          before += (unsigned)__popc(need[k]);
-        }
-        exhausted = exhausted || ran_out;
-        if (count > avail) { pool_next = fresh + (count - avail); pool_end = fresh + a.chunk; }
-        else pool_next += count;
-      }
-      bool any_run = false;
-#pragma unroll
-      for (int k = 0; k < S; ++k) any_run = any_run || st[k] == RUN;
-      if (!__any_sync(FULL, any_run)) break;
-    }
-
-    // ---- one 6-row DLS pass for all slots of all lanes -----------------------------------------------------
-    V s[NJ], c[NJ];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      const float qr = pnp_spec::spec_qref<float>(i);
-      trig(qr != 0.0f ? pnp_add(q[i], V(-qr)) : q[i], &s[i], &c[i]);
-    }
-    V p[3], J[42], R[9];
-    pnp_spec::spec_fk_full_v<V>(s, c, p, J, R);
-    V qc[4];
-#pragma unroll
-    for (int k = 0; k < S; ++k) {  // mju_mat2Quat: the case selection is per query
-      float m[9], o[4];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) m[i] = Slots<V>::get(R[i], k);
-      mat2quat_fast(m, o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) Slots<V>::set(qc[i], k, o[i]);
-    }
-    // err_quat = target (x) conj(current); rotation vector in the world frame
-    V eq[4];
-    eq[0] = pnp_fma(tq[3], qc[3], pnp_fma(tq[2], qc[2], pnp_fma(tq[1], qc[1], pnp_mul(tq[0], qc[0]))));
-    eq[1] = pnp_fma(tq[3], qc[2], pnp_fma(pnp_neg(tq[2]), qc[3], pnp_fma(tq[1], qc[0], pnp_mul(pnp_neg(tq[0]), qc[1]))));
-    eq[2] = pnp_fma(pnp_neg(tq[3]), qc[1], pnp_fma(tq[2], qc[0], pnp_fma(tq[1], qc[3], pnp_mul(pnp_neg(tq[0]), qc[2]))));
-    eq[3] = pnp_fma(tq[3], qc[0], pnp_fma(tq[2], qc[1], pnp_fma(pnp_neg(tq[1]), qc[2], pnp_mul(pnp_neg(tq[0]), qc[3]))));
-    V rv[3];
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-      const float e4[4] = {Slots<V>::get(eq[0], k), Slots<V>::get(eq[1], k), Slots<V>::get(eq[2], k), Slots<V>::get(eq[3], k)};
-      float r3[3];
-      quat2vel_fast(e4, r3);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) Slots<V>::set(rv[i], k, r3[i]);
-    }
-    V err[6];
-    err[0] = v_sub(tp[0], p[0]); err[1] = v_sub(tp[1], p[1]); err[2] = v_sub(tp[2], p[2]);
-    const V pe2 = pnp_fma(err[2], err[2], pnp_fma(err[1], err[1], pnp_mul(err[0], err[0])));
-    const V re2 = pnp_fma(rv[2], rv[2], pnp_fma(rv[1], rv[1], pnp_mul(rv[0], rv[0])));
-    const V wv(a.rot_weight);
-    err[3] = pnp_mul(rv[0], wv); err[4] = pnp_mul(rv[1], wv); err[5] = pnp_mul(rv[2], wv);
-
-    bool any_fin = false, any_run = false, imm = false;
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-      const bool last = it[k] >= a.k.max_iters;
-      const bool newly = st[k] == RUN && (last || (Slots<V>::get(pe2, k) < pt2 && Slots<V>::get(re2, k) < rt2));
-      const bool stays = st[k] == RUN && !newly;
-      imm = imm || (newly && it[k] == 0);
-      it[k] += (stays || (newly && !last)) ? 1 : 0;
-      if (newly) {
-        st[k] = last ? FIN_NOCONV : FIN_CONV;
-        Slots<V>::set(slim, k, 0.0f);  // freeze
-      }
-      any_fin = any_fin || st[k] >= FIN_CONV;
-      any_run = any_run || stays;
-    }
-    // update: J_w = [jacp; w jacr], dq = J_w^T (J_w J_w^T + damping I6)^-1 e
-    if (a.rot_weight != 1.0f) {
-#pragma unroll
-      for (int r = 3; r < 6; ++r)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-          if (!pnp_spec::spec_j6_zero(r, j)) J[r * 7 + j] = pnp_mul(J[r * 7 + j], wv);
-    }
-    V A[21];
-    pnp_spec::spec_jjt6_v<V>(J, A);
-    const V lam(a.k.damping);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) A[r * (r + 1) / 2 + r] = pnp_add(A[r * (r + 1) / 2 + r], lam);
-    ldlt6_solve_v<V>(A, err);
-    V dq[NJ];
-    pnp_spec::spec_jty6_v<V>(J, err, dq);
-#pragma unroll
-    for (int i = 0; i < NJ; ++i)
-      q[i] = v_clamp(pnp_add(q[i], v_clamp_sym(dq[i], slim)), pnp_spec::spec_lower<float>(i), pnp_spec::spec_upper<float>(i));
-
-    const int n_fin = __popc(__ballot_sync(FULL, any_fin));
-    const bool any_imm = __any_sync(FULL, imm);
-    flush = n_fin >= flush_min || !__any_sync(FULL, any_run) || any_imm;
-    if (flush) {  // warp-uniform
-      // ---- store finished slots (a frozen slot recomputes the same pose every pass: this pass's values are final) ----
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const bool f = st[k] >= FIN_CONV;
-        const bool conv = st[k] == FIN_CONV;
-        const float pe = finish_sqrt(Slots<V>::get(pe2, k)), re = finish_sqrt(Slots<V>::get(re2, k));
-        const int iterations = it[k];
-        const bool success = conv && (pe < a.k.pos_thresh * 2.0f) && (re < a.rot_thresh * 2.0f);
-        const unsigned id = idx[k];
-        float qf[NJ], pf[3], cf[4];
-#pragma unroll
-        for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) pf[i] = Slots<V>::get(p[i], k);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cf[i] = Slots<V>::get(qc[i], k);
-        if (any_imm && f && iterations == (conv ? 1 : 0)) {  // finished on the first pass: q_init comes back untouched
-          const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
-        }
-        if (f) {
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) a.q_out[(size_t)id * NJ + i] = qf[i];
-          if (a.final_pos) { a.final_pos[(size_t)id * 3] = pf[0]; a.final_pos[(size_t)id * 3 + 1] = pf[1]; a.final_pos[(size_t)id * 3 + 2] = pf[2]; }
-          if (a.final_quat) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a.final_quat[(size_t)id * 4 + i] = cf[i];
-          }
-          if (a.pos_err) a.pos_err[id] = pe;
-          if (a.rot_err) a.rot_err[id] = re;
-          if (a.iters) a.iters[id] = iterations;
-          if (a.flags) a.flags[id] = (uint8_t)((conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u));
-        }
-        c_n += f ? 1u : 0u;
-        c_conv += (f && conv) ? 1u : 0u;
-        c_iter += f ? (unsigned)iterations : 0u;
-        st[k] = f ? (int)IDLE : st[k];
-      }
-    }
-  }
-  if (a.counters) {
-    const unsigned long long w_n = warp_sum((unsigned long long)c_n), w_conv = warp_sum((unsigned long long)c_conv),
-                             w_iter = warp_sum(c_iter);
-    if (lane == 0) {
-      atomicAdd(a.counters + PNP_IK_CNT_N, w_n);
-      atomicAdd(a.counters + PNP_IK_CNT_CONVERGED, w_conv);
-      atomicAdd(a.counters + PNP_IK_CNT_SUCCESS, w_conv);
-      atomicAdd(a.counters + PNP_IK_CNT_ITERATIONS, w_iter);
-    }
-  }
-}
-
 // =============================================================================================
 // MoveIKSkill.reset trajectory planner (skills/move.py:76-191) as a per-lane state machine.
 //

@@ -1,5 +1,7 @@
-"""Pose-mode IK timing: one query per lane (scalar-template kernel) vs two per lane (ik_pose_solve_v_kernel<F2>)
-(development tool, GPU box).  Prints one JSON object."""
+"""Pose-mode IK timing (development tool, GPU box).  Prints one JSON object.
+(Round 2 measured a two-queries-per-lane packed variant of this kernel with this script: 230 registers, 2-3 blocks per
+SM, 1.067 ms against 1.091 ms for 2^22 poses - the per-query parts (mju_mat2Quat's case selection, atan2, the serial
+6x6 LDL^T) dominate and do not pack; dropped.)"""
 import json
 import os
 import sys
@@ -20,7 +22,7 @@ for lg in (20, 22):
     n = 1 << lg
     qp = synthetic.reachable_move_envs(n, tree.lower, tree.upper, seed=5, device=dev, spread=0.5)["q_goal"]
     ppos, pquat, _ = engine.fk_jac(qp, want_jac=False)
-    for kin in ("spec_lane", "spec_pair"):
+    for kin in ("spec_lane",):
         p = engine.ik_params(kinematics=kin)
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
         engine.ik_pose_solve(ppos, pquat, neutral, p, counters=cnt)

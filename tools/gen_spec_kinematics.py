@@ -352,9 +352,7 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
     rng = np.random.default_rng(12345)
     f_pos, st_pos, _, _ = gen_function(snapped, rng, "spec_fk_pos", False, False)
     f_jac, st_jac, jp_zero, _ = gen_function(snapped, rng, "spec_fk_jacp", True, False)
-    f_full, st_full, jpf_zero, jr_zero = gen_function(snapped, rng, "spec_fk_full", False, True)
-    assert (jpf_zero == jp_zero).all()
-    j6_zero = np.vstack([jp_zero, jr_zero])  # structural zeros of the 6x7 Jacobian [jacp; jacr]
+    f_full, st_full, _, _ = gen_function(snapped, rng, "spec_fk_full", False, True)
 
     # A = Jp Jp^T (upper triangle, 6 unique) and dq = Jp^T y skipping structural zeros
     jjt = ["template <typename T>\n__device__ __forceinline__ void spec_jjt(const T* __restrict__ J, T* __restrict__ A) {"]
@@ -399,39 +397,6 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         jty.append(f"  dq[{j}] = {'d%d' % j if started[j] else 'T(0.0)'};")
     jty.append("}")
 
-    # Pose-mode (6-row) task: A = J J^T (lower triangle, 21 entries, A[r (r + 1) / 2 + c]) and dq = J^T y over the
-    # full 6x7 Jacobian of spec_fk_full, skipping structural zeros; value-type ("_v") form only.
-    jjt6 = ["template <typename T>\n__device__ __forceinline__ void spec_jjt6_v(const T* __restrict__ J, T* __restrict__ A) {"]
-    pairs6 = [(r, c) for r in range(6) for c in range(r + 1)]
-    started6 = [False] * 21
-    flops_jjt6 = 0
-    for j in range(7):
-        for k, (r, c) in enumerate(pairs6):
-            if j6_zero[r, j] or j6_zero[c, j]:
-                continue
-            a_, b_ = f"J[{r * 7 + j}]", f"J[{c * 7 + j}]"
-            jjt6.append(f"  {'T ' if not started6[k] else ''}a{k} = " + (f"pnp_fma({a_}, {b_}, a{k});" if started6[k] else f"pnp_mul({a_}, {b_});"))
-            flops_jjt6 += 2 if started6[k] else 1
-            started6[k] = True
-    for k in range(21):
-        jjt6.append(f"  A[{k}] = {'a%d' % k if started6[k] else 'T(0.0)'};")
-    jjt6.append("}")
-    jty6 = ["template <typename T>\n__device__ __forceinline__ void spec_jty6_v(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {"]
-    started7 = [False] * 7
-    flops_jty6 = 0
-    for r in range(6):
-        for j in range(7):
-            if j6_zero[r, j]:
-                continue
-            jty6.append(f"  {'T ' if not started7[j] else ''}d{j} = " + (f"pnp_fma(J[{r * 7 + j}], y[{r}], d{j});" if started7[j] else f"pnp_mul(J[{r * 7 + j}], y[{r}]);"))
-            flops_jty6 += 2 if started7[j] else 1
-            started7[j] = True
-    for j in range(7):
-        jty6.append(f"  dq[{j}] = {'d%d' % j if started7[j] else 'T(0.0)'};")
-    jty6.append("}")
-    j6_expr = " || ".join(f"(r == {r} && j == {j})" for r in range(6) for j in range(7) if j6_zero[r, j]) or "false"
-    mask6_rows = ", ".join("{" + ", ".join("true" if z else "false" for z in row) + "}" for row in j6_zero)
-
     def flop(st):
         return st["mul"] + st["add"] + 2 * st["fma"]
 
@@ -445,7 +410,6 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
 //   spec_fk_jacp  {flop(st_jac):4d} FLOP   ({st_jac})
 //   spec_fk_full  {flop(st_full):4d} FLOP   ({st_full})
 //   spec_jjt      {flops_jjt:4d} FLOP      spec_jty {flops_jty:4d} FLOP
-//   spec_jjt6_v   {flops_jjt6:4d} FLOP      spec_jty6_v {flops_jty6:4d} FLOP   (pose mode, 6x7 Jacobian)
 #pragma once
 
 namespace pnp_spec {{
@@ -475,14 +439,6 @@ __host__ __device__ __forceinline__ constexpr bool spec_jp_col_zero(int j) {{ re
 {chr(10).join(jjt)}
 
 {chr(10).join(jty)}
-
-// structurally-zero entries of the full 6x7 Jacobian [jacp; jacr]
-static constexpr bool kJ6Zero[6][7] = {{{mask6_rows}}};
-__host__ __device__ __forceinline__ constexpr bool spec_j6_zero(int r, int j) {{ return {j6_expr}; }}
-
-{chr(10).join(jjt6)}
-
-{chr(10).join(jty6)}
 
 }}  // namespace pnp_spec
 """
