@@ -2,7 +2,7 @@
 # Run on the GPU box (via gpurun): bench line, ncu launch list of the same command, and one
 # `--set full` capture per hot kernel.  Outputs land in gpurun_out/ (copied to profiles/ here).
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
@@ -15,7 +15,7 @@ SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --log2-n-ik 22 --l
 # every --set full capture sits behind ONE successful plain run of the same command: ncu on a program that
 # faulted leaves the GPU unusable until a reset (B200_PROFILING.md)
 if $SMALL > $OUT/plain_small_${TAG}.log 2>&1; then
-  for K in ik_solve_v_kernel reward_kernel her_relabel_kernel; do
+  for K in ik_solve_v_kernel ik_solve_small_kernel reward_kernel her_relabel_kernel; do
     ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
     echo "$K full rc=$?"
   done
