@@ -238,3 +238,36 @@ def test_planner_full_size_properties():
         assert torch.equal(out[f], ref[f]), f
     mask = idx < L[:, None]
     assert torch.equal(traj[mask], ref["traj"][mask])
+
+
+def test_fallback_strategy_2_is_exercised_against_the_oracle(oracle_chain):
+    """move.py:160-176 (strategy 2: step with y frozen) cannot be reached with the reference's own constants - strategy
+    1 re-solves for a point <= 1 mm away with pos_thresh = 1e-3 and always "succeeds"  - so the 18
+    reference-generated moves never enter it.  With an IK that is allowed a single pass and a tighter threshold,
+    strategy 1 does fail and the planner walks through strategy 2, its success (`continue`) and its failure (`break`,
+    status bit 1): the FP64 device planner must reproduce the C oracle's state machine exactly, and the FP32 value-type
+    kernels (one / two envs per lane) must agree with each other bit for bit and with FP64 on nearly every env."""
+    n = 2048
+    w = synthetic.waypoint_envs(n, seed=11, dtype=torch.float64)
+    for thr, step in ((8e-4, 0.05), (3e-4, 0.01)):
+        p64 = engine.ik_params(max_iters=1, pos_thresh=thr)
+        kw = dict(step_size=step, max_outer=200, traj_cap=256)
+        ref = c_oracle.move_plan(oracle_chain, w["q_start"].numpy(), w["goal"].numpy(), max_iters=1, ik_pos_thresh=thr,
+                                 nthreads=8, **kw)
+        assert (ref["status"] & 1).sum() > n // 2          # most envs end in the `break` after strategy 2 fails ...
+        assert (ref["traj_len"] > 3).sum() > n // 10       # ... some after fallback successes on the way
+        out = engine.move_ik_plan(w["q_start"].cuda(), w["goal"].cuda(), p64, **kw)
+        np.testing.assert_array_equal(out["status"].cpu().numpy(), ref["status"])
+        np.testing.assert_array_equal(out["traj_len"].cpu().numpy(), ref["traj_len"])
+        np.testing.assert_array_equal(out["n_solves"].cpu().numpy(), ref["n_solves"])
+        tl = ref["traj_len"]
+        traj = out["traj"].cpu().numpy()
+        for k in range(0, n, 7):
+            np.testing.assert_allclose(traj[k, : tl[k]], ref["traj"][k, : tl[k]], atol=1e-8)
+        qs, gl = w["q_start"].float().cuda(), w["goal"].float().cuda()
+        a = engine.move_ik_plan(qs, gl, engine.ik_params(max_iters=1, pos_thresh=thr, kinematics="spec_lane"), **kw)
+        b = engine.move_ik_plan(qs, gl, engine.ik_params(max_iters=1, pos_thresh=thr, kinematics="spec_pair"), **kw)
+        for f in ("traj_len", "n_solves", "status", "q_final", "traj"):
+            assert torch.equal(a[f], b[f]), f
+        same = (a["status"].cpu().numpy() == ref["status"]) & (a["traj_len"].cpu().numpy() == ref["traj_len"])
+        assert same.mean() > 0.9, same.mean()
