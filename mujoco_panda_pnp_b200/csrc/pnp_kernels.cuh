@@ -188,7 +188,14 @@ enum { IK_OUT_SEPARATE = 0,  // five arrays (pnp_ik_solve_f32)
 __device__ __forceinline__ bool below_thresh(double n2, const IkConst<double>& k) { return sqrt(n2) < k.pos_thresh; }
 __device__ __forceinline__ bool below_thresh(float n2, const IkConst<float>& k) { return n2 < k.pos_thresh * k.pos_thresh; }
 __device__ __forceinline__ double finish_sqrt(double n2) { return sqrt(n2); }
-__device__ __forceinline__ float finish_sqrt(float n2) { return n2 > 0.0f ? n2 * rsqrtf(n2) : 0.0f; }
+// sqrt as x * rsqrt(x) on one MUFU.RSQ.  (rsqrtf() wraps the same instruction in a subnormal fix-up - scale by 2^24,
+// MUFU, scale by 2^12 - i.e. three more FMA-pipe instructions per call in the store block, where everything on that pipe
+// queues behind the packed math; squared distances below 1e-30 m^2 are reported as 0.)
+__device__ __forceinline__ float finish_sqrt(float n2) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));
+  return n2 > 1e-30f ? n2 * r : 0.0f;
+}
 
 template <typename T, typename Kin, int kOut>
 __global__ void __launch_bounds__(IK_BLOCK) ik_solve_kernel(const IkArgs<T> a) {

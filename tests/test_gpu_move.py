@@ -254,8 +254,8 @@ def test_fallback_strategy_2_is_exercised_against_the_oracle(oracle_chain):
         kw = dict(step_size=step, max_outer=200, traj_cap=256)
         ref = c_oracle.move_plan(oracle_chain, w["q_start"].numpy(), w["goal"].numpy(), max_iters=1, ik_pos_thresh=thr,
                                  nthreads=8, **kw)
-        assert (ref["status"] & 1).sum() > n // 2          # most envs end in the `break` after strategy 2 fails ...
-        assert (ref["traj_len"] > 3).sum() > n // 10       # ... some after fallback successes on the way
+        assert (ref["status"] & 1).sum() > n // 2          # most envs end in the `break` after strategy 2 fails,
+        assert (ref["status"] & 2).sum() > 0               # the rest keep going on fallback successes up to the round bound
         out = engine.move_ik_plan(w["q_start"].cuda(), w["goal"].cuda(), p64, **kw)
         np.testing.assert_array_equal(out["status"].cpu().numpy(), ref["status"])
         np.testing.assert_array_equal(out["traj_len"].cpu().numpy(), ref["traj_len"])

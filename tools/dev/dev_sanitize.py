@@ -1,4 +1,5 @@
-"""Small-size pass over every kernel family, meant to run under compute-sanitizer (memcheck)."""
+"""Small-size pass over every kernel family, meant to run under compute-sanitizer (memcheck; `race` as argv[1] keeps
+only the kernels with shared-memory hand-overs, for racecheck)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -7,6 +8,29 @@ from mujoco_panda_pnp_b200 import engine, synthetic, KinematicTree
 tree = KinematicTree.from_mjcf(); engine.set_tree(tree)
 dev = torch.device("cuda")
 neutral = torch.tensor(synthetic.NEUTRAL_Q, device=dev)
+RACE = len(sys.argv) > 1 and sys.argv[1] == "race"
+# round 2: the pair kernel's tail phase (needs a batch that fills the grid: spec_pair at 200 k queries, some of them
+# unreachable so that stragglers are parked), compact records, the small-batch latency kernel (AUTO at n <= 128 per SM)
+big = synthetic.random_joint_configs(200_003, tree.lower, tree.upper, seed=4, device=dev)
+tgb = engine.fk_jac(big, want_quat=False, want_jac=False)[0]
+tgb[::61] = torch.tensor([2.5, 0.0, 0.5], device=dev)
+for compact in (False, True):
+    engine.ik_solve(tgb, neutral, engine.ik_params(kinematics="spec_pair", max_iters=40), compact=compact)
+engine.ik_solve(tgb[:4096], neutral, engine.ik_params(max_iters=40))
+engine.ik_solve(tgb[:33], neutral, engine.ik_params(max_iters=40), compact=True)
+torch.cuda.synchronize()
+if RACE:
+    print("sanitize pass (race subset) done")
+    sys.exit(0)
+import numpy as _np
+from mujoco_panda_pnp_b200 import KinematicData, KinematicModel
+from mujoco_panda_pnp_b200.envs import FrankaShelfPNPReward
+from mujoco_panda_pnp_b200.skills import JacobianIKController
+_model = KinematicModel.from_xml_path(os.path.join(ROOT, "mujoco_panda_pnp_b200", "assets", "panda_shelf_kinematic.xml"))
+JacobianIKController(_model, KinematicData(_model)).solve(_np.array([1.415, 0.0, 0.73]), _np.array(synthetic.NEUTRAL_Q))
+FrankaShelfPNPReward("dense").compute_reward(_np.array([1.0, 0.0, 0.3]), _np.array([1.0, 0.1, 0.3]), {})
+order = torch.randperm(5000, device=dev).int()
+engine.move_plan_order_check(order)
 for n in (1, 65, 1000, 70001):
     q = synthetic.random_joint_configs(n, tree.lower, tree.upper, seed=1, device=dev)
     tg = engine.fk_jac(q)[0]
