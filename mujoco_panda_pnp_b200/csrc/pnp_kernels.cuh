@@ -1,6 +1,8 @@
 // Kernels of libpnp_b200.so (sm_100a).  See DESIGN.md for the rooflines and data layout.
 #pragma once
 
+#include <type_traits>
+
 #include "pnp_common.cuh"
 
 namespace pnp {
@@ -630,53 +632,60 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       //      so this pass's values are the query's final ones.  One exception: a query that finished on
       //      its FIRST pass returns q_init untouched (ik_solver.py:61-67 tests before any update) even
       //      when q_init violates the joint limits, where the limit clip of the frozen step has just
-      //      moved it: those are flushed in the same pass (imm) and re-read their q_init.
+      //      moved it: those are flushed in the same pass (imm) and re-read their q_init.  That only ever
+      //      happens in a flush such a finish forces itself, so the common flush is a second copy of the block
+      //      WITHOUT the reload: no seven predicated-off loads per slot and no copy of q into registers of its own.
+      auto store_finished = [&](auto with_reload) {
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const bool f = st[k] >= FIN_CONV;
-        const bool conv = st[k] == FIN_CONV;
-        const float err = finish_sqrt(Slots<V>::get(n2, k));
-        const int iterations = it[k];
-        const bool success = conv && (err < a.k.pos_thresh * 2.0f);  // :88-92
-        const unsigned fl = (conv ? PNP_IK_CONVERGED : 0u) | (success ? PNP_IK_SUCCESS : 0u);
-        const unsigned id = idx[k];
-        float qf[NJ];
+        for (int k = 0; k < S; ++k) {
+          const bool f = st[k] >= FIN_CONV;
+          const bool conv = st[k] == FIN_CONV;
+          const float err = finish_sqrt(Slots<V>::get(n2, k));
+          const int iterations = it[k];
+          // :88-92  success = converged && final_error < 2 * pos_thresh: a converged query has |e|^2 < pos_thresh^2, so
+          // the second test cannot fail - no compare, no 2 * pos_thresh on the FMA pipe of this block
+          const unsigned fl = conv ? (PNP_IK_CONVERGED | PNP_IK_SUCCESS) : 0u;
+          const unsigned id = idx[k];
+          float qf[NJ];
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
-        // finished on the first pass (non-converged: max_iters == 0): rare, and only ever in the flush that such a finish
-        // forces itself (imm) - a warp-uniform branch keeps the 7 predicated-off loads out of every other flush
-        if (any_imm && f && iterations == (conv ? 1 : 0)) {
-          const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
+          for (int i = 0; i < NJ; ++i) qf[i] = Slots<V>::get(q[i], k);
+          if constexpr (decltype(with_reload)::value) {
+            if (f && iterations == (conv ? 1 : 0)) {  // finished on the first pass (non-converged: max_iters == 0); rare
+              const float* qi = kBcast ? a.q_init : a.q_init + (size_t)id * NJ;
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
-        }
-        const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
-        if (kOut == IK_OUT_PACKED) {
-          float* oq = a.q_out + (size_t)id * 8u;
-          stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
-          stg128_if(f, oq + 4, qf[4], qf[5], qf[6], err);
-          stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k), word);
-        } else if (kOut == IK_OUT_COMPACT) {
-          float* oq = a.q_out + (size_t)id * 8u;
-          stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
-          stg128_if(f, oq + 4, qf[4], qf[5], qf[6], word);
-        } else if (f) {
-          float* qo = a.q_out + (size_t)id * NJ;
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
-          if (a.final_pos) {
-            float* fp = a.final_pos + (size_t)id * 3u;
-            fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
+              for (int i = 0; i < NJ; ++i) qf[i] = qi[i];
+            }
           }
-          if (a.pos_err) a.pos_err[id] = err;
-          if (a.iters) a.iters[id] = iterations;
-          if (a.flags) a.flags[id] = (uint8_t)fl;
+          const float word = __int_as_float((int)((unsigned)iterations | (fl << 24)));
+          if (kOut == IK_OUT_PACKED) {
+            float* oq = a.q_out + (size_t)id * 8u;
+            stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
+            stg128_if(f, oq + 4, qf[4], qf[5], qf[6], err);
+            stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k), word);
+          } else if (kOut == IK_OUT_COMPACT) {
+            float* oq = a.q_out + (size_t)id * 8u;
+            stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
+            stg128_if(f, oq + 4, qf[4], qf[5], qf[6], word);
+          } else if (f) {
+            float* qo = a.q_out + (size_t)id * NJ;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
+            if (a.final_pos) {
+              float* fp = a.final_pos + (size_t)id * 3u;
+              fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
+            }
+            if (a.pos_err) a.pos_err[id] = err;
+            if (a.iters) a.iters[id] = iterations;
+            if (a.flags) a.flags[id] = (uint8_t)fl;
+          }
+          c_n += f ? 1u : 0u;
+          c_conv += (f && conv) ? 1u : 0u;
+          c_iter += f ? (unsigned)iterations : 0u;
+          st[k] = f ? (int)IDLE : st[k];
         }
-        c_n += f ? 1u : 0u;
-        c_conv += (f && conv) ? 1u : 0u;
-        c_iter += f ? (unsigned)iterations : 0u;
-        st[k] = f ? (int)IDLE : st[k];
-      }
+      };
+      if (any_imm) store_finished(std::true_type{});
+      else store_finished(std::false_type{});
     }
   }
 

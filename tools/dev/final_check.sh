@@ -1,3 +1,5 @@
+#!/bin/bash
+# everything once on the GPU box: GPU tests, smoke(), the default bench line
 set -u
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q --timeout=900 2>&1 | tail -4
