@@ -192,11 +192,12 @@ __device__ __forceinline__ bool below_thresh(float n2, const IkConst<float>& k) 
 __device__ __forceinline__ double finish_sqrt(double n2) { return sqrt(n2); }
 // sqrt as x * rsqrt(x) on one MUFU.RSQ.  (rsqrtf() wraps the same instruction in a subnormal fix-up - scale by 2^24,
 // MUFU, scale by 2^12 - i.e. three more FMA-pipe instructions per call in the store block, where everything on that pipe
-// queues behind the packed math; squared distances below 1e-30 m^2 are reported as 0.)
+// queues behind the packed math.)  The clamp keeps 0 * rsqrt(0) = 0 * inf out: squared distances below 1e-30 m^2 come
+// back as n2 * 1e15, i.e. as nothing.
 __device__ __forceinline__ float finish_sqrt(float n2) {
   float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));
-  return n2 > 1e-30f ? n2 * r : 0.0f;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(n2, 1e-30f)));
+  return n2 * r;
 }
 
 template <typename T, typename Kin, int kOut>
