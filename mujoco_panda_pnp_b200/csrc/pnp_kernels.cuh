@@ -603,21 +603,23 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
     V p[3], n2, e[3], J[21];
     ik_eval_v<V>(q, tgt, trig, p, e, n2, J);
-    bool any_fin = false, any_run = false, imm = false;
+    // per-slot state update in integer arithmetic (0 / 1 flags): as booleans ptxas ran out of predicate registers and
+    // spilled them through SEL / LOP pairs, ~45 instructions per pass for the two slots
+    int any_fin_i = 0, any_run_i = 0, imm_i = 0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const bool last = it[k] >= a.k.max_iters;                            // loop ran out (ik_solver.py:57)
-      const bool newly = st[k] == RUN && (last || Slots<V>::get(n2, k) < thresh2);   // :61-64
-      const bool stays = st[k] == RUN && !newly;
-      imm = imm || (newly && it[k] == 0);                                  // finished on its first pass
-      it[k] += (stays || (newly && !last)) ? 1 : 0;                        // iterations = i+1 (:66 / :85), then frozen
-      if (newly) {
-        st[k] = last ? FIN_NOCONV : FIN_CONV;
-        Slots<V>::set(slim, k, 0.0f);                                      // freeze: the step below leaves q as it is
-      }
-      any_fin = any_fin || st[k] >= FIN_CONV;
-      any_run = any_run || stays;
+      const int run = st[k] == RUN ? 1 : 0;
+      const int last = it[k] >= a.k.max_iters ? 1 : 0;                           // loop ran out (ik_solver.py:57)
+      const int below = Slots<V>::get(n2, k) < thresh2 ? 1 : 0;                    // :61-64
+      const int newly = run & (last | below);
+      imm_i |= newly & (it[k] == 0 ? 1 : 0);                                       // finished on its first pass
+      it[k] += run & (last ^ 1);                                                   // iterations = i+1 (:66 / :85), then frozen
+      st[k] += newly + (newly & last);                                             // RUN -> FIN_CONV (2) / FIN_NOCONV (3)
+      Slots<V>::set(slim, k, newly ? 0.0f : Slots<V>::get(slim, k));               // freeze: the step below leaves q as it is
+      any_fin_i |= st[k] >> 1;
+      any_run_i |= run & (newly ^ 1);
     }
+    const bool any_fin = any_fin_i != 0, any_run = any_run_i != 0, imm = imm_i != 0;
     ik_step_v<V>(q, J, e, a.k.damping, slim);
     const int n_fin = __popc(__ballot_sync(FULL, any_fin));
     const bool any_imm = __any_sync(FULL, imm);
