@@ -395,6 +395,7 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
   a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.tail = 0; a.guided = 0;
+  a.thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   if constexpr (std::is_same<T, float>::value) {
     // the latency kernel needs no ticket: skip the memset node as well

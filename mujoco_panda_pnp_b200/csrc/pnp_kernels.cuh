@@ -178,6 +178,8 @@ struct IkArgs {
                       // only warp 0 solves (one warp per block spreads a small batch over all SMs)
   unsigned tail;      // ik_solve_v_kernel<F2>: finish the block's last stragglers in the one-query-per-lane latency loop
   unsigned guided;    // ik_solve_v_kernel: 0 = fixed ticket chunks; else a reservation is (queries left) / guided, within [32 S, chunk]
+  T thresh2;          // pos_thresh^2, squared on the host in T: read straight from the constant bank by the per-pass compare
+                      // (computed in the kernel, ptxas re-did the multiply every pass rather than keep it in a register)
 };
 
 // output layouts of the FP32 IK kernels
@@ -477,7 +479,6 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
-  const float thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const int flush_min = (int)a.flush_min;
   const bool tail = S == 2 && a.tail && !a.solo_warp;  // see the tail phase below the loop
   bool pool_dry = false;   // warp-uniform: a lane of this warp has drawn an index past the end of the batch
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     for (int k = 0; k < S; ++k) {
       const int run = st[k] == RUN ? 1 : 0;
       const int last = it[k] >= a.k.max_iters ? 1 : 0;                           // loop ran out (ik_solver.py:57)
-      const int below = Slots<V>::get(n2, k) < thresh2 ? 1 : 0;                    // :61-64
+      const int below = Slots<V>::get(n2, k) < a.thresh2 ? 1 : 0;                    // :61-64
       const int newly = run & (last | below);
       imm_i |= newly & (it[k] == 0 ? 1 : 0);                                       // finished on its first pass
       it[k] += run & (last ^ 1);                                                   // iterations = i+1 (:66 / :85), then frozen
