@@ -29,6 +29,18 @@ std::atomic<unsigned long long> g_launches{0};
 constexpr int kMaxDevices = 16;
 constexpr int kStreamSlots = 64;
 
+// What the previous ik_solve_v_kernel launch of a stream reads and writes, and which of the stream's two tickets the next
+// one takes: the host side of the programmatic-dependent-launch overlap described at IK_PDL_* in pnp_kernels.cuh.
+struct ByteRange {
+  const char* b = nullptr;
+  const char* e = nullptr;
+};
+struct IkPdlState {
+  bool primed = false;      // the previous launch of this stream was an ik_solve_v_kernel that zeroed the ticket `parity`
+  unsigned parity = 0;      // ticket the next launch draws from
+  ByteRange in[2], out[5];  // of the previous launch (valid while primed)
+};
+
 struct DeviceState {
   bool have_tree = false;
   bool specialized = false;
@@ -36,19 +48,21 @@ struct DeviceState {
   int sm_count = 0;
   unsigned* tickets = nullptr;     // kStreamSlots refill tickets
   unsigned* order_work = nullptr;  // kStreamSlots blocks of 2*PLAN_BUCKETS words: plan-order histograms + cursors
+  unsigned* ik_tickets = nullptr;  // kStreamSlots pairs of tickets for ik_solve_v_kernel (consecutive launches alternate)
+  IkPdlState ik_pdl[kStreamSlots];
   cudaStream_t slot_stream[kStreamSlots] = {};
   bool slot_used[kStreamSlots] = {};
   unsigned slot_clock = 0;
   int occ_ik[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool obs_smem_set = false;
   bool fk_smem_set = false;
+  bool plan_smem_set = false;
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
 
-// the scratch slot of `st` on this device (see above)
-int stream_slot(DeviceState* s, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_mu);
+// the scratch slot of `st` on this device (see above); g_mu held by the caller
+int stream_slot_locked(DeviceState* s, cudaStream_t st) {
   for (int i = 0; i < kStreamSlots; ++i)
     if (s->slot_used[i] && s->slot_stream[i] == st) return i;
   int i = 0;
@@ -57,8 +71,14 @@ int stream_slot(DeviceState* s, cudaStream_t st) {
   if (i == kStreamSlots) i = (int)(s->slot_clock++ % kStreamSlots);  // all taken: recycle, oldest assignment first
   s->slot_used[i] = true;
   s->slot_stream[i] = st;
+  s->ik_pdl[i] = IkPdlState{};
   return i;
 }
+int stream_slot(DeviceState* s, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return stream_slot_locked(s, st);
+}
+bool ranges_overlap(const ByteRange& x, const ByteRange& y) { return x.b && y.b && x.b < y.e && y.b < x.e; }
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -335,12 +355,70 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     static const int env_guided = env_int("PNP_IK_GUIDED", 1);
     args.guided = (!small && env_guided != 0) ? (unsigned)(warps * 2) : 0u;
   }
-  if (a.q_init_stride == 0)
-    pnp::ik_solve_v_kernel<V, kOut, true><<<grid, block, 0, st>>>(args);
-  else
-    pnp::ik_solve_v_kernel<V, kOut, false><<<grid, block, 0, st>>>(args);
+  auto kernel = a.q_init_stride == 0 ? pnp::ik_solve_v_kernel<V, kOut, true> : pnp::ik_solve_v_kernel<V, kOut, false>;
+  static const int env_pdl = env_int("PNP_IK_PDL", 1);  // 0: every launch zeroes its ticket with a memset node (measurements)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+  std::lock_guard<std::mutex> lk(g_mu);  // the slot's state changes in the order of the launches on its stream
+  const int sl = stream_slot_locked(s, st);
+  IkPdlState& ps = s->ik_pdl[sl];
+  if (small || !env_pdl || cap != cudaStreamCaptureStatusNone) {
+    // small batches (a launch is one dependent chain: nothing to overlap), captured launches (a replayed node cannot
+    // alternate tickets): the launch zeroes its own ticket, plain stream order
+    args.ticket = s->ik_tickets + 2 * sl;
+    args.ticket_next = nullptr;
+    args.pdl = pnp::IK_PDL_OFF;
+    ps = IkPdlState{};
+    CUDA_TRY(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
+    kernel<<<grid, block, 0, st>>>(args);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return PNP_OK;
+  }
+  // what this launch reads and writes
+  ByteRange in[2], out[5];
+  auto range = [](const void* p, size_t bytes) { ByteRange r; if (p) { r.b = (const char*)p; r.e = r.b + bytes; } return r; };
+  const size_t n = a.n;
+  in[0] = range(a.targets, n * 12);
+  in[1] = range(a.q_init, a.q_init_stride ? n * 28 : 28);
+  if (kOut == pnp::IK_OUT_SEPARATE) {
+    out[0] = range(a.q_out, n * 28); out[1] = range(a.final_pos, n * 12); out[2] = range(a.pos_err, n * 4);
+    out[3] = range(a.iters, n * 4); out[4] = range(a.flags, n);
+  } else {
+    out[0] = range(a.q_out, n * 32);
+    if (kOut == pnp::IK_OUT_PACKED) out[1] = range(a.final_pos, n * 16);
+  }
+  bool clash = false;  // with the previous launch of this stream, which may still be draining when this one starts
+  if (ps.primed) {
+    for (const ByteRange& o : out)
+      for (int k = 0; k < 7; ++k) clash = clash || ranges_overlap(o, k < 2 ? ps.in[k] : ps.out[k - 2]);
+    for (const ByteRange& i : in)
+      for (const ByteRange& po : ps.out) clash = clash || ranges_overlap(i, po);
+  }
+  args.ticket = s->ik_tickets + 2 * sl + ps.parity;
+  args.ticket_next = s->ik_tickets + 2 * sl + (ps.parity ^ 1u);
+  args.pdl = clash ? pnp::IK_PDL_WAIT_FIRST : pnp::IK_PDL_WAIT_AT_DRY;
+  if (!ps.primed) CUDA_TRY(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args);
   ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  if (e != cudaSuccess) {
+    ps = IkPdlState{};
+    return cuda_fail(e, "cudaLaunchKernelEx(ik_solve_v_kernel)");
+  }
+  ps.primed = true;
+  ps.parity ^= 1u;
+  for (int k = 0; k < 2; ++k) ps.in[k] = in[k];
+  for (int k = 0; k < 5; ++k) ps.out[k] = out[k];
   return PNP_OK;
 }
 
@@ -395,6 +473,7 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.k = make_ik_const<T>(params);
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
   a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.tail = 0; a.guided = 0;
+  a.ticket_next = nullptr; a.pdl = 0;
   a.thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   if constexpr (std::is_same<T, float>::value) {
@@ -403,12 +482,13 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
     if (spec && small && env_small && (params->kinematics == PNP_KIN_AUTO || params->kinematics == PNP_KIN_SPECIALIZED))
       return launch_ik_small<kOut>(a, st);
   }
+  if (spec) {
+    if constexpr (std::is_same<T, float>::value) return launch_ik_spec_f32<kOut>(s, a, params->kinematics, small, st);  // own tickets
+  }
   a.ticket = s->tickets + stream_slot(s, st);
   CUDA_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned), st));
   if (spec) {
-    if constexpr (std::is_same<T, float>::value) {
-      return launch_ik_spec_f32<kOut>(s, a, params->kinematics, small, st);
-    } else {
+    if constexpr (!std::is_same<T, float>::value) {
       return launch_ik<T, pnp::SpecKin, kOut>(s, a, small, st);
     }
   }
@@ -527,6 +607,7 @@ int pnp_set_tree(const PnpTree* t) {
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
   if (!s->tickets) {
     CUDA_TRY(cudaMalloc(&s->tickets, kStreamSlots * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&s->ik_tickets, 2 * kStreamSlots * sizeof(unsigned)));
     CUDA_TRY(cudaMalloc(&s->order_work, (size_t)kStreamSlots * 2 * pnp::PLAN_BUCKETS * sizeof(unsigned)));
     // sin(k * 2*pi/8192), k < 8192 + 2048, for the FP32 IK kernels' first-order table trig, evaluated in FP64
     static float tabv[pnp::kTrigVWords];
@@ -713,8 +794,9 @@ int pose_solve_impl(const T* tpos, const T* tquat, const T* q_init, int32_t q_in
 }
 
 template <typename T>
-int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* order, int32_t kinematics, void* stream) {
-  if (n < 0 || (n > 0 && (!q_start || !target || !order))) return fail(PNP_EINVAL, "move_plan_order: null pointer or negative n");
+int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* order, int32_t kinematics, void* stream,
+                    float4* records = nullptr) {
+  if (n < 0 || (n > 0 && (!q_start || !target || (!order && !records)))) return fail(PNP_EINVAL, "move_plan_order: null pointer or negative n");
   DeviceState* s;
   int rc = current_state(&s);
   if (rc) return rc;
@@ -729,10 +811,10 @@ int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* orde
   const int grid = (int)((n + per_block - 1) / per_block);
   if (spec) {
     pnp::plan_order_hist_kernel<T, pnp::SpecKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work);
-    pnp::plan_order_scatter_kernel<T, pnp::SpecKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order);
+    pnp::plan_order_scatter_kernel<T, pnp::SpecKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order, records);
   } else {
     pnp::plan_order_hist_kernel<T, pnp::GenericKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work);
-    pnp::plan_order_scatter_kernel<T, pnp::GenericKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order);
+    pnp::plan_order_scatter_kernel<T, pnp::GenericKin><<<grid, pnp::PLAN_ORDER_BLOCK, 0, st>>>(q_start, target, (unsigned)n, work, order, records);
   }
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
@@ -742,11 +824,20 @@ int plan_order_impl(const T* q_start, const T* target, int64_t n, uint32_t* orde
 template <typename T>
 int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMoveParams* mp, const PnpIkParams* params,
                    T* traj, int32_t* traj_len, T* q_final, int32_t* n_solves, int32_t* status,
-                   unsigned long long* counters, uint32_t* order, void* stream) {
+                   unsigned long long* counters, uint32_t* order, void* stream, float4* records = nullptr) {
   int rc = check_ik_params(params);
   if (rc) return rc;
   if (!mp) return fail(PNP_EINVAL, "move params is NULL");
-  if (order && mp->compute_order) {
+  if (records) {
+    // pnp_move_ik_plan_sorted_f32: `records` is scratch of 48 B per env.  The FP32 value-type planner of the specialised
+    // tree reads its envs from it (filled here, longest plan first); every other kernel takes the same scratch as a
+    // plain order[n]
+    DeviceState* s0;
+    bool spec0;
+    if ((rc = current_state(&s0)) || (rc = pick_kin(s0, params->kinematics, &spec0))) return rc;
+    if (!(std::is_same<T, float>::value && spec0)) { order = reinterpret_cast<uint32_t*>(records); records = nullptr; }
+    if ((rc = plan_order_impl<T>(q_start, target, n, order, params->kinematics, stream, records))) return rc;
+  } else if (order && mp->compute_order) {
     if ((rc = plan_order_impl<T>(q_start, target, n, order, params->kinematics, stream))) return rc;
   }
   if (mp->traj_cap < 2 || mp->max_traj_points < 0 || !(mp->step_size > 0.0) || !(mp->pos_thresh >= 0.0))
@@ -772,17 +863,35 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
   a.traj = traj; a.traj_len = traj_len; a.q_final = q_final; a.n_solves = n_solves; a.status = status;
   a.counters = counters;
   a.order = order;
+  a.records = records;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
-  const int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
+  int block = pnp::IK_BLOCK;  // small: one working warp + three table-loading helper warps per block
   if constexpr (std::is_same<T, float>::value) {
     if (spec) {
       // specialised tree, FP32: the value-type kernels (same arithmetic in both, branch-free common path)
       const bool pair = params->kinematics == PNP_KIN_SPEC_PAIR;
       const int S = pair ? 2 : 1;
+      // PNP_WAYPOINT_FUSE=0 (read per call; tests and measurements only): a separate pass for the first
+      // iteration of every solve, bit-identical results
+      const char* fe = getenv("PNP_WAYPOINT_FUSE");
+      const bool fuse = !fe || atoi(fe) != 0;
+      // trajectory points staged in shared memory, blocks of 160 threads (PNP_PLAN_STAGE=0: direct stores, measurements)
+      static const int env_stage = env_int("PNP_PLAN_STAGE", 1);
+      const bool stage = env_stage && !pair && !small && mp->traj_cap % 4 == 0 && aligned16(traj);
+      if (stage) block = pnp::PLAN_BLOCK;
+      const size_t smem = pnp::plan_smem_bytes(S, block, stage);
+      if (stage && !s->plan_smem_set) {  // 53 KB of dynamic shared memory: above the default 48 KB cap
+        CUDA_TRY(cudaFuncSetAttribute(pnp::move_ik_plan_v_kernel<float, true, pnp::PLAN_BLOCK, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(pnp::move_ik_plan_v_kernel<float, false, pnp::PLAN_BLOCK, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->plan_smem_set = true;
+      }
       int occv = 4;
       if (!small) {
-        cudaError_t e = pair ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<pnp::F2, true>, pnp::IK_BLOCK, 0)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float, true>, pnp::IK_BLOCK, 0);
+        cudaError_t e = pair    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<pnp::F2, true>, block, smem)
+                        : stage ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float, true, pnp::PLAN_BLOCK, true>, block, smem)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occv, pnp::move_ik_plan_v_kernel<float, true>, block, smem);
         if (e != cudaSuccess || occv < 1) occv = 4;
       }
       const long long lanes_needed = (n + S - 1) / S;
@@ -791,14 +900,12 @@ int move_plan_impl(const T* q_start, const T* target, int64_t n, const PnpMovePa
       chunkv = chunkv < 32 * S ? 32 * S : (chunkv > 128 ? 128 : chunkv);
       a.chunk = (unsigned)(chunkv & ~31ll);
       a.solo_warp = small ? 1u : 0u;
-      // PNP_WAYPOINT_FUSE=0 (read per call; tests and measurements only): a separate pass for the first
-      // iteration of every solve, bit-identical results
-      const char* fe = getenv("PNP_WAYPOINT_FUSE");
-      const bool fuse = !fe || atoi(fe) != 0;
-      if (pair && fuse) pnp::move_ik_plan_v_kernel<pnp::F2, true><<<gridv, block, 0, st>>>(a);
-      else if (pair) pnp::move_ik_plan_v_kernel<pnp::F2, false><<<gridv, block, 0, st>>>(a);
-      else if (fuse) pnp::move_ik_plan_v_kernel<float, true><<<gridv, block, 0, st>>>(a);
-      else pnp::move_ik_plan_v_kernel<float, false><<<gridv, block, 0, st>>>(a);
+      if (pair && fuse) pnp::move_ik_plan_v_kernel<pnp::F2, true><<<gridv, block, smem, st>>>(a);
+      else if (pair) pnp::move_ik_plan_v_kernel<pnp::F2, false><<<gridv, block, smem, st>>>(a);
+      else if (stage && fuse) pnp::move_ik_plan_v_kernel<float, true, pnp::PLAN_BLOCK, true><<<gridv, block, smem, st>>>(a);
+      else if (stage) pnp::move_ik_plan_v_kernel<float, false, pnp::PLAN_BLOCK, true><<<gridv, block, smem, st>>>(a);
+      else if (fuse) pnp::move_ik_plan_v_kernel<float, true><<<gridv, block, smem, st>>>(a);
+      else pnp::move_ik_plan_v_kernel<float, false><<<gridv, block, smem, st>>>(a);
       ++g_launches;
       CUDA_TRY(cudaGetLastError());
       return PNP_OK;
@@ -880,6 +987,13 @@ int pnp_move_ik_plan_ordered_f32(const float* q_start, const float* target, uint
                                  void* stream) {
   return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, order,
                                stream);
+}
+int pnp_move_ik_plan_sorted_f32(const float* q_start, const float* target, void* scratch48, int64_t n,
+                                const PnpMoveParams* mp, const PnpIkParams* params, float* traj, int32_t* traj_len,
+                                float* q_final, int32_t* n_solves, int32_t* status, unsigned long long* counters, void* stream) {
+  if (n > 0 && (!scratch48 || !aligned16(scratch48))) return fail(PNP_EINVAL, "move_ik_plan_sorted: scratch must be non-null and 16-byte aligned");
+  return move_plan_impl<float>(q_start, target, n, mp, params, traj, traj_len, q_final, n_solves, status, counters, nullptr,
+                               stream, reinterpret_cast<float4*>(scratch48));
 }
 int pnp_move_ik_plan_f64(const double* q_start, const double* target, int64_t n, const PnpMoveParams* mp,
                          const PnpIkParams* params, double* traj, int32_t* traj_len, double* q_final,

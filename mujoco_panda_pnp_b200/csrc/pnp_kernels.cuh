@@ -180,7 +180,27 @@ struct IkArgs {
   unsigned guided;    // ik_solve_v_kernel: 0 = fixed ticket chunks; else a reservation is (queries left) / guided, within [32 S, chunk]
   T thresh2;          // pos_thresh^2, squared on the host in T: read straight from the constant bank by the per-pass compare
                       // (computed in the kernel, ptxas re-did the multiply every pass rather than keep it in a register)
+  unsigned* ticket_next;  // ik_solve_v_kernel: the ticket of this stream's NEXT launch, zeroed by block 0 (no memset node between
+                          // two launches, so the next one can be a programmatic dependent of this one); nullptr = leave it alone
+  unsigned pdl;       // ik_solve_v_kernel, programmatic dependent launch (see IK_PDL_*)
 };
+
+// Back-to-back launches of ik_solve_v_kernel on one stream overlap the drain of launch k with the ramp of launch k+1
+// (programmatic dependent launch).  A launch's last ~0.09 ms are its drain: the ticket pool is dry and every block waits
+// for a handful of queries on their way to max_iters.  Each block signals `griddepcontrol.launch_dependents` once ALL its
+// warps have seen the pool dry (none of them touches the ticket again), so the next launch's blocks move into the SMs as
+// this launch's blocks leave them.  What keeps that safe:
+//   * the two launches draw from different tickets (the stream's two tickets alternate; block 0 of launch k zeroes the one
+//     launch k+1 will use - launch k-1, its last user, is past its pool by the time launch k starts);
+//   * IK_PDL_WAIT_FIRST: the host found that this launch reads or overwrites something the previous launch on the stream
+//     writes or reads (same output buffers, q_init = the previous q_out, ...): `griddepcontrol.wait` before the first
+//     global access, i.e. plain stream order, nothing overlaps;
+//   * IK_PDL_WAIT_AT_DRY: no such overlap: the wait moves to the point where the block's last warp sees the pool dry,
+//     right before the block's own launch_dependents - by then the previous launch ended long ago, so it costs nothing, and
+//     it bounds the overlap to TWO consecutive launches (launch k+2 cannot start before launch k has completed).
+enum { IK_PDL_OFF = 0, IK_PDL_WAIT_FIRST = 1, IK_PDL_WAIT_AT_DRY = 2 };
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // output layouts of the FP32 IK kernels
 enum { IK_OUT_SEPARATE = 0,  // five arrays (pnp_ik_solve_f32)
@@ -471,10 +491,14 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   __shared__ __align__(16) float s_trig[kTrigVWords];
   __shared__ float2 s_dump[S == 2 ? IK_BLOCK * NJ : 1];            // tail: every thread's q register pairs
   __shared__ unsigned s_list[S == 2 ? IK_TAIL_MAX * 3 : 1];        // tail: query index, pass counter, owner of each parked slot
-  __shared__ unsigned s_list_n, s_live_warps;
-  load_trigv_table(s_trig);
+  __shared__ unsigned s_list_n, s_live_warps, s_dry_warps;
+  load_trigv_table(s_trig);  // (the table is the library's own: nothing a previous launch writes)
+  if (a.pdl == IK_PDL_WAIT_FIRST) griddep_wait();
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
-  if (threadIdx.x == 0) { s_list_n = 0; s_live_warps = IK_BLOCK / 32; }
+  if (threadIdx.x == 0) {
+    s_list_n = 0; s_live_warps = IK_BLOCK / 32; s_dry_warps = 0;
+    if (blockIdx.x == 0 && a.ticket_next) { atomicExch(a.ticket_next, 0u); __threadfence(); }
+  }
   __syncthreads();
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
@@ -513,8 +537,13 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         const unsigned avail = pool_end - pool_next;
         unsigned fresh = 0;
         if (count > avail) {  // warp-uniform
-          if (lane == 0) fresh = atomicAdd(a.ticket, my_chunk);
-          fresh = __shfl_sync(FULL, fresh, 0);
+          if (pool_dry) {
+            fresh = a.n;  // this warp has seen the end of the batch: it never touches the ticket again (the next launch
+                          // of the stream may already have zeroed it for the launch after that, see IK_PDL_*)
+          } else {
+            if (lane == 0) fresh = atomicAdd(a.ticket, my_chunk);
+            fresh = __shfl_sync(FULL, fresh, 0);
+          }
         }
         unsigned before = 0;
         bool ran_out = false;
@@ -557,7 +586,19 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         } else {
           pool_next += count;
         }
-        if (S == 2) pool_dry = pool_dry || __any_sync(FULL, ran_out);
+        if (S == 2 || a.pdl) {
+          const bool dry_now = __any_sync(FULL, ran_out);
+          if (a.pdl && dry_now && !pool_dry) {  // warp-uniform, once per warp: this warp is done with the ticket
+            unsigned before_me = 0;
+            if (lane == 0) before_me = atomicAdd(&s_dry_warps, 1u);
+            before_me = __shfl_sync(FULL, before_me, 0);
+            if (before_me + 1u == (a.solo_warp ? 1u : (unsigned)(IK_BLOCK / 32))) {  // the block's last warp to get here
+              if (a.pdl == IK_PDL_WAIT_AT_DRY) griddep_wait();
+              griddep_launch_dependents();
+            }
+          }
+          pool_dry = pool_dry || dry_now;
+        }
       }
       if (S == 2 && tail && pool_dry) {  // warp-uniform
         // ---- nothing left to take: once this warp is down to a few running slots it parks them and leaves ----------
@@ -1511,6 +1552,9 @@ struct MoveArgs {
   unsigned chunk;   // envs a warp reserves per ticket atomic
   unsigned solo_warp;  // small batches: 4 warps load the trig table, only warp 0 works (see IkArgs)
   const unsigned* order;  // nullable: env taken by the i-th ticket (longest plans first, plan_order_* kernels below)
+  const float4* records;  // nullable (FP32 value-type kernel): the i-th ticket's inputs as one 48-byte record
+                          // {q_start[7], target[3], env, -}, written in plan order by plan_order_scatter_kernel: a refill is
+                          // one sequential read instead of order[i] -> q_start[env], two dependent random ones
 };
 
 // ---- longest plan first ------------------------------------------------------------------------------
@@ -1557,7 +1601,8 @@ __global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_hist_kernel(const
 // order[start(bucket) + rank within bucket] = env; work[PLAN_BUCKETS..2*PLAN_BUCKETS) are the bucket cursors
 template <typename T, typename Kin>
 __global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_scatter_kernel(const T* q_start, const T* target, unsigned n,
-                                                                               unsigned* work, unsigned* order) {
+                                                                               unsigned* work, unsigned* order,
+                                                                               float4* records = nullptr) {
   __shared__ unsigned s_hist[PLAN_BUCKETS], s_cnt[PLAN_BUCKETS], s_base[PLAN_BUCKETS];
   if (threadIdx.x < PLAN_BUCKETS) { s_hist[threadIdx.x] = work[threadIdx.x]; s_cnt[threadIdx.x] = 0; }
   __syncthreads();
@@ -1584,7 +1629,21 @@ __global__ void __launch_bounds__(PLAN_ORDER_BLOCK) plan_order_scatter_kernel(co
 #pragma unroll
   for (int j = 0; j < PLAN_ORDER_PER_THREAD; ++j) {
     const unsigned e = base + j * PLAN_ORDER_BLOCK + threadIdx.x;
-    if (e < n) order[s_base[bucket[j]] + rank[j]] = e;
+    if (e < n) {
+      const unsigned at = s_base[bucket[j]] + rank[j];
+      if (order) order[at] = e;
+      if (records) {  // (rows just read by plan_bucket: L1 / L2 hits)
+        float v[10];
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) v[i] = (float)q_start[(size_t)e * NJ + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[7 + i] = (float)target[(size_t)e * 3 + i];
+        float4* r = records + (size_t)at * 3u;
+        r[0] = make_float4(v[0], v[1], v[2], v[3]);
+        r[1] = make_float4(v[4], v[5], v[6], v[7]);
+        r[2] = make_float4(v[8], v[9], __uint_as_float(e), 0.0f);
+      }
+    }
   }
 }
 
@@ -2045,12 +2104,34 @@ __device__ __forceinline__ void stg1_if(bool pred, float* ptr, float x) {
                :: "r"((unsigned)pred), "l"(ptr), "f"(x) : "memory");
 }
 
-template <typename V, bool kFuse>
-__global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) move_ik_plan_v_kernel(const MoveArgs<float> a) {
+//
+// kStage (one env per lane, blocks of PLAN_BLOCK = 160 threads, 4 per SM - the same 20 warps as 5 blocks of 128, with
+// 12 KB of shared memory per block to spare): the trajectory point of an accepted solve - one per lane on nearly every
+// pass - goes into a 4-point (48-byte) row of shared memory and leaves as three 128-bit stores once the row is full.
+// Written straight to global memory the three 4-byte stores of a pass hit 32 different 128-byte lines each: 96 L1
+// wavefronts per warp pass, 1.5x the algorithmic DRAM bytes in partial-sector write-backs, and 31 % of the launch
+// (measured with the appends predicated off).  The last 1-3 points of an env and its final goal point are stored
+// directly, once per env.  Needs traj_cap % 4 == 0 and a 16-byte aligned trajectory buffer (the host checks).
+constexpr int PLAN_BLOCK = 160;
+constexpr int PLAN_STAGE_PTS = 4;
+constexpr size_t plan_smem_bytes(int slots, int block, bool stage) {
+  return sizeof(float) * ((size_t)kTrigVWords + (size_t)slots * NJ * block + (stage ? (size_t)block * PLAN_STAGE_PTS * 3 : 0));
+}
+__device__ __forceinline__ void sts1_if(bool pred, float* ptr, float x) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.f32 [%1], %2;\n\t}"
+               :: "r"((unsigned)pred), "r"((unsigned)__cvta_generic_to_shared(ptr)), "f"(x) : "memory");
+}
+
+template <typename V, bool kFuse, int kBlock = IK_BLOCK, bool kStage = false>
+__global__ void __launch_bounds__(kBlock, (Slots<V>::kN == 2 || kBlock == PLAN_BLOCK) ? IK_PAIR_MIN_BLOCKS : 5) move_ik_plan_v_kernel(const MoveArgs<float> a) {
   constexpr int S = Slots<V>::kN;
+  static_assert(!kStage || S == 1, "trajectory staging is written for one env per lane");
   const unsigned lane = threadIdx.x & 31u;
-  __shared__ __align__(16) float s_trig[kTrigVWords];
-  __shared__ float s_qa[S * NJ * IK_BLOCK];  // q_current of every slot: [(k * NJ + i) * IK_BLOCK + thread]
+  // dynamic shared memory (the staged variant needs 53 KB, above the 48 KB a kernel may declare statically): plan_smem_bytes()
+  extern __shared__ __align__(16) unsigned char plan_smem[];
+  float* const s_trig = reinterpret_cast<float*>(plan_smem);
+  float* const s_qa = s_trig + kTrigVWords;       // q_current of every slot: [(k * NJ + i) * kBlock + thread]
+  float* const s_pts = s_qa + S * NJ * kBlock;    // kStage: [thread][point][xyz] (16-byte aligned: every term is a multiple of 16 B)
   load_trigv_table(s_trig);
   __syncthreads();
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
@@ -2075,7 +2156,27 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   for (int k = 0; k < S; ++k) {
     state[k] = IDLE; it[k] = len[k] = solves[k] = st[k] = point_count[k] = cf[k] = outer[k] = 0; astep[k] = 0.0f; env[k] = 0;
   }
-  // traj[len] = point (move.py:98,135,157,173,191), predicated; beyond traj_cap the point is dropped (status bit 4)
+  int staged = 0, gbase = 0;  // kStage: points of this lane's env waiting in s_pts / already in global memory
+  float* const my_pts = s_pts + (kStage ? threadIdx.x * (PLAN_STAGE_PTS * 3) : 0);
+  // the point of an accepted solve (move.py:98,135,157,173): staged (kStage) or stored like the others
+  auto append_take = [&](bool pred, int k, float x, float y, float z) {
+    const bool room = len[k] < a.traj_cap;
+    if (kStage) {
+      float* sp = my_pts + staged * 3;
+      sts1_if(pred && room, sp, x);
+      sts1_if(pred && room, sp + 1, y);
+      sts1_if(pred && room, sp + 2, z);
+      staged += (pred && room) ? 1 : 0;
+    } else {
+      float* t = a.traj + ((size_t)env[k] * a.traj_cap + (room ? len[k] : 0)) * 3;
+      stg1_if(pred && room, t, x);
+      stg1_if(pred && room, t + 1, y);
+      stg1_if(pred && room, t + 2, z);
+    }
+    st[k] |= (pred && !room) ? 4 : 0;
+    len[k] += pred ? 1 : 0;
+  };
+  // traj[len] = point (move.py:191 and the failure exits), predicated; beyond traj_cap the point is dropped (status bit 4)
   auto append_if = [&](bool pred, int k, float x, float y, float z) {
     const bool room = len[k] < a.traj_cap;
     float* t = a.traj + ((size_t)env[k] * a.traj_cap + (room ? len[k] : 0)) * 3;
@@ -2092,8 +2193,13 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     for (int k = 0; k < S; ++k) {
       if (state[k] == DONE) {
         const unsigned id = env[k];
+        if (kStage) {  // the env's last 1-3 staged points (a full row left at the end of its pass)
+          float* t = a.traj + ((size_t)id * a.traj_cap + gbase) * 3;
+          for (int w = 0; w < staged * 3; ++w) t[w] = my_pts[w];
+          staged = 0; gbase = 0;
+        }
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) a.q_final[(size_t)id * NJ + i] = qa[(k * NJ + i) * IK_BLOCK];
+        for (int i = 0; i < NJ; ++i) a.q_final[(size_t)id * NJ + i] = qa[(k * NJ + i) * kBlock];
         a.traj_len[id] = len[k];
         if (a.n_solves) a.n_solves[id] = solves[k];
         if (a.status) a.status[id] = st[k];
@@ -2121,17 +2227,31 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
           if (id < a.n) {
-            const unsigned e = a.order ? a.order[id] : id;
+            float rec[12];
+            unsigned e;
+            if (a.records) {  // warp-uniform
+              const float4 r0 = a.records[(size_t)id * 3u], r1 = a.records[(size_t)id * 3u + 1], r2 = a.records[(size_t)id * 3u + 2];
+              rec[0] = r0.x; rec[1] = r0.y; rec[2] = r0.z; rec[3] = r0.w; rec[4] = r1.x; rec[5] = r1.y; rec[6] = r1.z;
+              rec[7] = r1.w; rec[8] = r2.x; rec[9] = r2.y;
+              e = __float_as_uint(r2.z);
+            } else {
+              e = a.order ? a.order[id] : id;
+              if (e < a.n) {
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) rec[i] = a.q_start[(size_t)e * NJ + i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) rec[7 + i] = a.target[(size_t)e * 3 + i];
+              }
+            }
             if (e < a.n) {  // an out-of-range entry of a caller-made order is skipped: nothing is read or written for it
               env[k] = e;
 #pragma unroll
               for (int i = 0; i < NJ; ++i) {
-                const float v = a.q_start[(size_t)e * NJ + i];
-                Slots<V>::set(qs[i], k, v);
-                qa[(k * NJ + i) * IK_BLOCK] = v;
+                Slots<V>::set(qs[i], k, rec[i]);
+                qa[(k * NJ + i) * kBlock] = rec[i];
               }
 #pragma unroll
-              for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, a.target[(size_t)e * 3 + i]);
+              for (int i = 0; i < 3; ++i) Slots<V>::set(goal[i], k, rec[7 + i]);
               len[k] = 0; solves[k] = 0; st[k] = 0; point_count[k] = 0; cf[k] = 0; outer[k] = 0; astep[k] = 0.0f; it[k] = 0;
               state[k] = INIT;
             }
@@ -2182,12 +2302,12 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       solves[k] += f ? 1 : 0;
       c_n += f ? 1u : 0u; c_conv += (f && conv) ? 1u : 0u; c_iter += f ? (unsigned)iters : 0u;
       const float px = Slots<V>::get(p[0], k), py = Slots<V>::get(p[1], k), pz = Slots<V>::get(p[2], k);
-      append_if(take, k, px, py, pz);
+      append_take(take, k, px, py, pz);
       if (take) { Slots<V>::set(pos[0], k, px); Slots<V>::set(pos[1], k, py); Slots<V>::set(pos[2], k, pz); }
       const bool keep = acc && it[k] > 0;  // q_current = result.q
       if (keep) {
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) qa[(k * NJ + i) * IK_BLOCK] = Slots<V>::get(qs[i], k);
+        for (int i = 0; i < NJ; ++i) qa[(k * NJ + i) * kBlock] = Slots<V>::get(qs[i], k);
       }
       // rejected: the next solve restarts from q_current; INIT / accepted on the first pass: q_current itself
       // (reloaded: the frozen limit clip may have moved an out-of-limits q_start)
@@ -2195,7 +2315,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       fused[k] = take;
       if (!kFuse && reload[k]) {
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
+        for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * kBlock]);
       }
       point_count[k] += (acc && state[k] == NORMAL) ? 1 : 0;                          // :186 (fallbacks `continue`)
       cf[k] = take ? 0 : cf[k];
@@ -2282,6 +2402,17 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         }
       }
     }
+    if (kStage) {  // a full row of four points leaves as three 128-bit stores (16-byte aligned: see the host checks)
+      const bool full = staged == PLAN_STAGE_PTS;
+      const float4* row = reinterpret_cast<const float4*>(my_pts);
+      const float4 c0 = row[0], c1 = row[1], c2 = row[2];
+      float* t = a.traj + ((size_t)env[0] * a.traj_cap + gbase) * 3;
+      stg128_if(full, t, c0.x, c0.y, c0.z, c0.w);
+      stg128_if(full, t + 4, c1.x, c1.y, c1.z, c1.w);
+      stg128_if(full, t + 8, c2.x, c2.y, c2.z, c2.w);
+      gbase += full ? PLAN_STAGE_PTS : 0;
+      staged = full ? 0 : staged;
+    }
     if (kFuse) {
       // error of the new targets at this pass's p: what the first pass of the next solve would compute
       V en[3];
@@ -2303,7 +2434,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       for (int k = 0; k < S; ++k) {
         if (reload[k] && !fused[k]) {
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * IK_BLOCK]);
+          for (int i = 0; i < NJ; ++i) Slots<V>::set(qs[i], k, qa[(k * NJ + i) * kBlock]);
         }
       }
     }

@@ -413,6 +413,18 @@ def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParam
         if order != "auto":
             raise ValueError("order must be 'auto', None or a tensor from move_plan_order")
         order = None
+        if n >= PLAN_ORDER_MIN and dt == torch.float32:
+            # longest plan first with gathered inputs: 48 B of scratch per env for the call to fill and read
+            scratch = out.get("_scratch48") if out is not None else None
+            if scratch is None or scratch.shape != (n, 12) or scratch.device != dev:
+                scratch = torch.empty((n, 12), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(
+                    lib.pnp_move_ik_plan_sorted_f32(_ptr(q_start), _ptr(target), _ptr(scratch), n, ctypes.byref(mp), ctypes.byref(params),
+                                                    _ptr(traj), _ptr(tlen), _ptr(qf), _ptr(solves), _ptr(status), _ptr(counters), _stream()),
+                    "pnp_move_ik_plan_sorted",
+                )
+            return dict(traj=traj, traj_len=tlen, q_final=qf, n_solves=solves, status=status, _scratch48=scratch)
         if n >= PLAN_ORDER_MIN:  # scratch for the call to fill and use (PnpMoveParams.compute_order)
             order = torch.empty((n,), dtype=torch.int32, device=dev)
             mp.compute_order = 1

@@ -147,3 +147,28 @@ def reachable_move_envs(n: int, lower, upper, seed: int = 0, device="cpu", dtype
     lo = torch.as_tensor(lower, dtype=f64, device=device)
     hi = torch.as_tensor(upper, dtype=f64, device=device)
     return dict(q_start=q0.to(dtype).contiguous(), q_goal=torch.minimum(torch.maximum(qs, lo), hi).to(dtype).contiguous())
+
+
+def her_future_indices(n: int, episode_len: int = 300, seed: int = 0, device="cpu", keep_fraction: float = 0.2,
+                       strategy: str = "future") -> torch.Tensor:
+    """int32[n] `future_idx` of a HER relabel over a replay buffer that stores its episodes as runs of ``episode_len``
+    consecutive transitions (300 = the reference's max_episode_steps, panda_mujoco_gym/__init__.py:15).
+
+    ``future``  (SB3 GoalSelectionStrategy.FUTURE, the default of HerReplayBuffer): the goal of transition t of an episode
+                is the achieved goal of a transition drawn uniformly from [t, T-1] of the SAME episode;
+    ``uniform`` any transition of the buffer (no locality at all: the worst case for the gather).
+    A fraction ``keep_fraction`` of the rows keeps the stored goal (index -1; n_sampled_goal = 4 -> 1 in 5)."""
+    g = _gen(seed, device)
+    idx = torch.arange(n, device=device, dtype=torch.int64)
+    if strategy == "future":
+        t = idx % episode_len
+        last = torch.clamp(idx - t + (episode_len - 1), max=n - 1)            # last transition of the episode
+        span = (last - idx + 1).to(torch.float64)
+        fut = idx + torch.clamp((torch.rand(n, generator=g, device=device, dtype=torch.float64) * span).long(), max=episode_len - 1)
+        fut = torch.minimum(fut, last)
+    elif strategy == "uniform":
+        fut = torch.randint(0, max(n, 1), (n,), generator=g, device=device, dtype=torch.int64)
+    else:
+        raise ValueError("strategy must be 'future' or 'uniform'")
+    keep = torch.rand(n, generator=g, device=device) < keep_fraction
+    return torch.where(keep, torch.full_like(fut, -1), fut).to(torch.int32)

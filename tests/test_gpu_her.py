@@ -126,3 +126,19 @@ def test_relabel_from_goal_table_is_identical(cuda_lib, n):
             assert torch.equal(u.view(torch.int32), v.view(torch.int32))
     with pytest.raises(ValueError):
         engine.her_relabel(obs, nxt, fut, quat, task, engine.reward_params("dense"), future_ag=table[:-1])
+
+
+@pytest.mark.parametrize("episode_len", [50, 300])
+def test_relabel_future_strategy_episode_indices(cuda_lib, episode_len):
+    """The bench's headline HER workload: goals from a later transition of the same episode (synthetic.her_future_indices).
+    Bit-exact against the oracle on a sample that spans several tiles and a ragged last episode."""
+    n = 5 * 300 + 77
+    obs, nxt, _, quat, task = _transitions(n, seed=21)
+    fut = synthetic.her_future_indices(n, episode_len, seed=4, device="cuda", strategy="future")
+    o, x, r, s = engine.her_relabel(obs, nxt, fut, quat, task, engine.reward_params("dense"))
+    wo, wx, wr, ws = her_oracle.relabel(obs.cpu().numpy(), nxt.cpu().numpy(), fut.cpu().numpy(), quat.cpu().numpy(),
+                                        task.cpu().numpy(), reward_type="dense")
+    np.testing.assert_array_equal(_bits(o.cpu().numpy()), _bits(wo))
+    np.testing.assert_array_equal(_bits(x.cpu().numpy()), _bits(wx))
+    np.testing.assert_array_equal(_bits(r.cpu().numpy()), _bits(wr))
+    np.testing.assert_array_equal(s.cpu().numpy(), ws)

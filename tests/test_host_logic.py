@@ -91,3 +91,21 @@ def test_synthetic_generators_are_deterministic_and_stratified():
     assert q.shape == (100, 7) and float(q.abs().max()) <= 1.0
     w = synthetic.waypoint_envs(10, seed=2)
     assert w["q_start"].shape == (10, 7) and w["goal"].shape == (10, 3)
+
+
+def test_her_future_indices_stay_inside_their_episode():
+    """synthetic.her_future_indices('future'): index -1 (keep) or a transition of the same episode, not before the row."""
+    import torch
+    from mujoco_panda_pnp_b200 import synthetic
+
+    for n, T in ((10_000, 300), (1000, 50), (7, 300)):
+        fut = synthetic.her_future_indices(n, T, seed=3, strategy="future").long()
+        idx = torch.arange(n)
+        rel = fut >= 0
+        assert 0.1 < float((~rel).float().mean()) < 0.35 or n < 100
+        assert bool((fut[rel] >= idx[rel]).all()) and bool((fut[rel] < n).all())
+        assert bool(((fut[rel] // T) == (idx[rel] // T)).all())
+        assert torch.equal(fut, synthetic.her_future_indices(n, T, seed=3, strategy="future").long())
+    uni = synthetic.her_future_indices(10_000, 300, seed=3, strategy="uniform").long()
+    assert int(uni.max()) < 10_000 and int(uni.min()) == -1
+    assert float(((uni // 300) == (torch.arange(10_000) // 300))[uni >= 0].float().mean()) < 0.1
