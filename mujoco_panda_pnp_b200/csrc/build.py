@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call([sys.executable, gen])
     if not force and up_to_date():
         return OUT
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", OUT, *SOURCES]
+    extra = os.environ.get("PNP_NVCC_EXTRA", "").split()  # development: -D switches of kernel variants
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", OUT, *SOURCES]
     res = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:

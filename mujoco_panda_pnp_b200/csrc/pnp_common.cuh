@@ -74,8 +74,8 @@ struct Trig<float> {
     const float t = fmaf(x, 1303.7972412109375f, 12582912.0f);
     const int ji = __float_as_int(t) & (kTrigVN - 1);
     const float k = t + (-12582912.0f);
-    float r = fmaf(k, -7.669904152862728e-4f, x);
-    r = fmaf(k, 2.1343451311883754e-11f, r);
+    const float r = fmaf(k, -7.669904152862728e-4f, x);  // |k| <= 4900 inside the joint range: the rounding of the constant
+                                                           // (2.1e-11) moves r by < 1.1e-7 rad - no second reduction term
     const float es = tab[ji], ec = tab[ji + kTrigVN / 4];
     *s = fmaf(ec, r, es);
     *c = fmaf(-es, r, ec);
@@ -370,8 +370,8 @@ struct TrigV {
     const float t = fmaf(x, 1303.7972412109375f, 12582912.0f);
     const int ji = __float_as_int(t) & (kTrigVN - 1);
     const float k = t + (-12582912.0f);
-    float r = fmaf(k, -7.669904152862728e-4f, x);
-    r = fmaf(k, 2.1343451311883754e-11f, r);
+    const float r = fmaf(k, -7.669904152862728e-4f, x);  // |k| <= 4900 inside the joint range: the rounding of the constant
+                                                           // (2.1e-11) moves r by < 1.1e-7 rad - no second reduction term
     const float es = tab[ji], ec = tab[ji + kTrigVN / 4];
     *s = fmaf(ec, r, es);
     *c = fmaf(-es, r, ec);
@@ -381,8 +381,7 @@ struct TrigV {
     const P t = pnp_fma(x, P(1303.7972412109375f), P(12582912.0f));
     const int ja = __float_as_int(t.v.x) & (kTrigVN - 1), jb = __float_as_int(t.v.y) & (kTrigVN - 1);
     const P k = pnp_add(t, P(-12582912.0f));
-    P r = pnp_fma(k, P(-7.669904152862728e-4f), x);
-    r = pnp_fma(k, P(2.1343451311883754e-11f), r);
+    const P r = pnp_fma(k, P(-7.669904152862728e-4f), x);
     const P es(tab[ja], tab[jb]), ec(tab[ja + kTrigVN / 4], tab[jb + kTrigVN / 4]);
     *s = pnp_fma(ec, r, es);
     *c = pnp_fma(pnp_neg(es), r, ec);
@@ -411,9 +410,8 @@ template <typename V>
 __device__ __forceinline__ void ik_step_v(V (&q)[NJ], const V (&J)[21], const V (&e)[3], float damping,
                                           const V& slim) {  // q is updated in place
   V A[6];
-  pnp_spec::spec_jjt_v<V>(J, A);
-  const V lam(damping);
-  const V a00 = pnp_add(A[0], lam), a11 = pnp_add(A[3], lam), a22 = pnp_add(A[5], lam);
+  pnp_spec::spec_jjt_damped_v<V>(J, V(damping), A);  // J J^T + damping I (:76-77; damping is the start value of the diagonal sums)
+  const V a00 = A[0], a11 = A[3], a22 = A[5];
   const V i0 = v_rcp(a00);
   const V l10 = pnp_mul(A[1], i0), l20 = pnp_mul(A[2], i0);
   const V d1 = pnp_fma(pnp_neg(l10), A[1], a11);

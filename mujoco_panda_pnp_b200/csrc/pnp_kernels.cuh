@@ -478,8 +478,11 @@ __device__ __forceinline__ void store_lane_result(const IkArgs<float>& a, unsign
 // (First attempt, dropped: the last warp took the list back into its 64 slots through the refill code.  No gain -
 // a lone two-queries-per-lane warp needs ~1000 clocks per pass, and a refill that can also read the list put 40
 // predicated instructions more into every flush.)
-constexpr int IK_TAIL_PER_WARP = 8;                          // a warp parks once it is down to this many running slots
-constexpr int IK_TAIL_MAX = (IK_BLOCK / 32) * IK_TAIL_PER_WARP;  // = 32: the block's stragglers fit one warp, one per lane
+#ifndef IK_TAIL_PER_WARP_N
+#define IK_TAIL_PER_WARP_N 8
+#endif
+constexpr int IK_TAIL_PER_WARP = IK_TAIL_PER_WARP_N;         // a warp parks once it is down to this many running slots
+constexpr int IK_TAIL_MAX = (IK_BLOCK / 32) * IK_TAIL_PER_WARP;  // the block's stragglers: one per lane, 32 at a time
 __device__ __forceinline__ float2 pair_of(float v) { return make_float2(v, 0.0f); }
 __device__ __forceinline__ float2 pair_of(const F2& v) { return v.v; }
 
@@ -740,10 +743,10 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     //      way to max_iters - finish here, one per lane, in the latency loop of the small-batch kernel: ~500 clocks
     //      per pass for a lone warp, where four straggler warps sharing a scheduler needed ~2000 per round. -----------
     __threadfence_block();
-    const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&s_list_n);  // <= 4 warps x IK_TAIL_PER_WARP = 32
-    if (cnt) {
-      const bool valid = lane < cnt;
-      const unsigned* e = s_list + (valid ? lane : 0u) * 3u;
+    const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&s_list_n);  // <= 4 warps x IK_TAIL_PER_WARP
+    for (unsigned base = 0; base < cnt; base += 32u) {
+      const bool valid = base + lane < cnt;
+      const unsigned* e = s_list + (valid ? base + lane : 0u) * 3u;
       const unsigned id = e[0], who = e[2];
       const int it0 = (int)e[1];
       const float* src = reinterpret_cast<const float*>(s_dump + (size_t)(who >> 1) * NJ) + (who & 1u);

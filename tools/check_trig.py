@@ -42,6 +42,9 @@ INVV = f32(NV / (2 * np.pi))
 TABV = np.sin(np.arange(NV + NV // 4) * DV).astype(f32)
 
 
+TWO_TERM = False
+
+
 def sincos_tabv(x):
     x = x.astype(f32)
     full = lambda v: np.full_like(x, f32(v))  # noqa: E731
@@ -50,7 +53,8 @@ def sincos_tabv(x):
     ji = t.view(np.int32) & (NV - 1)
     k = (t - mag).astype(f32)
     r = fma(k, full(-DV_HI), x)
-    r = fma(k, full(-DV_LO), r)
+    if TWO_TERM:  # rounds 1 and 2 of the build: a second Cody-Waite term (one more packed instruction per joint and pass)
+        r = fma(k, full(-DV_LO), r)
     sk, ck = TABV[ji], TABV[ji + NV // 4]
     return fma(ck, r, sk), fma(-sk, r, ck)
 
@@ -69,4 +73,6 @@ if __name__ == "__main__":
     print(f"first session: INV={INV:.9g} D_HI={D_HI:.17g} D_LO={D_LO:.17g}")
     report("first session (1024, 2nd order)", sincos_tab, (4.0, 100.0, 1e4, 2.5e4))
     print(f"Trig<float> / TrigV: INV={INVV:.17g} D_HI={DV_HI:.17g} -D_LO={-DV_LO:.17g}")
-    report("Trig<float>/TrigV (8192, 1st order)", sincos_tabv, (4.0, 100.0, 1e3, 3.2e3))
+    report("Trig<float>/TrigV (8192, 1st order, one-term reduction)", sincos_tabv, (3.8, 6.3, 100.0, 1e3))
+    TWO_TERM = True
+    report("same with the second reduction term (until round 2)", sincos_tabv, (3.8, 100.0, 1e3, 3.2e3))

@@ -377,6 +377,25 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
     for k in range(6):
         jjt.append(f"  A[{k}] = {'a%d' % k if started[k] else 'T(0.0)'};")
     jjt.append("}")
+    # A = Jp Jp^T + lam I with lam as the start value of the three diagonal sums (one FMA instead of a multiply and,
+    # later, an add per diagonal entry: three packed instructions fewer per DLS pass)
+    jjt.append("template <typename T>\n__device__ __forceinline__ void spec_jjt_damped_v(const T* __restrict__ J, const T lam, T* __restrict__ A) {")
+    started = [False] * 6
+    for j in range(7):
+        for k, (r, s_) in enumerate(pairs):
+            if jp_zero[r, j] or jp_zero[s_, j]:
+                continue
+            a_, b_ = f"J[{r * 7 + j}]", f"J[{s_ * 7 + j}]"
+            if started[k]:
+                jjt.append(f"  a{k} = pnp_fma({a_}, {b_}, a{k});")
+            elif r == s_:
+                jjt.append(f"  T a{k} = pnp_fma({a_}, {b_}, lam);")
+            else:
+                jjt.append(f"  T a{k} = pnp_mul({a_}, {b_});")
+            started[k] = True
+    for k, (r, s_) in enumerate(pairs):
+        jjt.append(f"  A[{k}] = {'a%d' % k if started[k] else ('lam' if r == s_ else 'T(0.0)')};")
+    jjt.append("}")
     jty = ["template <typename T>\n__device__ __forceinline__ void spec_jty(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {"]
     flops_jty = 0
     for j in range(7):
