@@ -389,28 +389,69 @@ struct TrigV {
 };
 
 // Split in two so that a kernel can decide between the halves (from n2) whether a slot takes the step:
-//   ik_eval_v : p = FK(q), J = jacp, e = target - p, n2 = |e|^2          (ik_solver.py:58-61, 70-72)
-//   ik_step_v : qn = clip(q + clip(J^T (J J^T + damping I)^-1 e, +-slim), lower, upper)   (:78-81)
+//   ik_eval_*  : p = FK(q), J = jacp, e = target - p, n2 = |e|^2          (ik_solver.py:58-61, 70-72)
+//   ik_step_v  : qn = clip(q + clip(J^T (J J^T + damping I)^-1 e, +-slim), lower, upper)   (:78-81)
 // slim is per slot: step_limit for a running query, 0 to freeze a finished one (qn == q).
+//
+// The frame of the evaluation.  J^T (J J^T + damping I)^-1 e and |e| do not depend on the frame J and e are written in, as
+// long as they share it, and in the frame that JOINT 1 CARRIES (A_0 Rz(q_1) of the canonical chain) the first joint's
+// rotation drops out of every product down the chain: FK + Jp is 85 operations instead of 107 (Panda), Jp has one more
+// structural zero (3 operations off J J^T, 1 off J^T y), and what it costs is the rotation of the target into that frame,
+// 4 operations per pass - 22 of 215 packed instructions per pass of the two-queries-per-lane kernel.  So:
+//   tb          the target in the frame of joint 1's parent (spec_world_to_base_v: a constant rigid transform, once per query)
+//   ik_eval_j1_v  everything in joint 1's frame: pr = FK there, J, e = Rz(-q_1) tb - pr; returns sin / cos of joint 1 too
+//   p_world_v   pr back in the world frame (final_pos: only when a query is stored)
+//   ik_eval_v   world-frame target in, world-frame p out (e and J are in joint 1's frame all the same)
+// Every FP32 kernel on the specialised tree goes through ik_eval_j1_v, so they stay bit-identical to each other.
+// e = Rz(-q_1) tb - pr and |e|^2: the error of a target (frame of joint 1's parent) at a position in joint 1's frame.
+// Also what the fused waypoint / planner passes call for the NEXT solve's target at this pass's pr (same operations as
+// the evaluation that solve's own first pass would do: bit-identical).
 template <typename V>
-__device__ __forceinline__ void ik_eval_v(const V (&q)[NJ], const V (&tgt)[3], const TrigV& trig, V (&p)[3],
-                                          V (&e)[3], V& n2, V (&J)[21]) {
+__device__ __forceinline__ void target_err_j1_v(const V (&tb)[3], const V (&pr)[3], const V& s0, const V& c0, V (&e)[3], V& n2) {
+  const V trx = pnp_fma(c0, tb[0], pnp_mul(s0, tb[1]));            // Rz(-q_1) tb
+  const V try_ = pnp_fma(c0, tb[1], pnp_mul(pnp_neg(s0), tb[0]));
+  e[0] = v_sub(trx, pr[0]); e[1] = v_sub(try_, pr[1]); e[2] = v_sub(tb[2], pr[2]);
+  n2 = pnp_fma(e[2], e[2], pnp_fma(e[1], e[1], pnp_mul(e[0], e[0])));
+}
+
+template <typename V>
+__device__ __forceinline__ void ik_eval_j1_v(const V (&q)[NJ], const V (&tb)[3], const TrigV& trig, V (&pr)[3],
+                                             V (&e)[3], V& n2, V (&J)[21], V& s0, V& c0) {
   V s[NJ], c[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     const float qr = pnp_spec::spec_qref<float>(i);
     trig(qr != 0.0f ? pnp_add(q[i], V(-qr)) : q[i], &s[i], &c[i]);
   }
-  pnp_spec::spec_fk_jacp_v<V>(s, c, p, J);
-  e[0] = v_sub(tgt[0], p[0]); e[1] = v_sub(tgt[1], p[1]); e[2] = v_sub(tgt[2], p[2]);
-  n2 = pnp_fma(e[2], e[2], pnp_fma(e[1], e[1], pnp_mul(e[0], e[0])));
+  pnp_spec::spec_fk_jacp_j1_v<V>(s, c, pr, J);
+  s0 = s[0]; c0 = c[0];
+  target_err_j1_v<V>(tb, pr, s0, c0, e, n2);
+}
+
+// joint-1-frame position -> world (A_0.pos + A_0.rot Rz(q_1) pr)
+template <typename V>
+__device__ __forceinline__ void p_world_v(const V (&pr)[3], const V& s0, const V& c0, V (&pw)[3]) {
+  V pb[3];
+  pb[0] = pnp_fma(c0, pr[0], pnp_mul(pnp_neg(s0), pr[1]));
+  pb[1] = pnp_fma(s0, pr[0], pnp_mul(c0, pr[1]));
+  pb[2] = pr[2];
+  pnp_spec::spec_base_to_world_v<V>(pb, pw);
+}
+
+template <typename V>
+__device__ __forceinline__ void ik_eval_v(const V (&q)[NJ], const V (&tgt)[3], const TrigV& trig, V (&p)[3],
+                                          V (&e)[3], V& n2, V (&J)[21], V& s0, V& c0) {
+  V tb[3], pr[3];
+  pnp_spec::spec_world_to_base_v<V>(tgt, tb);
+  ik_eval_j1_v<V>(q, tb, trig, pr, e, n2, J, s0, c0);
+  p_world_v<V>(pr, s0, c0, p);
 }
 
 template <typename V>
 __device__ __forceinline__ void ik_step_v(V (&q)[NJ], const V (&J)[21], const V (&e)[3], float damping,
                                           const V& slim) {  // q is updated in place
   V A[6];
-  pnp_spec::spec_jjt_damped_v<V>(J, V(damping), A);  // J J^T + damping I (:76-77; damping is the start value of the diagonal sums)
+  pnp_spec::spec_jjt_damped_j1_v<V>(J, V(damping), A);  // J J^T + damping I (:76-77; damping is the start value of the diagonal sums)
   const V a00 = A[0], a11 = A[3], a22 = A[5];
   const V i0 = v_rcp(a00);
   const V l10 = pnp_mul(A[1], i0), l20 = pnp_mul(A[2], i0);
@@ -427,7 +468,7 @@ __device__ __forceinline__ void ik_step_v(V (&q)[NJ], const V (&J)[21], const V 
   y[1] = pnp_fma(pnp_neg(l21), y[2], pnp_mul(z1, i1));
   y[0] = pnp_fma(pnp_neg(l20), y[2], pnp_fma(pnp_neg(l10), y[1], pnp_mul(e[0], i0)));
   V dq[NJ];
-  pnp_spec::spec_jty_v<V>(J, y, dq);
+  pnp_spec::spec_jty_j1_v<V>(J, y, dq);
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     // a joint whose Jacobian column is structurally zero (joint 7: the EE site lies on its axis) has

@@ -408,22 +408,25 @@ __device__ __forceinline__ void lane_solve(const IkConst<float>& k, const TrigV&
   bool done = !valid;
   conv = false;
   iterations = 0;
-  pf[0] = pf[1] = pf[2] = 0.0f;
+  float pr_f[3] = {0.0f, 0.0f, 0.0f}, s0_f = 0.0f, c0_f = 1.0f;  // final position in joint 1's frame, and that joint's sin / cos
   n2f = 0.0f;
+  float tb[3];
+  pnp_spec::spec_world_to_base_v<float>(tgt, tb);
   for (;; ++it) {
-    float p[3], e[3], n2, J[21];
-    ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
+    float p[3], e[3], n2, J[21], s0, c0;
+    ik_eval_j1_v<float>(q, tb, trig, p, e, n2, J, s0, c0);
     const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
     const bool fin = !done && (last || n2 < thresh2);          // :61-64
     if (fin) {
       conv = !last;
       iterations = conv ? it + 1 : it;                         // :66 / :85
-      pf[0] = p[0]; pf[1] = p[1]; pf[2] = p[2]; n2f = n2;      // final_pos / final_error (:88-89)
+      pr_f[0] = p[0]; pr_f[1] = p[1]; pr_f[2] = p[2]; s0_f = s0; c0_f = c0; n2f = n2;  // final_pos / final_error (:88-89)
     }
     done = done || fin;
     if (__all_sync(FULL, done)) break;
     ik_step_v<float>(q, J, e, k.damping, done ? 0.0f : k.step_limit);  // frozen once finished
   }
+  p_world_v<float>(pr_f, s0_f, c0_f, pf);
 }
 
 // the result record(s) of one query in the layout kOut (see IK_OUT_*)
@@ -557,11 +560,12 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
           const bool ok = want && id < a.n;
           ran_out = ran_out || (want && !ok);
-          float t0 = Slots<V>::get(tgt[0], k), t1 = Slots<V>::get(tgt[1], k), t2 = Slots<V>::get(tgt[2], k);
-          ldg3_if(ok, a.targets + (size_t)id * 3u, t0, t1, t2);
-          Slots<V>::set(tgt[0], k, t0);
-          Slots<V>::set(tgt[1], k, t1);
-          Slots<V>::set(tgt[2], k, t2);
+          float tw[3] = {0.0f, 0.0f, 0.0f}, tbk[3];
+          ldg3_if(ok, a.targets + (size_t)id * 3u, tw[0], tw[1], tw[2]);
+          pnp_spec::spec_world_to_base_v<float>(tw, tbk);  // tgt holds the target in the frame of joint 1's parent (ik_eval_j1_v)
+          Slots<V>::set(tgt[0], k, ok ? tbk[0] : Slots<V>::get(tgt[0], k));
+          Slots<V>::set(tgt[1], k, ok ? tbk[1] : Slots<V>::get(tgt[1], k));
+          Slots<V>::set(tgt[2], k, ok ? tbk[2] : Slots<V>::get(tgt[2], k));
 #pragma unroll
           for (int i = 0; i < NJ; ++i) {
             float qi = Slots<V>::get(q[i], k);
@@ -646,8 +650,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
 
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
-    V p[3], n2, e[3], J[21];
-    ik_eval_v<V>(q, tgt, trig, p, e, n2, J);
+    V p[3], n2, e[3], J[21], s0, c0;  // p: in joint 1's frame
+    ik_eval_j1_v<V>(q, tgt, trig, p, e, n2, J, s0, c0);
     // per-slot state update in integer arithmetic (0 / 1 flags): as booleans ptxas ran out of predicate registers and
     // spilled them through SEL / LOP pairs, ~45 instructions per pass for the two slots
     int any_fin_i = 0, any_run_i = 0, imm_i = 0;
@@ -683,6 +687,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       //      moved it: those are flushed in the same pass (imm) and re-read their q_init.  That only ever
       //      happens in a flush such a finish forces itself, so the common flush is a second copy of the block
       //      WITHOUT the reload: no seven predicated-off loads per slot and no copy of q into registers of its own.
+      V pw[3];
+      p_world_v<V>(p, s0, c0, pw);  // final_pos in the world frame (both slots, packed)
       auto store_finished = [&](auto with_reload) {
 #pragma unroll
         for (int k = 0; k < S; ++k) {
@@ -709,7 +715,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
             float* oq = a.q_out + (size_t)id * 8u;
             stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
             stg128_if(f, oq + 4, qf[4], qf[5], qf[6], err);
-            stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(p[0], k), Slots<V>::get(p[1], k), Slots<V>::get(p[2], k), word);
+            stg128_if(f, a.final_pos + (size_t)id * 4u, Slots<V>::get(pw[0], k), Slots<V>::get(pw[1], k), Slots<V>::get(pw[2], k), word);
           } else if (kOut == IK_OUT_COMPACT) {
             float* oq = a.q_out + (size_t)id * 8u;
             stg128_if(f, oq, qf[0], qf[1], qf[2], qf[3]);
@@ -720,7 +726,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
             for (int i = 0; i < NJ; ++i) qo[i] = qf[i];
             if (a.final_pos) {
               float* fp = a.final_pos + (size_t)id * 3u;
-              fp[0] = Slots<V>::get(p[0], k); fp[1] = Slots<V>::get(p[1], k); fp[2] = Slots<V>::get(p[2], k);
+              fp[0] = Slots<V>::get(pw[0], k); fp[1] = Slots<V>::get(pw[1], k); fp[2] = Slots<V>::get(pw[2], k);
             }
             if (a.pos_err) a.pos_err[id] = err;
             if (a.iters) a.iters[id] = iterations;
@@ -856,8 +862,8 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_one_kernel(const float* __r
     const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
     if (kSpec) {
       const TrigV trig{s_trig};
-      float e[3], J[21];
-      ik_eval_v<float>(q, tgt, trig, p, e, n2, J);
+      float e[3], J[21], s0, c0;
+      ik_eval_v<float>(q, tgt, trig, p, e, n2, J, s0, c0);
       conv = !last && n2 < thresh2;                            // :61-64
       if (conv || last) break;
       ik_step_v<float>(q, J, e, k.damping, k.step_limit);
@@ -1156,8 +1162,10 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     if (!__any_sync(FULL, any_live)) break;
 
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
-    V p[3], n2, ev[3], J[21];
-    ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
+    V p[3], pr[3], n2, ev[3], J[21], s0, c0, tb[3];  // pr: FK in joint 1's frame (ik_eval_j1_v); p: the same point in the world
+    pnp_spec::spec_world_to_base_v<V>(tgt, tb);
+    ik_eval_j1_v<V>(qs, tb, trig, pr, ev, n2, J, s0, c0);
+    p_world_v<V>(pr, s0, c0, p);
     bool fin[S], iterating[S], reload[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
@@ -1248,9 +1256,9 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
     if (kFuse) {
       // error of the new targets at this pass's p: what the first pass of the next solve would compute
-      V en[3];
-      en[0] = v_sub(tgt[0], p[0]); en[1] = v_sub(tgt[1], p[1]); en[2] = v_sub(tgt[2], p[2]);
-      const V n2n = pnp_fma(en[2], en[2], pnp_fma(en[1], en[1], pnp_mul(en[0], en[0])));
+      V en[3], n2n, tbn[3];
+      pnp_spec::spec_world_to_base_v<V>(tgt, tbn);
+      target_err_j1_v<V>(tbn, pr, s0, c0, en, n2n);
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         // a new solve that is already within pos_thresh of its target (or an env that is done, or a rejected
@@ -2274,8 +2282,10 @@ __global__ void __launch_bounds__(kBlock, (Slots<V>::kN == 2 || kBlock == PLAN_B
     if (!__any_sync(FULL, any_live)) break;
 
     // ---- one DLS pass for all slots of all lanes (ik_solver.py:58-83) ---------------------------------
-    V p[3], n2, ev[3], J[21];
-    ik_eval_v<V>(qs, tgt, trig, p, ev, n2, J);
+    V p[3], pr[3], n2, ev[3], J[21], s0, c0, tb[3];  // pr: FK in joint 1's frame (ik_eval_j1_v); p: the same point in the world
+    pnp_spec::spec_world_to_base_v<V>(tgt, tb);
+    ik_eval_j1_v<V>(qs, tb, trig, pr, ev, n2, J, s0, c0);
+    p_world_v<V>(pr, s0, c0, p);
     bool fin[S], iterating[S], reload[S], fused[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
@@ -2418,9 +2428,9 @@ __global__ void __launch_bounds__(kBlock, (Slots<V>::kN == 2 || kBlock == PLAN_B
     }
     if (kFuse) {
       // error of the new targets at this pass's p: what the first pass of the next solve would compute
-      V en[3];
-      en[0] = v_sub(tgt[0], p[0]); en[1] = v_sub(tgt[1], p[1]); en[2] = v_sub(tgt[2], p[2]);
-      const V n2n = pnp_fma(en[2], en[2], pnp_fma(en[1], en[1], pnp_mul(en[0], en[0])));
+      V en[3], n2n, tbn[3];
+      pnp_spec::spec_world_to_base_v<V>(tgt, tbn);
+      target_err_j1_v<V>(tbn, pr, s0, c0, en, n2n);
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         // a new solve already within pos_thresh of its target stays frozen and is finished by the next pass

@@ -233,16 +233,24 @@ class Compiler:
         return out, stats, vout
 
 
-def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: bool):
-    """Emit FK down the chain; returns (p_ee, R_ee or None, anchors, axes)."""
+def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: bool, joint1_frame: bool = False):
+    """Emit FK down the chain; returns (p_ee, R_ee or None, anchors, axes).
+
+    joint1_frame: everything is expressed in the frame that joint 1 carries, A_0 Rz(q_1) - i.e. the chain starts at
+    the identity with s_1 = 0, c_1 = 1 and the caller rotates the target into that frame (4 operations per pass).
+    The DLS step J^T (J J^T + lam I)^-1 e does not depend on the frame J and e share, and in this one the first
+    joint's rotation drops out of every product down the chain (Panda: 85 instead of 107 operations for FK + Jp,
+    one more structural zero in Jp)."""
     s = [cp.input(f"s[{i}]", np.sin(qs[:, i] - tree.qref[i])) for i in range(7)]
     c = [cp.input(f"c[{i}]", np.cos(qs[:, i] - tree.qref[i])) for i in range(7)]
+    if joint1_frame:
+        s[0], c[0] = cp.const(0.0), cp.const(1.0)
     R = [[cp.const(1.0 if r == k else 0.0) for k in range(3)] for r in range(3)]
     p = [cp.const(0.0) for _ in range(3)]
     anchors, axes = [], []
     for i in range(7):
-        pos = [cp.const(v) for v in tree.link_pos[i]]
-        rot = [[cp.const(v) for v in row] for row in tree.link_rot[i]]
+        pos = [cp.const(v) for v in (np.zeros(3) if joint1_frame and i == 0 else tree.link_pos[i])]
+        rot = [[cp.const(v) for v in row] for row in (np.eye(3) if joint1_frame and i == 0 else tree.link_rot[i])]
         p = [cp.dot(R[r], pos, init=p[r]) for r in range(3)]
         R = [[cp.dot(R[r], [rot[k][j] for k in range(3)]) for j in range(3)] for r in range(3)]
         anchors.append(list(p))
@@ -254,7 +262,7 @@ def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: boo
             # delivers two 64-bit operands per instruction slot (a third costs an extra cycle unless it
             # sits in the operand-reuse cache, tools/microbench/fp32x2_operands.cu)
             mx = [cp.mul(s[i], R[r][1]) for r in range(3)]
-            my = [cp.mul(Signed(s[i].node, -s[i].sign), R[r][0]) for r in range(3)]
+            my = [cp.mul(cp.const(-s[i].cval) if s[i].is_const else Signed(s[i].node, -s[i].sign), R[r][0]) for r in range(3)]
             newx = [cp.fma(c[i], R[r][0], mx[r]) for r in range(3)]
             newy = [cp.fma(c[i], R[r][1], my[r]) for r in range(3)]
             R = [[newx[r], newy[r], R[r][2]] for r in range(3)]
@@ -282,10 +290,10 @@ def cross_fused(cp, a, b):
     return [comp(1, 2), comp(2, 0), comp(0, 1)]
 
 
-def gen_function(tree, rng, name, want_jacp, want_full):
+def gen_function(tree, rng, name, want_jacp, want_full, joint1_frame=False):
     qs = rng.uniform(-3.0, 3.0, size=(K_SAMPLES, 7))
     cp = Compiler(rng)
-    p_ee, R_ee, anchors, axes = build_chain(cp, tree, qs, want_rot=want_full)
+    p_ee, R_ee, anchors, axes = build_chain(cp, tree, qs, want_rot=want_full, joint1_frame=joint1_frame)
     out_lines = []
     jp_zero = np.ones((3, 7), dtype=bool)
     jr_zero = np.ones((3, 7), dtype=bool)
@@ -353,6 +361,36 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
     f_pos, st_pos, _, _ = gen_function(snapped, rng, "spec_fk_pos", False, False)
     f_jac, st_jac, jp_zero, _ = gen_function(snapped, rng, "spec_fk_jacp", True, False)
     f_full, st_full, _, _ = gen_function(snapped, rng, "spec_fk_full", False, True)
+    f_j1, st_j1, jp_zero_j1, _ = gen_function(snapped, rng, "spec_fk_jacp_j1", True, False, joint1_frame=True)
+
+    # world <-> frame of joint 1's parent (A_0 = the first fixed transform of the canonical chain)
+    def rigid(name, fn_doc, apply):
+        cp = Compiler(rng)
+        fp = rng.uniform(-2.0, 2.0, size=(3, K_SAMPLES))
+        x = [cp.input(f"x[{r}]", fp[r]) for r in range(3)]
+        for r, v in enumerate(apply(cp, x)):
+            cp.store(f"y[{r}]", v)
+        _, _, vbody = cp.finish()
+        return (f"// {fn_doc}\ntemplate <typename T>\n__device__ __forceinline__ void {name}(const T* __restrict__ x, T* __restrict__ y) {{\n"
+                + "\n".join(vbody) + "\n}")
+
+    a0_pos, a0_rot = snapped.link_pos[0], snapped.link_rot[0]
+
+    def to_base(cp, x):  # A_0.rot^T (x - A_0.pos)
+        d = [cp.sub(x[r], cp.const(a0_pos[r])) for r in range(3)]
+        return [cp.dot([cp.const(a0_rot[r][k]) for r in range(3)], d) for k in range(3)]
+
+    def to_world(cp, x):  # A_0.pos + A_0.rot x
+        return [cp.dot([cp.const(a0_rot[r][k]) for k in range(3)], x, init=cp.const(a0_pos[r])) for r in range(3)]
+
+    def to_base_vec(cp, x):  # A_0.rot^T x (a difference of two points)
+        return [cp.dot([cp.const(a0_rot[r][k]) for r in range(3)], x) for k in range(3)]
+
+    f_rigid = "\n\n".join([
+        rigid("spec_world_to_base_v", "a world point in the frame of joint 1's parent: A_0.rot^T (x - A_0.pos)", to_base),
+        rigid("spec_base_to_world_v", "and back: A_0.pos + A_0.rot x", to_world),
+        rigid("spec_world_to_base_vec_v", "a world displacement in that frame: A_0.rot^T x", to_base_vec),
+    ])
 
     # A = Jp Jp^T (upper triangle, 6 unique) and dq = Jp^T y skipping structural zeros
     jjt = ["template <typename T>\n__device__ __forceinline__ void spec_jjt(const T* __restrict__ J, T* __restrict__ A) {"]
@@ -416,6 +454,36 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
         jty.append(f"  dq[{j}] = {'d%d' % j if started[j] else 'T(0.0)'};")
     jty.append("}")
 
+    # the same two routines for the Jacobian of spec_fk_jacp_j1 (its own structural zeros)
+    jjt.append("template <typename T>\n__device__ __forceinline__ void spec_jjt_damped_j1_v(const T* __restrict__ J, const T lam, T* __restrict__ A) {")
+    started = [False] * 6
+    for j in range(7):
+        for k, (r, s_) in enumerate(pairs):
+            if jp_zero_j1[r, j] or jp_zero_j1[s_, j]:
+                continue
+            a_, b_ = f"J[{r * 7 + j}]", f"J[{s_ * 7 + j}]"
+            if started[k]:
+                jjt.append(f"  a{k} = pnp_fma({a_}, {b_}, a{k});")
+            elif r == s_:
+                jjt.append(f"  T a{k} = pnp_fma({a_}, {b_}, lam);")
+            else:
+                jjt.append(f"  T a{k} = pnp_mul({a_}, {b_});")
+            started[k] = True
+    for k, (r, s_) in enumerate(pairs):
+        jjt.append(f"  A[{k}] = {'a%d' % k if started[k] else ('lam' if r == s_ else 'T(0.0)')};")
+    jjt.append("}")
+    jty.append("template <typename T>\n__device__ __forceinline__ void spec_jty_j1_v(const T* __restrict__ J, const T* __restrict__ y, T* __restrict__ dq) {")
+    started = [False] * 7
+    for r in range(3):
+        for j in range(7):
+            if jp_zero_j1[r, j]:
+                continue
+            jty.append(f"  {'T ' if not started[j] else ''}d{j} = " + (f"pnp_fma(J[{r * 7 + j}], y[{r}], d{j});" if started[j] else f"pnp_mul(J[{r * 7 + j}], y[{r}]);"))
+            started[j] = True
+    for j in range(7):
+        jty.append(f"  dq[{j}] = {'d%d' % j if started[j] else 'T(0.0)'};")
+    jty.append("}")
+
     def flop(st):
         return st["mul"] + st["add"] + 2 * st["fma"]
 
@@ -428,6 +496,7 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
 //   spec_fk_pos   {flop(st_pos):4d} FLOP   ({st_pos})
 //   spec_fk_jacp  {flop(st_jac):4d} FLOP   ({st_jac})
 //   spec_fk_full  {flop(st_full):4d} FLOP   ({st_full})
+//   spec_fk_jacp_j1 {flop(st_j1):4d} FLOP ({st_j1}; FK + Jp in the frame joint 1 carries, what the FP32 IK kernels evaluate)
 //   spec_jjt      {flops_jjt:4d} FLOP      spec_jty {flops_jty:4d} FLOP
 #pragma once
 
@@ -454,6 +523,10 @@ __host__ __device__ __forceinline__ constexpr bool spec_jp_col_zero(int j) {{ re
 {f_jac}
 
 {f_full}
+
+{f_j1}
+
+{f_rigid}
 
 {chr(10).join(jjt)}
 
