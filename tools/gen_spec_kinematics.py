@@ -233,14 +233,20 @@ class Compiler:
         return out, stats, vout
 
 
-def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: bool, joint1_frame: bool = False):
+def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: bool, joint1_frame: bool = False,
+                fold_tail: bool = False):
     """Emit FK down the chain; returns (p_ee, R_ee or None, anchors, axes).
 
     joint1_frame: everything is expressed in the frame that joint 1 carries, A_0 Rz(q_1) - i.e. the chain starts at
     the identity with s_1 = 0, c_1 = 1 and the caller rotates the target into that frame (4 operations per pass).
     The DLS step J^T (J J^T + lam I)^-1 e does not depend on the frame J and e share, and in this one the first
     joint's rotation drops out of every product down the chain (Panda: 85 instead of 107 operations for FK + Jp,
-    one more structural zero in Jp)."""
+    one more structural zero in Jp).
+
+    fold_tail: the last joint L whose rotation moves the EE site is not multiplied into the frame; the (constant) offset
+    from its origin to the site is rotated by q_L instead - w = Rz(q_L) v, p = p_L + R_L w: 4 + 9 operations where the
+    frame product and the offsets cost 12 + 6.  Only valid when no later joint moves the site (its Jacobian columns are
+    then structurally zero and are emitted as such); checked numerically against the unfolded chain."""
     s = [cp.input(f"s[{i}]", np.sin(qs[:, i] - tree.qref[i])) for i in range(7)]
     c = [cp.input(f"c[{i}]", np.cos(qs[:, i] - tree.qref[i])) for i in range(7)]
     if joint1_frame:
@@ -256,6 +262,23 @@ def build_chain(cp: Compiler, tree: KinematicTree, qs: np.ndarray, want_rot: boo
         anchors.append(list(p))
         axes.append([R[r][2] for r in range(3)])
         need_xy = want_rot or i < 6 or np.any(np.abs(tree.ee_pos[:2]) > 0)
+        last_xy = 5 if not np.any(np.abs(tree.ee_pos[:2]) > 0) else 6
+        if fold_tail and not want_rot and i == last_xy:
+            # offset from this joint's origin to the site in the frame after its rotation: later fixed transforms and
+            # later joints' rotations folded from the end (constants if those joints cannot move the site)
+            tail = [cp.const(v) for v in tree.ee_pos]
+            for j in range(6, i, -1):
+                tail = [cp.sub(cp.mul(c[j], tail[0]), cp.mul(s[j], tail[1])), cp.add(cp.mul(s[j], tail[0]), cp.mul(c[j], tail[1])), tail[2]]
+                rot_j = [[cp.const(v) for v in row] for row in tree.link_rot[j]]
+                tail = [cp.dot(rot_j[r], tail, init=cp.const(tree.link_pos[j][r])) for r in range(3)]
+            if all(t.is_const for t in tail):
+                sm = Signed(s[i].node, -s[i].sign)
+                w = [cp.fma(c[i], tail[0], cp.mul(sm, tail[1])), cp.fma(s[i], tail[0], cp.mul(c[i], tail[1])), tail[2]]
+                p_fold = [cp.dot(R[r], w, init=p[r]) for r in range(3)]
+                for j in range(i + 1, 7):  # joints that cannot move the site: rel = 0 -> zero columns
+                    anchors.append(list(p_fold))
+                    axes.append([cp.const(0.0), cp.const(0.0), cp.const(1.0)])
+                return p_fold, None, anchors, axes
         if need_xy:
             # emission order groups the three rows of each product so that consecutive instructions
             # share s_i (then c_i) in the same operand slot: on the packed f32x2 path the register file
@@ -290,10 +313,13 @@ def cross_fused(cp, a, b):
     return [comp(1, 2), comp(2, 0), comp(0, 1)]
 
 
-def gen_function(tree, rng, name, want_jacp, want_full, joint1_frame=False):
+def gen_function(tree, rng, name, want_jacp, want_full, joint1_frame=False, fold_tail=False):
     qs = rng.uniform(-3.0, 3.0, size=(K_SAMPLES, 7))
     cp = Compiler(rng)
-    p_ee, R_ee, anchors, axes = build_chain(cp, tree, qs, want_rot=want_full, joint1_frame=joint1_frame)
+    p_ee, R_ee, anchors, axes = build_chain(cp, tree, qs, want_rot=want_full, joint1_frame=joint1_frame, fold_tail=fold_tail)
+    if fold_tail:  # the folded chain must be the same function of q as the plain one
+        ref = build_chain(Compiler(rng), tree, qs, want_rot=want_full, joint1_frame=joint1_frame)
+        assert all(np.allclose(a.fp, b.fp, atol=1e-9) for a, b in zip(p_ee, ref[0])), "fold_tail changed the site position"
     out_lines = []
     jp_zero = np.ones((3, 7), dtype=bool)
     jr_zero = np.ones((3, 7), dtype=bool)
@@ -361,7 +387,9 @@ def generate(tree: KinematicTree, src_desc: str) -> str:
     f_pos, st_pos, _, _ = gen_function(snapped, rng, "spec_fk_pos", False, False)
     f_jac, st_jac, jp_zero, _ = gen_function(snapped, rng, "spec_fk_jacp", True, False)
     f_full, st_full, _, _ = gen_function(snapped, rng, "spec_fk_full", False, True)
-    f_j1, st_j1, jp_zero_j1, _ = gen_function(snapped, rng, "spec_fk_jacp_j1", True, False, joint1_frame=True)
+    _, _, jp_zero_plain, _ = gen_function(snapped, np.random.default_rng(777), "unused", True, False, joint1_frame=True)
+    f_j1, st_j1, jp_zero_j1, _ = gen_function(snapped, rng, "spec_fk_jacp_j1", True, False, joint1_frame=True, fold_tail=True)
+    assert (jp_zero_j1 == jp_zero_plain).all(), "fold_tail zeroed a Jacobian column that the plain chain does not"
 
     # world <-> frame of joint 1's parent (A_0 = the first fixed transform of the canonical chain)
     def rigid(name, fn_doc, apply):
