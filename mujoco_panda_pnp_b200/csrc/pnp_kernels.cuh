@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
   __shared__ __align__(16) float s_trig[kTrigVWords];
-  __shared__ float2 s_dump[S == 2 ? IK_BLOCK * NJ : 1];            // tail: every thread's q register pairs
+  __shared__ float2 s_dump[S == 2 ? IK_TAIL_MAX * NJ : 1];         // tail: the q register pairs of the lanes that park a slot
   __shared__ unsigned s_list[S == 2 ? IK_TAIL_MAX * 3 : 1];        // tail: query index, pass counter, owner of each parked slot
   __shared__ unsigned s_list_n, s_live_warps, s_dry_warps;
   load_trigv_table(s_trig);  // (the table is the library's own: nothing a previous launch writes)
@@ -620,10 +620,15 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           if (n_run) {
             if (lane == 0) base = atomicAdd(&s_list_n, n_run);
             base = __shfl_sync(FULL, base, 0);
-            // every lane dumps BOTH its slots as whole register pairs: 64-bit stores that never touch a half (reading
-            // the halves inside this divergent block made ptxas split the pairs and re-pack them in the hot loop)
+            // a lane that parks a slot dumps BOTH its slots as whole register pairs: 64-bit stores that never touch a half
+            // (reading the halves inside this divergent block made ptxas split the pairs and re-pack them in the hot
+            // loop).  At most n_run <= IK_TAIL_PER_WARP lanes per warp do, into rows [base, base + n_run) of the dump.
+            const unsigned any_m = S == 2 ? (run_m[0] | run_m[S - 1]) : run_m[0];
+            const unsigned row = base + (unsigned)__popc(any_m & lanemask_lt);
+            if ((any_m >> lane) & 1u) {
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) s_dump[threadIdx.x * NJ + i] = pair_of(q[i]);
+              for (int i = 0; i < NJ; ++i) s_dump[row * NJ + i] = pair_of(q[i]);
+            }
             unsigned before = 0;
 #pragma unroll
             for (int k = 0; k < S; ++k) {
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
                 unsigned* e = s_list + (base + before + (unsigned)__popc(run_m[k] & lanemask_lt)) * 3u;
                 e[0] = idx[k];
                 e[1] = (unsigned)it[k];
-                e[2] = threadIdx.x * 2u + (unsigned)k;
+                e[2] = row * 2u + (unsigned)k;
               }
               before += (unsigned)__popc(run_m[k]);
             }
