@@ -560,12 +560,11 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
           const bool ok = want && id < a.n;
           ran_out = ran_out || (want && !ok);
-          float tw[3] = {0.0f, 0.0f, 0.0f}, tbk[3];
-          ldg3_if(ok, a.targets + (size_t)id * 3u, tw[0], tw[1], tw[2]);
-          pnp_spec::spec_world_to_base_v<float>(tw, tbk);  // tgt holds the target in the frame of joint 1's parent (ik_eval_j1_v)
-          Slots<V>::set(tgt[0], k, ok ? tbk[0] : Slots<V>::get(tgt[0], k));
-          Slots<V>::set(tgt[1], k, ok ? tbk[1] : Slots<V>::get(tgt[1], k));
-          Slots<V>::set(tgt[2], k, ok ? tbk[2] : Slots<V>::get(tgt[2], k));
+          float t0 = Slots<V>::get(tgt[0], k), t1 = Slots<V>::get(tgt[1], k), t2 = Slots<V>::get(tgt[2], k);
+          ldg3_if(ok, a.targets + (size_t)id * 3u, t0, t1, t2);
+          Slots<V>::set(tgt[0], k, t0);
+          Slots<V>::set(tgt[1], k, t1);
+          Slots<V>::set(tgt[2], k, t2);
 #pragma unroll
           for (int i = 0; i < NJ; ++i) {
             float qi = Slots<V>::get(q[i], k);
@@ -655,8 +654,12 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
     }
 
     // ---- one DLS pass for all slots of all lanes ---------------------------------------------------
-    V p[3], n2, e[3], J[21], s0, c0;  // p: in joint 1's frame
-    ik_eval_j1_v<V>(q, tgt, trig, p, e, n2, J, s0, c0);
+    // (the target stays in the world frame in its registers and takes the constant shift into the frame of joint 1's
+    //  parent here, two packed adds per pass: converted in the refill, the adds sat right behind the target loads and the
+    //  store + refill block waited a global-load latency for them - 6 % of all warp samples)
+    V p[3], n2, e[3], J[21], s0, c0, tb[3];  // p: in joint 1's frame
+    pnp_spec::spec_world_to_base_v<V>(tgt, tb);
+    ik_eval_j1_v<V>(q, tb, trig, p, e, n2, J, s0, c0);
     // per-slot state update in integer arithmetic (0 / 1 flags): as booleans ptxas ran out of predicate registers and
     // spilled them through SEL / LOP pairs, ~45 instructions per pass for the two slots
     int any_fin_i = 0, any_run_i = 0, imm_i = 0;

@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 KERNELS = (("ik_solve_v_kernel", 4194304), ("ik_solve_small_kernel", 4096), ("reward_kernel", 16777216),
-           ("her_relabel_kernel", 8388608))
+           ("her_relabel_kernel", 8388608), ("move_ik_plan_v_kernel", 1048576))
 
 
 def ncu_csv(rep, page):
@@ -76,6 +76,9 @@ def main():
     summary, traffic = [], {}
     for k, units in KERNELS:
         rep = os.path.join(P, f"{k}_{tag}.ncu-rep")
+        if not os.path.exists(os.path.join(G, f"{k}_{tag}.ncu-rep")):
+            print(f"no capture of {k} in gpurun_out/ - skipped")
+            continue
         shutil.copy(os.path.join(G, f"{k}_{tag}.ncu-rep"), rep)
         summary.append(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(units)],
                                       capture_output=True, text=True).stdout)

@@ -15,8 +15,9 @@ SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --log2-n-ik 22 --l
 # every --set full capture sits behind ONE successful plain run of the same command: ncu on a program that
 # faulted leaves the GPU unusable until a reset (B200_PROFILING.md)
 if $SMALL > $OUT/plain_small_${TAG}.log 2>&1; then
-  for K in ik_solve_v_kernel ik_solve_small_kernel reward_kernel her_relabel_kernel; do
-    ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
+  for K in ik_solve_v_kernel ik_solve_small_kernel reward_kernel her_relabel_kernel move_ik_plan_v_kernel; do
+    SKIP=3; [ $K = move_ik_plan_v_kernel ] && SKIP=1   # the bench launches the planner three times in all
+    ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
     echo "$K full rc=$?"
   done
 else
