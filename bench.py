@@ -140,9 +140,9 @@ class ClockSampler:
 
 def ncu_traffic(kernel: str, units: int):
     """DRAM bytes per launch for `kernel` from the committed `ncu --set full` capture
-    (profiles/ncu_traffic_r2.json, else _r1: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
+    (profiles/ncu_traffic_r2c.json, else _r2 / _r1: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
     this launch's unit count); None when no capture is on file."""
-    for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):  # the latest capture on file
+    for name in ("ncu_traffic_r2c.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json"):  # the latest capture on file
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
                 return float(json.load(fh)[kernel]["dram_bytes_per_unit"]) * units
