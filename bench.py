@@ -138,11 +138,11 @@ class ClockSampler:
         }
 
 
-def ncu_traffic(kernel: str, units: int):
+def ncu_traffic(kernel: str, units: int, files=("ncu_traffic_r2c.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json")):
     """DRAM bytes per launch for `kernel` from the committed `ncu --set full` capture
     (profiles/ncu_traffic_r2c.json, else _r2 / _r1: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
     this launch's unit count); None when no capture is on file."""
-    for name in ("ncu_traffic_r2c.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json"):  # the latest capture on file
+    for name in files:  # the latest capture on file
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
                 return float(json.load(fh)[kernel]["dram_bytes_per_unit"]) * units
@@ -679,11 +679,12 @@ def run_ours(args) -> int:
 
         fut_ep = synthetic.her_future_indices(n_h, 300, seed=7, device=dev, strategy="future")
         side["her_relabel"] = her_line(fut_ep, "2^23 stored transitions, HER 'future' strategy (goal = achieved goal of a later transition "
-                                       "of the same 300-step episode, 1 in 5 keeps its goal): gather, relabel obs/next_obs, reward, VecNormalize")
+                                       "of the same 300-step episode, 1 in 5 keeps its goal): gather, relabel obs/next_obs, reward, VecNormalize",
+                                       traffic=ncu_traffic("her_relabel_kernel", n_h, files=("ncu_traffic_r2c.json",)))  # captured on this workload
         del fut_ep
         fut_un = synthetic.her_future_indices(n_h, 300, seed=7, device=dev, strategy="uniform")
         side["her_relabel_uniform_gather"] = her_line(fut_un, "same, goal gathered from ANY row of the buffer (no locality: every 12-byte goal "
-                                                      "costs a DRAM burst)", traffic=ncu_traffic("her_relabel_kernel", n_h))
+                                                      "costs a DRAM burst)", traffic=ncu_traffic("her_relabel_kernel", n_h, files=("ncu_traffic_r2.json",)))  # captured on this one
         h_tab = h_next[:, 19:22].contiguous()
         side["her_relabel_goal_table"] = her_line(fut_un, "uniform gather from a separate [N,3] achieved-goal table (pnp_her_relabel_table_f32)",
                                                   alg_bytes=476.0, future_ag=h_tab)

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define PNP_ABI_VERSION 2
+#define PNP_ABI_VERSION 3
 #define PNP_NJOINT 7
 
 /* error codes (negative; positive values are cudaError_t) */

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert set(declared_functions()) <= exported
     for name in declared_functions():
         assert hasattr(cuda_lib, name)
-    assert cuda_lib.pnp_abi_version() == 2
+    assert cuda_lib.pnp_abi_version() == 3
 
 
 def test_struct_layouts_match_header(cuda_lib):
