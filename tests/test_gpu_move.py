@@ -271,3 +271,40 @@ def test_fallback_strategy_2_is_exercised_against_the_oracle(oracle_chain):
             assert torch.equal(a[f], b[f]), f
         same = (a["status"].cpu().numpy() == ref["status"]) & (a["traj_len"].cpu().numpy() == ref["traj_len"])
         assert same.mean() > 0.9, same.mean()
+
+
+def test_staged_trajectory_stores_equal_direct_stores_and_stay_inside_their_rows():
+    """The FP32 planner stages the points of accepted solves in shared memory and writes them four at a time (trajectory
+    capacity % 4 == 0, 160-thread blocks); any other capacity takes the kernel that stores every point directly.  Same plans,
+    same points; nothing is written past traj_len or past the capacity (rows pre-filled with a sentinel), also when plans
+    overflow a small capacity (status bit 4) and when goals are unreachable."""
+    n = 50_000
+    mv = synthetic.reachable_move_envs(n, KinematicTree.from_mjcf().lower, KinematicTree.from_mjcf().upper, seed=4, device="cuda")
+    goal = engine.fk_jac(mv["q_goal"], want_quat=False, want_jac=False)[0]
+    goal[::301] = torch.tensor([2.5, 0.0, 0.5], device="cuda")  # unreachable: runs into max_outer
+    pk = engine.ik_params()
+    runs = {}
+    for cap in (256, 254, 12, 10):  # 256 / 12: staged; 254 / 10: direct
+        out = dict(traj=torch.full((n, cap, 3), -7.0, device="cuda"), traj_len=torch.empty(n, dtype=torch.int32, device="cuda"),
+                   q_final=torch.empty((n, 7), device="cuda"), n_solves=torch.empty(n, dtype=torch.int32, device="cuda"),
+                   status=torch.empty(n, dtype=torch.int32, device="cuda"))
+        for order in ("auto", None):
+            r = engine.move_ik_plan(mv["q_start"], goal, pk, traj_cap=cap, max_outer=40, out=out, order=order)
+            tl = r["traj_len"].long()
+            stored = torch.minimum(tl, torch.tensor(cap, device="cuda"))
+            idx = torch.arange(cap, device="cuda")[None, :]
+            untouched = r["traj"][idx.expand(n, cap) >= stored[:, None]]
+            assert bool((untouched == -7.0).all()), (cap, order)
+            assert bool((r["traj"][idx.expand(n, cap) < stored[:, None]] != -7.0).all()), (cap, order)
+            assert torch.equal((r["status"] & 4) != 0, tl > cap), (cap, order)
+            runs[(cap, order)] = {k: v.clone() for k, v in r.items() if not k.startswith("_")}
+            out["traj"].fill_(-7.0)
+    ref = runs[(256, None)]
+    for key, r in runs.items():
+        cap = key[0]
+        for f in ("traj_len", "n_solves", "q_final"):
+            assert torch.equal(ref[f], r[f]), (key, f)
+        assert torch.equal(ref["status"] & 3, r["status"] & 3), key
+        m = min(cap, 254)
+        keep = torch.arange(m, device="cuda")[None, :] < torch.minimum(ref["traj_len"].long(), torch.tensor(m, device="cuda"))[:, None]
+        assert torch.equal(ref["traj"][:, :m][keep], r["traj"][:, :m][keep]), key
