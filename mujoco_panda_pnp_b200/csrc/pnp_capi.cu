@@ -39,7 +39,14 @@ struct IkPdlState {
   bool primed = false;      // the previous launch of this stream was an ik_solve_v_kernel that zeroed the ticket `parity`
   unsigned parity = 0;      // ticket the next launch draws from
   ByteRange in[2], out[5];  // of the previous launch (valid while primed)
+  // drain hand-over (pair kernel -> resume kernel): two parking areas per stream, allocated on the stream's first big launch
+  float2* dump[2] = {nullptr, nullptr};
+  uint4* list[2] = {nullptr, nullptr};
+  size_t rows_cap = 0;
+  bool last_handover = false;  // the previous launch had a resume launch behind it (which zeroed this parity's counters)
 };
+// per stream and parity: {ticket, parked rows, parked slots, ticket of the resume launch}
+constexpr int kIkScratchWords = 4;
 
 struct DeviceState {
   bool have_tree = false;
@@ -48,7 +55,7 @@ struct DeviceState {
   int sm_count = 0;
   unsigned* tickets = nullptr;     // kStreamSlots refill tickets
   unsigned* order_work = nullptr;  // kStreamSlots blocks of 2*PLAN_BUCKETS words: plan-order histograms + cursors
-  unsigned* ik_tickets = nullptr;  // kStreamSlots pairs of tickets for ik_solve_v_kernel (consecutive launches alternate)
+  unsigned* ik_sc = nullptr;       // kStreamSlots x 2 parities x kIkScratchWords counters of ik_solve_v_kernel (launches alternate)
   IkPdlState ik_pdl[kStreamSlots];
   cudaStream_t slot_stream[kStreamSlots] = {};
   bool slot_used[kStreamSlots] = {};
@@ -71,7 +78,12 @@ int stream_slot_locked(DeviceState* s, cudaStream_t st) {
   if (i == kStreamSlots) i = (int)(s->slot_clock++ % kStreamSlots);  // all taken: recycle, oldest assignment first
   s->slot_used[i] = true;
   s->slot_stream[i] = st;
-  s->ik_pdl[i] = IkPdlState{};
+  {  // a new owner: forget the previous stream's launch history, keep the parking areas
+    IkPdlState fresh;
+    for (int k = 0; k < 2; ++k) { fresh.dump[k] = s->ik_pdl[i].dump[k]; fresh.list[k] = s->ik_pdl[i].list[k]; }
+    fresh.rows_cap = s->ik_pdl[i].rows_cap;  // (last_handover = false: the first launch memsets the counters)
+    s->ik_pdl[i] = fresh;
+  }
   return i;
 }
 int stream_slot(DeviceState* s, cudaStream_t st) {
@@ -357,18 +369,23 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   }
   auto kernel = a.q_init_stride == 0 ? pnp::ik_solve_v_kernel<V, kOut, true> : pnp::ik_solve_v_kernel<V, kOut, false>;
   static const int env_pdl = env_int("PNP_IK_PDL", 1);  // 0: every launch zeroes its ticket with a memset node (measurements)
+  static const int env_handover = env_int("PNP_IK_HANDOVER", 1);  // 0: stragglers finish inside their blocks (measurements)
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   CUDA_TRY(cudaStreamIsCapturing(st, &cap));
   std::lock_guard<std::mutex> lk(g_mu);  // the slot's state changes in the order of the launches on its stream
   const int sl = stream_slot_locked(s, st);
   IkPdlState& ps = s->ik_pdl[sl];
+  unsigned* sc = s->ik_sc + (size_t)sl * 2 * kIkScratchWords;
+  args.park_dump = nullptr; args.park_list = nullptr; args.park_lanes = nullptr; args.park_slots = nullptr;
+  args.zero_next[0] = args.zero_next[1] = args.zero_next[2] = nullptr;
+  auto forget = [&]() { ps.primed = false; ps.parity = 0; ps.last_handover = false; };
   if (small || !env_pdl || cap != cudaStreamCaptureStatusNone) {
     // small batches (a launch is one dependent chain: nothing to overlap), captured launches (a replayed node cannot
     // alternate tickets): the launch zeroes its own ticket, plain stream order
-    args.ticket = s->ik_tickets + 2 * sl;
+    args.ticket = sc;
     args.ticket_next = nullptr;
     args.pdl = pnp::IK_PDL_OFF;
-    ps = IkPdlState{};
+    forget();
     CUDA_TRY(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
     kernel<<<grid, block, 0, st>>>(args);
     ++g_launches;
@@ -395,10 +412,40 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     for (const ByteRange& i : in)
       for (const ByteRange& po : ps.out) clash = clash || ranges_overlap(i, po);
   }
-  args.ticket = s->ik_tickets + 2 * sl + ps.parity;
-  args.ticket_next = s->ik_tickets + 2 * sl + (ps.parity ^ 1u);
+  // drain hand-over: the pair kernel parks what is still running when its pool runs dry, a resume launch finishes it
+  bool handover = S == 2 && env_handover && args.tail;
+  if (handover) {
+    const size_t rows = (size_t)grid * (block / 32) * (IK_HANDOVER_AT);  // a warp parks at most IK_HANDOVER_AT slots (<= that many lanes)
+    if (ps.rows_cap < rows) {  // first big launch of this stream (cudaMalloc synchronises the device once)
+      const size_t most = (size_t)s->sm_count * 8 * (block / 32) * (IK_HANDOVER_AT);
+      const size_t cap_rows = most > rows ? most : rows;
+      for (int k = 0; k < 2; ++k) {
+        if (ps.dump[k]) cudaFree(ps.dump[k]);
+        if (ps.list[k]) cudaFree(ps.list[k]);
+        ps.dump[k] = nullptr; ps.list[k] = nullptr;
+      }
+      ps.rows_cap = 0;
+      bool ok = true;
+      for (int k = 0; k < 2 && ok; ++k)
+        ok = cudaMalloc(&ps.dump[k], cap_rows * 8 * sizeof(float2)) == cudaSuccess &&
+             cudaMalloc(&ps.list[k], cap_rows * sizeof(uint4)) == cudaSuccess;
+      if (ok) ps.rows_cap = cap_rows;
+      else { (void)cudaGetLastError(); handover = false; }  // no memory for it: stragglers finish in their blocks
+      forget();  // (the synchronising allocation ended whatever was in flight)
+    }
+  }
+  const unsigned p = ps.parity;
+  unsigned* scp = sc + p * kIkScratchWords;
+  unsigned* scn = sc + (p ^ 1u) * kIkScratchWords;
+  args.ticket = scp + 0;
+  args.ticket_next = scn + 0;
   args.pdl = clash ? pnp::IK_PDL_WAIT_FIRST : pnp::IK_PDL_WAIT_AT_DRY;
-  if (!ps.primed) CUDA_TRY(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
+  if (handover) {
+    args.park_dump = ps.dump[p]; args.park_list = ps.list[p];
+    args.park_lanes = scp + 1; args.park_slots = scp + 2;
+  }
+  // (a hand-over launch after one without: no resume launch has zeroed this parity's parking counters)
+  if (!ps.primed || (handover && !ps.last_handover)) CUDA_TRY(cudaMemsetAsync(sc, 0, 2 * kIkScratchWords * sizeof(unsigned), st));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -409,13 +456,33 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args);
   ++g_launches;
   if (e != cudaSuccess) {
-    ps = IkPdlState{};
+    forget();
     return cuda_fail(e, "cudaLaunchKernelEx(ik_solve_v_kernel)");
   }
+  if (handover) {
+    // the resume launch: one block per SM (it shares the SMs with the next pair launch), one query per lane
+    pnp::IkArgs<float> r = args;
+    r.ticket = scp + 3;
+    r.ticket_next = nullptr;
+    r.pdl = pnp::IK_PDL_OFF;
+    r.zero_next[0] = scn + 1; r.zero_next[1] = scn + 2; r.zero_next[2] = scn + 3;
+    r.chunk = 32; r.flush_min = 1; r.solo_warp = 0; r.tail = 0; r.guided = 0;
+    auto resume = a.q_init_stride == 0 ? pnp::ik_solve_v_kernel<float, kOut, true, true> : pnp::ik_solve_v_kernel<float, kOut, false, true>;
+    cfg.gridDim = dim3((unsigned)s->sm_count);
+    e = cudaLaunchKernelEx(&cfg, resume, r);
+    ++g_launches;
+    if (e != cudaSuccess) {
+      forget();
+      return cuda_fail(e, "cudaLaunchKernelEx(ik_solve_v_kernel, resume)");
+    }
+  } else {
+    // no resume launch will zero the other parity's hand-over counters: nothing uses them in this mode
+  }
   ps.primed = true;
+  ps.last_handover = handover;
   ps.parity ^= 1u;
   for (int k = 0; k < 2; ++k) ps.in[k] = in[k];
   for (int k = 0; k < 5; ++k) ps.out[k] = out[k];
@@ -474,6 +541,8 @@ int ik_solve_impl(const T* targets, const T* q_init, int32_t q_init_stride, int6
   a.q_out = q_out; a.final_pos = final_pos; a.pos_err = pos_err; a.iters = iters; a.flags = flags;
   a.counters = counters; a.ticket = nullptr; a.chunk = 32; a.flush_min = 1; a.solo_warp = 0; a.tail = 0; a.guided = 0;
   a.ticket_next = nullptr; a.pdl = 0;
+  a.park_dump = nullptr; a.park_list = nullptr; a.park_lanes = nullptr; a.park_slots = nullptr;
+  a.zero_next[0] = a.zero_next[1] = a.zero_next[2] = nullptr;
   a.thresh2 = a.k.pos_thresh * a.k.pos_thresh;
   const bool small = n <= (long long)s->sm_count * pnp::IK_BLOCK;
   if constexpr (std::is_same<T, float>::value) {
@@ -607,7 +676,7 @@ int pnp_set_tree(const PnpTree* t) {
   CUDA_TRY(cudaMemcpyToSymbol(pnp::c_tree_f64, &td, sizeof td));
   if (!s->tickets) {
     CUDA_TRY(cudaMalloc(&s->tickets, kStreamSlots * sizeof(unsigned)));
-    CUDA_TRY(cudaMalloc(&s->ik_tickets, 2 * kStreamSlots * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&s->ik_sc, 2 * kIkScratchWords * kStreamSlots * sizeof(unsigned)));
     CUDA_TRY(cudaMalloc(&s->order_work, (size_t)kStreamSlots * 2 * pnp::PLAN_BUCKETS * sizeof(unsigned)));
     // sin(k * 2*pi/8192), k < 8192 + 2048, for the FP32 IK kernels' first-order table trig, evaluated in FP64
     static float tabv[pnp::kTrigVWords];

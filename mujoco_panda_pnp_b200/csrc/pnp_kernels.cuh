@@ -183,6 +183,14 @@ struct IkArgs {
   unsigned* ticket_next;  // ik_solve_v_kernel: the ticket of this stream's NEXT launch, zeroed by block 0 (no memset node between
                           // two launches, so the next one can be a programmatic dependent of this one); nullptr = leave it alone
   unsigned pdl;       // ik_solve_v_kernel, programmatic dependent launch (see IK_PDL_*)
+  // Hand-over of a launch's unfinished queries to a follow-up launch (see "drain hand-over" at ik_solve_v_kernel).
+  //   pair kernel: park_dump / park_list non-null = a warp that sees the pool dry parks ALL its running slots there and leaves
+  //   resume kernel (kResume): takes its queries from them; n = *park_slots
+  float2* park_dump;      // [lane rows][8]: the q register pairs of every lane that parked a slot (row stride 64 B)
+  uint4* park_list;       // [slots]: query index, pass counter, 2 * row + slot
+  unsigned* park_lanes;   // rows written   (device counters, zero before the pair launch)
+  unsigned* park_slots;   // slots written
+  unsigned* zero_next[3]; // resume kernel: the counters the NEXT launch pair of this stream will use, zeroed by block 0
 };
 
 // Back-to-back launches of ik_solve_v_kernel on one stream overlap the drain of launch k with the ramp of launch k+1
@@ -484,14 +492,31 @@ __device__ __forceinline__ void store_lane_result(const IkArgs<float>& a, unsign
 #ifndef IK_TAIL_PER_WARP_N
 #define IK_TAIL_PER_WARP_N 8
 #endif
+// drain hand-over (see ik_solve_v_kernel): a warp hands its running slots to the resume launch once it is down to this many.
+// Measured at 2^24 queries, launches back to back / one launch alone: no hand-over 2.392 / 2.433 ms, at <= 8 slots 2.383 /
+// 2.428, <= 16: 2.357 / 2.405, <= 32: 2.354 / 2.412, everything at the dry point (64): 2.378 / 2.464.
+#ifndef IK_HANDOVER_AT
+#define IK_HANDOVER_AT 16
+#endif
 constexpr int IK_TAIL_PER_WARP = IK_TAIL_PER_WARP_N;         // a warp parks once it is down to this many running slots
 constexpr int IK_TAIL_MAX = (IK_BLOCK / 32) * IK_TAIL_PER_WARP;  // the block's stragglers: one per lane, 32 at a time
 __device__ __forceinline__ float2 pair_of(float v) { return make_float2(v, 0.0f); }
 __device__ __forceinline__ float2 pair_of(const F2& v) { return v.v; }
 
-template <typename V, int kOut, bool kBcast>
+//
+// Drain hand-over (pair kernel, launches that run as programmatic dependents).  A block cannot give its registers and
+// shared memory to the next launch while its last warp finishes the block's stragglers, and nearly every block holds a
+// query on its way to max_iters - so the overlap of two launches hid only a third of the drain.  With park_dump / park_list
+// set, a warp that has seen the ticket pool dry and is down to IK_HANDOVER_AT running slots parks them in GLOBAL memory
+// (whole register pairs, like the in-block tail) and leaves; no block waits for a straggler.  The follow-up launch - this kernel as <float, kOut, kBcast,
+// kResume = true>, one block per SM, small enough to sit next to four blocks of the NEXT pair launch - resumes the parked
+// queries one per lane from exactly the state they were parked in (same arithmetic: no result bit depends on where a query
+// finishes) while the next pair launch already runs.  Chain per stream: pair k -> resume k -> pair k+1 -> resume k+1, every
+// edge a programmatic one; resume k waits for pair k to complete before it reads the list, and only then lets pair k+1 start.
+template <typename V, int kOut, bool kBcast, bool kResume = false>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
+  static_assert(!kResume || S == 1, "the resume kernel runs one query per lane");
   const unsigned lane = threadIdx.x & 31u;
   __shared__ __align__(16) float s_q0[8];
   __shared__ __align__(16) float s_trig[kTrigVWords];
@@ -499,13 +524,24 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
   __shared__ unsigned s_list[S == 2 ? IK_TAIL_MAX * 3 : 1];        // tail: query index, pass counter, owner of each parked slot
   __shared__ unsigned s_list_n, s_live_warps, s_dry_warps;
   load_trigv_table(s_trig);  // (the table is the library's own: nothing a previous launch writes)
-  if (a.pdl == IK_PDL_WAIT_FIRST) griddep_wait();
+  if (a.pdl == IK_PDL_WAIT_FIRST || kResume) griddep_wait();  // resume: the pair launch has completed, its list is final
   if (kBcast && threadIdx.x < NJ) s_q0[threadIdx.x] = a.q_init[threadIdx.x];
   if (threadIdx.x == 0) {
     s_list_n = 0; s_live_warps = IK_BLOCK / 32; s_dry_warps = 0;
     if (blockIdx.x == 0 && a.ticket_next) { atomicExch(a.ticket_next, 0u); __threadfence(); }
+    if (kResume && blockIdx.x == 0) {
+      // the pair launch before this one has completed, hence (its wait at the dry point) so has the resume launch before
+      // that: the counters of the stream's other parity are free, and the next pair launch starts only after this block
+      // has let it (below)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (a.zero_next[i]) atomicExch(a.zero_next[i], 0u);
+      __threadfence();
+    }
   }
   __syncthreads();
+  if (kResume) griddep_launch_dependents();  // the next pair launch may move in next to this one
+  const unsigned n_lim = kResume ? *reinterpret_cast<volatile unsigned*>(a.park_slots) : a.n;
   if (a.solo_warp && threadIdx.x >= 32) return;  // helper warps of a small-batch block: table loaded, done
   const TrigV trig{s_trig};
   const unsigned lanemask_lt = (1u << lane) - 1u;
@@ -544,7 +580,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
         unsigned fresh = 0;
         if (count > avail) {  // warp-uniform
           if (pool_dry) {
-            fresh = a.n;  // this warp has seen the end of the batch: it never touches the ticket again (the next launch
+            fresh = n_lim;  // this warp has seen the end of the batch: it never touches the ticket again (the next launch
                           // of the stream may already have zeroed it for the launch after that, see IK_PDL_*)
           } else {
             if (lane == 0) fresh = atomicAdd(a.ticket, my_chunk);
@@ -558,22 +594,40 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           const bool want = st[k] == IDLE && !exhausted;
           const unsigned rank = before + (unsigned)__popc(need[k] & lanemask_lt);
           const unsigned id = rank < avail ? pool_next + rank : fresh + (rank - avail);
-          const bool ok = want && id < a.n;
+          const bool ok = want && id < n_lim;
           ran_out = ran_out || (want && !ok);
+          unsigned qid = id;   // the query behind ticket `id`
+          int it0 = 0;         // and the pass it starts at
+          if constexpr (kResume) {
+            // ticket `id` is a parked slot: its query, its pass counter, and where its q sits in the dump
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) m = a.park_list[id];
+            qid = m.x;
+            it0 = (int)m.y;
+            const float* src = reinterpret_cast<const float*>(a.park_dump + (size_t)(m.z >> 1) * 8u) + (m.z & 1u);
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+              float qi = Slots<V>::get(q[i], k);
+              ldg1_if(ok, src + 2 * i, qi);
+              Slots<V>::set(q[i], k, qi);
+            }
+          }
           float t0 = Slots<V>::get(tgt[0], k), t1 = Slots<V>::get(tgt[1], k), t2 = Slots<V>::get(tgt[2], k);
-          ldg3_if(ok, a.targets + (size_t)id * 3u, t0, t1, t2);
+          ldg3_if(ok, a.targets + (size_t)qid * 3u, t0, t1, t2);
           Slots<V>::set(tgt[0], k, t0);
           Slots<V>::set(tgt[1], k, t1);
           Slots<V>::set(tgt[2], k, t2);
+          if constexpr (!kResume) {
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) {
-            float qi = Slots<V>::get(q[i], k);
-            if (kBcast) lds1_if(ok, s_q0 + i, qi);   // predicated load: one instruction instead of LDS + select
-            else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
-            Slots<V>::set(q[i], k, qi);
+            for (int i = 0; i < NJ; ++i) {
+              float qi = Slots<V>::get(q[i], k);
+              if (kBcast) lds1_if(ok, s_q0 + i, qi);   // predicated load: one instruction instead of LDS + select
+              else ldg1_if(ok, a.q_init + (size_t)id * NJ + i, qi);
+              Slots<V>::set(q[i], k, qi);
+            }
           }
-          idx[k] = ok ? id : idx[k];
-          it[k] = ok ? 0 : it[k];
+          idx[k] = ok ? qid : idx[k];
+          it[k] = ok ? it0 : it[k];
           st[k] = ok ? (int)RUN : st[k];
           Slots<V>::set(slim, k, ok ? a.k.step_limit : Slots<V>::get(slim, k));
           before += (unsigned)__popc(need[k]);
@@ -614,7 +668,30 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
           run_m[k] = __ballot_sync(FULL, st[k] == RUN);
           n_run += (unsigned)__popc(run_m[k]);
         }
-        if (n_run <= (unsigned)IK_TAIL_PER_WARP) {
+        if (a.park_list && n_run <= (unsigned)(IK_HANDOVER_AT)) {
+          // drain hand-over: what is still running goes to the follow-up launch, whole register pairs again
+          if (n_run) {
+            const unsigned any_m = S == 2 ? (run_m[0] | run_m[S - 1]) : run_m[0];
+            unsigned row0 = 0, slot0 = 0;
+            if (lane == 0) { row0 = atomicAdd(a.park_lanes, (unsigned)__popc(any_m)); slot0 = atomicAdd(a.park_slots, n_run); }
+            row0 = __shfl_sync(FULL, row0, 0);
+            slot0 = __shfl_sync(FULL, slot0, 0);
+            const unsigned row = row0 + (unsigned)__popc(any_m & lanemask_lt);
+            if ((any_m >> lane) & 1u) {
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) a.park_dump[(size_t)row * 8u + i] = pair_of(q[i]);
+            }
+            unsigned before = 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+              if (st[k] == RUN)
+                a.park_list[slot0 + before + (unsigned)__popc(run_m[k] & lanemask_lt)] = make_uint4(idx[k], (unsigned)it[k], row * 2u + (unsigned)k, 0u);
+              before += (unsigned)__popc(run_m[k]);
+            }
+          }
+          break;
+        }
+        if (!a.park_list && n_run <= (unsigned)IK_TAIL_PER_WARP) {
           unsigned base = 0;
           if (n_run) {
             if (lane == 0) base = atomicAdd(&s_list_n, n_run);
@@ -685,7 +762,7 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       unsigned n_run = 0;
 #pragma unroll
       for (int k = 0; k < S; ++k) n_run += (unsigned)__popc(__ballot_sync(FULL, st[k] == RUN));
-      flush = n_run <= (unsigned)IK_TAIL_PER_WARP;
+      flush = n_run <= (unsigned)(a.park_list ? (IK_HANDOVER_AT) : IK_TAIL_PER_WARP);
     }
     if (flush) {  // warp-uniform
       // ---- store finished slots.  A frozen slot keeps its q and recomputes the same p / n2 every pass,

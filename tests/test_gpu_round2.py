@@ -345,3 +345,32 @@ def test_back_to_back_launches_overlap_without_changing_a_bit(tree):
     torch.cuda.synchronize()
     for x, y in zip(a2, b2):
         assert torch.equal(x.view(torch.uint8), y.view(torch.uint8))
+
+
+def test_drain_handover_in_mixed_launch_sequences(tree):
+    """The pair kernel hands its last running slots to a resume launch (one query per lane) and leaves; the counters of
+    that hand-over alternate per stream and are zeroed by the resume launch before.  Sequences that break the alternation -
+    a one-query-per-lane launch (no resume launch behind it) between two pair launches, small batches, per-query q_init,
+    the three output layouts - return what each launch returns alone; nothing is lost or solved twice."""
+    n = (1 << 20) + 77
+    tg = [_targets(tree, n, seed=300 + i) for i in range(3)]
+    for t in tg:
+        t[::211] = torch.tensor([2.5, 0.0, 0.5], device="cuda")
+    qi = (_neutral() + 0.1 * torch.randn((n, 7), device="cuda")).contiguous()
+    seq = [("spec_pair", tg[0], _neutral(), {}), ("spec_lane", tg[1], _neutral(), {}), ("spec_pair", tg[2], qi, {}),
+           ("spec_pair", tg[1], _neutral(), {"compact": True}), ("auto", tg[0][:4096].contiguous(), _neutral(), {}),
+           ("spec_pair", tg[2], _neutral(), {"packed": False}), ("spec_pair", tg[0], qi, {})]
+    fields = ("q", "iterations", "converged", "success")
+    ref = []
+    for kin, t, q0, kw in seq:  # one at a time, on the one-query-per-lane kernel, the device idle in between
+        r = engine.ik_solve(t, q0, engine.ik_params(kinematics="spec_lane" if kin != "auto" else "auto"), **kw)
+        torch.cuda.synchronize()
+        ref.append({f: getattr(r, f).clone() for f in fields})
+    for rep in range(2):
+        cnts = [torch.zeros(4, dtype=torch.int64, device="cuda") for _ in seq]
+        got = [engine.ik_solve(t, q0, engine.ik_params(kinematics=kin), counters=c, **kw) for (kin, t, q0, kw), c in zip(seq, cnts)]
+        torch.cuda.synchronize()
+        for i, (r, want, c) in enumerate(zip(got, ref, cnts)):
+            for f in fields:
+                assert torch.equal(getattr(r, f), want[f]), (rep, i, f)
+            assert int(c[0]) == len(want["q"]) and int(c[1]) == int(want["converged"].sum()) and int(c[3]) == int(want["iterations"].long().sum()), (rep, i)
