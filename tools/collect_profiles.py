@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 KERNELS = (("ik_solve_v_kernel", 4194304), ("ik_solve_small_kernel", 4096), ("reward_kernel", 16777216),
-           ("her_relabel_kernel", 8388608), ("move_ik_plan_v_kernel", 1048576))
+           ("her_relabel_kernel", 8388608), ("move_ik_plan_v_kernel", 1048576), ("ik_solve_resume_kernel", 4194304))
 
 
 def ncu_csv(rep, page):

@@ -17,7 +17,10 @@ SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --log2-n-ik 22 --l
 if $SMALL > $OUT/plain_small_${TAG}.log 2>&1; then
   for K in ik_solve_v_kernel ik_solve_small_kernel reward_kernel her_relabel_kernel move_ik_plan_v_kernel; do
     SKIP=3; [ $K = move_ik_plan_v_kernel ] && SKIP=1   # the bench launches the planner three times in all
-    ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
+    RE="regex:$K"; BASE=function
+    # a big IK solve is two launches of the same template (pair kernel + resume launch): pick the pair kernel by its type
+    [ $K = ik_solve_v_kernel ] && { RE="regex:ik_solve_v_kernel<pnp_spec::F2"; BASE=demangled; }
+    ncu --set full --clock-control none --import-source on --kernel-name-base $BASE -k "$RE" -s $SKIP -c 1 -f -o $OUT/${K}_${TAG} $SMALL > $OUT/ncu_${K}_${TAG}.log 2>&1
     echo "$K full rc=$?"
   done
 else
