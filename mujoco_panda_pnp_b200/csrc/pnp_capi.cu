@@ -413,7 +413,9 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
       for (const ByteRange& po : ps.out) clash = clash || ranges_overlap(i, po);
   }
   // drain hand-over: the pair kernel parks what is still running when its pool runs dry, a resume launch finishes it
-  bool handover = S == 2 && env_handover && args.tail;
+  // (from 16384 queries per SM up: a smaller launch timed alone loses more to the resume launch's fixed cost than its blocks
+  //  gain by leaving early - 2^20 queries alone 0.241 -> 0.264 ms with it, 2^22 0.679 -> 0.668 ms)
+  bool handover = S == 2 && env_handover && args.tail && (long long)a.n >= (long long)s->sm_count * 16384;
   if (handover) {
     const size_t rows = (size_t)grid * (block / 32) * (IK_HANDOVER_AT);  // a warp parks at most IK_HANDOVER_AT slots (<= that many lanes)
     if (ps.rows_cap < rows) {  // first big launch of this stream (cudaMalloc synchronises the device once)
