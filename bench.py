@@ -138,9 +138,9 @@ class ClockSampler:
         }
 
 
-def ncu_traffic(kernel: str, units: int, files=("ncu_traffic_r2c.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json")):
+def ncu_traffic(kernel: str, units: int, files=("ncu_traffic_r2d.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json")):
     """DRAM bytes per launch for `kernel` from the committed `ncu --set full` capture
-    (profiles/ncu_traffic_r2c.json, else _r2 / _r1: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
+    (profiles/ncu_traffic_r2d.json, else _r2 / _r1: dram__bytes_read.sum + dram__bytes_write.sum per unit, scaled to
     this launch's unit count); None when no capture is on file."""
     for name in files:  # the latest capture on file
         try:
@@ -680,7 +680,7 @@ def run_ours(args) -> int:
         fut_ep = synthetic.her_future_indices(n_h, 300, seed=7, device=dev, strategy="future")
         side["her_relabel"] = her_line(fut_ep, "2^23 stored transitions, HER 'future' strategy (goal = achieved goal of a later transition "
                                        "of the same 300-step episode, 1 in 5 keeps its goal): gather, relabel obs/next_obs, reward, VecNormalize",
-                                       traffic=ncu_traffic("her_relabel_kernel", n_h, files=("ncu_traffic_r2c.json",)))  # captured on this workload
+                                       traffic=ncu_traffic("her_relabel_kernel", n_h, files=("ncu_traffic_r2d.json",)))  # captured on this workload
         del fut_ep
         fut_un = synthetic.her_future_indices(n_h, 300, seed=7, device=dev, strategy="uniform")
         side["her_relabel_uniform_gather"] = her_line(fut_un, "same, goal gathered from ANY row of the buffer (no locality: every 12-byte goal "
