@@ -145,8 +145,15 @@ int pnp_fk_jac_f64(const double* q, int64_t n, double* pos, double* quat, double
 int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_stride, int64_t n,
                      const PnpIkParams* params, float* q_out, float* final_pos, float* pos_err,
                      int32_t* iters, uint8_t* flags, unsigned long long* counters, void* stream);
-/* FP32 IK kernels evaluate sin/cos of the joint angles by table look-up with magic-number range reduction:
- * joint angles must satisfy |q| < 3.2e3 rad (any sane configuration; q_init outside the joint limits is fine). */
+/* FP32 IK kernels evaluate sin/cos of the joint angles by table look-up with a one-term magic-number range reduction:
+ * 1.8e-7 absolute inside +-2 pi (the joint range; a q_init outside the joint limits is fine), growing by 2.8e-8 per
+ * radian beyond; the index arithmetic needs |q| < 3.2e3 rad.
+ * Stream semantics of the FP32 solves on the build-time tree: two consecutive launches of >= 128 queries per SM on one
+ * stream with nothing between them overlap their drain / ramp (programmatic dependent launch) unless the second one reads
+ * or overwrites memory of the first (the library compares the byte ranges and falls back to plain stream order); from
+ * 16384 queries per SM up a launch is followed by a small resume launch that finishes its last stragglers.  Neither
+ * changes a result bit.  The first such launch on a stream allocates 6 MB of device scratch (cudaMalloc: one device
+ * synchronisation).  Captured launches (CUDA graphs) keep plain stream order.  See INTEGRATION.md section 4. */
 /* Same solve with PACKED outputs (the fast path: 3 x 128-bit stores per query instead of 13):
  *   out_q8  [n][8] float = q0..q6, pos_error
  *   out_aux4[n][4] float = final_pos xyz, then a 32-bit word (iterations | flags << 24)
