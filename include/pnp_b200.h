@@ -89,7 +89,7 @@ typedef struct PnpIkParams {
 #define PNP_KIN_SPEC_LANE 3    /* one query / env per lane, explicit-FMA specialised code (what AUTO picks for the
                                   waypoint and planner kernels and for small IK batches) */
 #define PNP_KIN_SPEC_PAIR 4    /* two queries / envs per lane on packed FFMA2/FMUL2/FADD2 (what AUTO picks for
-                                  FP32 IK batches of >= 4096 queries per SM on the specialised tree) */
+                                  FP32 IK batches of > 256 queries per SM on the specialised tree) */
 
 /* flags[] bits written by the IK kernels (IKResult.converged / .success, ik_solver.py:92-100) */
 #define PNP_IK_CONVERGED 1u
@@ -148,7 +148,7 @@ int pnp_ik_solve_f32(const float* targets, const float* q_init, int32_t q_init_s
 /* FP32 IK kernels evaluate sin/cos of the joint angles by table look-up with a one-term magic-number range reduction:
  * 1.8e-7 absolute inside +-2 pi (the joint range; a q_init outside the joint limits is fine), growing by 2.8e-8 per
  * radian beyond; the index arithmetic needs |q| < 3.2e3 rad.
- * Stream semantics of the FP32 solves on the build-time tree: two consecutive launches of >= 128 queries per SM on one
+ * Stream semantics of the FP32 solves on the build-time tree: two consecutive launches of > 128 queries per SM on one
  * stream with nothing between them overlap their drain / ramp (programmatic dependent launch) unless the second one reads
  * or overwrites memory of the first (the library compares the byte ranges and falls back to plain stream order); from
  * 16384 queries per SM up a launch is followed by a small resume launch that finishes its last stragglers.  Neither

@@ -507,11 +507,12 @@ int launch_ik_small(const pnp::IkArgs<float>& a, cudaStream_t st) {
 // FP32 on the specialised tree always runs the value-type arithmetic (ik_eval_v / ik_step_v: a batch gives
 // bit-identical results whichever kernel is picked).  AUTO / SPECIALIZED:
 //   n <= 128 queries per SM          ik_solve_small_kernel (latency bound: the launch lasts as long as its slowest query)
-//   n >= 4096 queries per SM         two queries per lane (packed FFMA2/FMUL2/FADD2)
+//   n > 256 queries per SM           two queries per lane (packed FFMA2/FMUL2/FADD2): measured faster than one per lane from
+//                                    2^16 queries up (0.071 vs 0.093 ms; 2^19: 0.167 vs 0.192 ms), slower at 2^15 (0.077 vs 0.071 ms)
 //   in between                       one query per lane with refill
 template <int kOut>
 int launch_ik_spec_f32(DeviceState* s, const pnp::IkArgs<float>& a, int kinematics, bool small, cudaStream_t st) {
-  const bool big = (long long)a.n >= (long long)s->sm_count * 4096;
+  const bool big = (long long)a.n > (long long)s->sm_count * pnp::IK_BLOCK * 2;
   if (kinematics == PNP_KIN_SPEC_PAIR || (kinematics != PNP_KIN_SPEC_LANE && big))
     return launch_ik_v<pnp::F2, kOut>(s, a, (long long)a.n <= (long long)s->sm_count * pnp::IK_BLOCK * 2, st);
   return launch_ik_v<float, kOut>(s, a, small, st);
