@@ -386,7 +386,9 @@ def move_ik_plan(q_start: torch.Tensor, target: torch.Tensor, params: PnpIkParam
     call with the same N / traj_cap / dtype, whose buffers are then reused (trajectory rows beyond traj_len
     keep their old contents); fresh trajectory storage is zero-filled.
 
-    Returns dict(traj[N,traj_cap,3], traj_len[N], q_final[N,7], n_solves[N], status[N])."""
+    Returns dict(traj[N,traj_cap,3], traj_len[N], q_final[N,7], n_solves[N], status[N]).  With ``order="auto"`` on float32
+    batches of >= 2^16 envs the call goes through pnp_move_ik_plan_sorted_f32 (inputs gathered in plan order) and the dict
+    also carries ``_scratch48``, the [N,12] int32 scratch of that call, so that ``out=`` reuses it as well."""
     lib = _lib.load()
     dt = q_start.dtype
     if dt not in (torch.float32, torch.float64):
