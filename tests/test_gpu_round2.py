@@ -374,3 +374,44 @@ def test_drain_handover_in_mixed_launch_sequences(tree):
             for f in fields:
                 assert torch.equal(getattr(r, f), want[f]), (rep, i, f)
             assert int(c[0]) == len(want["q"]) and int(c[1]) == int(want["converged"].sum()) and int(c[3]) == int(want["iterations"].long().sum()), (rep, i)
+
+
+def test_random_launch_sequences_on_two_streams(tree):
+    """Random sequences of IK solves of different sizes (the latency kernel, one / two queries per lane, with and without the
+    drain hand-over), q_init modes and kernels on two streams, nothing synchronised in between, now and then into the previous
+    launch's buffers: every launch returns what the same solve returns alone (tools/dev/dev_pdl_stress.py runs longer ones)."""
+    import random
+
+    dev = torch.device("cuda")
+    rng = random.Random(3)
+    sizes = [4096, 30_000, 60_000, 300_000, (1 << 20) + 3, 3_000_000]
+    inputs, ref = {}, {}
+    for n in sizes:
+        t = _targets(tree, n, seed=n % 977)
+        t[::173] = torch.tensor([2.5, 0.0, 0.5], device=dev)
+        inputs[n] = (t, (_neutral() + 0.1 * torch.randn((n, 7), device=dev)).contiguous())
+        for pq in (False, True):
+            r = engine.ik_solve(t, inputs[n][1] if pq else _neutral(), engine.ik_params(kinematics="spec_lane" if n > 20000 else "auto"))
+            torch.cuda.synchronize()
+            ref[(n, pq)] = (r.q.clone(), r.iterations.clone(), r.final_pos.clone())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(2):
+        got = []
+        for _ in range(16):
+            n, pq, si = rng.choice(sizes), rng.random() < 0.3, rng.randrange(2)
+            kin = rng.choice(["auto", "auto", "spec_pair", "spec_lane"]) if n > 40000 else "auto"
+            t, qi = inputs[n]
+            with torch.cuda.stream(streams[si]):
+                if rng.random() < 0.2 and got and got[-1] is not None and got[-1][0] == n and got[-1][4] == si:
+                    bufs = got[-1][3]          # into the previous launch's buffers: the library must serialise the two
+                    got[-1] = None
+                else:
+                    bufs = (torch.empty((n, 8), device=dev), torch.empty((n, 4), device=dev))
+                r = engine.ik_solve(t, qi if pq else _neutral(), engine.ik_params(kinematics=kin), out_q8=bufs[0], out_aux4=bufs[1])
+                got.append((n, pq, r, bufs, si))
+        torch.cuda.synchronize()
+        for g in got:
+            if g is not None:
+                n, pq, r, _, _ = g
+                q, it, fp = ref[(n, pq)]
+                assert torch.equal(r.q, q) and torch.equal(r.iterations, it) and torch.equal(r.final_pos, fp), (n, pq)
