@@ -411,30 +411,39 @@ __device__ __forceinline__ void ldg1_if(bool pred, const float* ptr, float& x) {
 // limit 0).  `it` is the lane's pass counter on entry (0 for a fresh query).  All 32 lanes must call.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void lane_solve(const IkConst<float>& k, const TrigV& trig, bool valid, int it, float (&q)[NJ],
-                                           const float (&tgt)[3], float (&pf)[3], float& n2f, int& iterations, bool& conv) {
+                                           const float (&q0)[NJ], const float (&tgt)[3], float (&pf)[3], float& n2f, int& iterations,
+                                           bool& conv) {
   const float thresh2 = k.pos_thresh * k.pos_thresh;
   bool done = !valid;
   conv = false;
   iterations = 0;
-  float pr_f[3] = {0.0f, 0.0f, 0.0f}, s0_f = 0.0f, c0_f = 1.0f;  // final position in joint 1's frame, and that joint's sin / cos
-  n2f = 0.0f;
   float tb[3];
   pnp_spec::spec_world_to_base_v<float>(tgt, tb);
+  float p[3], e[3], n2, J[21], s0, c0;  // of the last pass
   for (;; ++it) {
-    float p[3], e[3], n2, J[21], s0, c0;
     ik_eval_j1_v<float>(q, tb, trig, p, e, n2, J, s0, c0);
     const bool last = it >= k.max_iters;                       // loop ran out (ik_solver.py:57)
     const bool fin = !done && (last || n2 < thresh2);          // :61-64
     if (fin) {
       conv = !last;
       iterations = conv ? it + 1 : it;                         // :66 / :85
-      pr_f[0] = p[0]; pr_f[1] = p[1]; pr_f[2] = p[2]; s0_f = s0; c0_f = c0; n2f = n2;  // final_pos / final_error (:88-89)
     }
     done = done || fin;
     if (__all_sync(FULL, done)) break;
     ik_step_v<float>(q, J, e, k.damping, done ? 0.0f : k.step_limit);  // frozen once finished
   }
-  p_world_v<float>(pr_f, s0_f, c0_f, pf);
+  // final_pos / final_error (:88-89).  A finished lane keeps its q (step limit 0) and every pass recomputes the same p / n2
+  // from it, so the values of the LAST pass are every lane's final ones - no per-pass copies.  One exception: a query that
+  // finished on its FIRST pass returns q (q0: the state it entered with) untouched even outside the joint limits, where the
+  // limit clip of the frozen step has moved it: those lanes get their q back and the warp evaluates once more (rare).
+  const bool first_pass = valid && iterations == (conv ? 1 : 0);
+  if (__any_sync(FULL, first_pass)) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) q[i] = first_pass ? q0[i] : q[i];
+    ik_eval_j1_v<float>(q, tb, trig, p, e, n2, J, s0, c0);
+  }
+  n2f = n2;
+  p_world_v<float>(p, s0, c0, pf);
 }
 
 // the result record(s) of one query in the layout kOut (see IK_OUT_*)
@@ -848,12 +857,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       for (int i = 0; i < 3; ++i) tl[i] = a.targets[(size_t)id * 3u + i];
       bool conv;
       int iterations;
-      lane_solve(a.k, trig, valid, it0, ql, tl, pf, n2f, iterations, conv);
+      lane_solve(a.k, trig, valid, it0, ql, q0, tl, pf, n2f, iterations, conv);  // (a first-pass finish gets q0 back in there)
       if (valid) {
-        if (iterations == (conv ? 1 : 0)) {  // parked before its first pass and finished on it: q_init untouched
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) ql[i] = q0[i];
-        }
         store_lane_result<kOut>(a, id, ql, pf, n2f, iterations, conv);
         c_n += 1u;
         c_conv += conv ? 1u : 0u;
@@ -891,15 +896,15 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<f
   const unsigned id = blockIdx.x * 32u + lane;
   const bool valid = id < a.n;
   const unsigned ld = valid ? id : 0u;
-  float q[NJ], tgt[3], pf[3], n2f;
+  float q[NJ], q0[NJ], tgt[3], pf[3], n2f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) tgt[i] = a.targets[(size_t)ld * 3u + i];
   const float* qi = kBcast ? a.q_init : a.q_init + (size_t)ld * NJ;
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) q[i] = qi[i];
+  for (int i = 0; i < NJ; ++i) q[i] = q0[i] = qi[i];
   bool conv;
   int iterations;
-  lane_solve(a.k, trig, valid, 0, q, tgt, pf, n2f, iterations, conv);
+  lane_solve(a.k, trig, valid, 0, q, q0, tgt, pf, n2f, iterations, conv);  // (a first-pass finish gets q_init back in there)
   if (a.counters) {  // whole warp (lanes past the end of the batch add zeros)
     const unsigned long long w_n = warp_sum((unsigned long long)(valid ? 1u : 0u)),
                              w_conv = warp_sum((unsigned long long)((valid && conv) ? 1u : 0u)),
@@ -912,10 +917,6 @@ __global__ void __launch_bounds__(IK_BLOCK) ik_solve_small_kernel(const IkArgs<f
     }
   }
   if (!valid) return;
-  if (iterations == (conv ? 1 : 0)) {  // finished on the first pass: q_init comes back untouched (see ik_solve_v_kernel)
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) q[i] = qi[i];
-  }
   store_lane_result<kOut>(a, id, q, pf, n2f, iterations, conv);
 }
 
