@@ -367,7 +367,10 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     static const int env_guided = env_int("PNP_IK_GUIDED", 1);
     args.guided = (!small && env_guided != 0) ? (unsigned)(warps * 2) : 0u;
   }
-  auto kernel = a.q_init_stride == 0 ? pnp::ik_solve_v_kernel<V, kOut, true> : pnp::ik_solve_v_kernel<V, kOut, false>;
+  // (no counters asked for: the instantiation without the counter updates in its store block)
+  const bool bc = a.q_init_stride == 0, cnt = a.counters != nullptr;
+  auto kernel = bc ? (cnt ? pnp::ik_solve_v_kernel<V, kOut, true, false, true> : pnp::ik_solve_v_kernel<V, kOut, true, false, false>)
+                   : (cnt ? pnp::ik_solve_v_kernel<V, kOut, false, false, true> : pnp::ik_solve_v_kernel<V, kOut, false, false, false>);
   static const int env_pdl = env_int("PNP_IK_PDL", 1);  // 0: every launch zeroes its ticket with a memset node (measurements)
   static const int env_handover = env_int("PNP_IK_HANDOVER", 1);  // 0: stragglers finish inside their blocks (measurements)
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -472,7 +475,8 @@ int launch_ik_v(DeviceState* s, const pnp::IkArgs<float>& a, bool small, cudaStr
     r.pdl = pnp::IK_PDL_OFF;
     r.zero_next[0] = scn + 1; r.zero_next[1] = scn + 2; r.zero_next[2] = scn + 3;
     r.chunk = 32; r.flush_min = 1; r.solo_warp = 0; r.tail = 0; r.guided = 0;
-    auto resume = a.q_init_stride == 0 ? pnp::ik_solve_v_kernel<float, kOut, true, true> : pnp::ik_solve_v_kernel<float, kOut, false, true>;
+    auto resume = bc ? (cnt ? pnp::ik_solve_v_kernel<float, kOut, true, true, true> : pnp::ik_solve_v_kernel<float, kOut, true, true, false>)
+                     : (cnt ? pnp::ik_solve_v_kernel<float, kOut, false, true, true> : pnp::ik_solve_v_kernel<float, kOut, false, true, false>);
     cfg.gridDim = dim3((unsigned)s->sm_count);
     e = cudaLaunchKernelEx(&cfg, resume, r);
     ++g_launches;

@@ -522,7 +522,9 @@ __device__ __forceinline__ float2 pair_of(const F2& v) { return v.v; }
 // queries one per lane from exactly the state they were parked in (same arithmetic: no result bit depends on where a query
 // finishes) while the next pair launch already runs.  Chain per stream: pair k -> resume k -> pair k+1 -> resume k+1, every
 // edge a programmatic one; resume k waits for pair k to complete before it reads the list, and only then lets pair k+1 start.
-template <typename V, int kOut, bool kBcast, bool kResume = false>
+// kCount = false (the caller passed no counters): the per-slot counter updates drop out of the store block - 8 instructions of
+// 158, two of them 64-bit adds whose carries queue on the FMA pipe: 2.351 -> 2.312 ms for 2^24 queries (A/B on one box).
+template <typename V, int kOut, bool kBcast, bool kResume = false, bool kCount = true>
 __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOCKS : 1) ik_solve_v_kernel(const IkArgs<float> a) {
   constexpr int S = Slots<V>::kN;
   static_assert(!kResume || S == 1, "the resume kernel runs one query per lane");
@@ -826,9 +828,11 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
             if (a.iters) a.iters[id] = iterations;
             if (a.flags) a.flags[id] = (uint8_t)fl;
           }
-          c_n += f ? 1u : 0u;
-          c_conv += (f && conv) ? 1u : 0u;
-          c_iter += f ? (unsigned)iterations : 0u;
+          if constexpr (kCount) {
+            c_n += f ? 1u : 0u;
+            c_conv += (f && conv) ? 1u : 0u;
+            c_iter += f ? (unsigned)iterations : 0u;
+          }
           st[k] = f ? (int)IDLE : st[k];
         }
       };
@@ -866,7 +870,8 @@ __global__ void __launch_bounds__(IK_BLOCK, Slots<V>::kN == 2 ? IK_PAIR_MIN_BLOC
       }
     }
   }
-  if (a.counters) {
+  if (a.counters) {  // (kept in the kCount = false instantiation, which only runs with a.counters == nullptr: compiled out, the same
+                     //  kernel was 2 % SLOWER - 2.364 vs 2.312 ms - for no reason visible in the source; A/B three ways on one box)
     const unsigned long long w_n = warp_sum((unsigned long long)c_n), w_conv = warp_sum((unsigned long long)c_conv),
                              w_iter = warp_sum(c_iter);
     if (lane == 0) {
